@@ -1,0 +1,188 @@
+/* libssw -- C ABI of the B200-native embed / extract / similarity hot path of
+ * iwanders/spread_spectrum_watermarking (Cox et al. 1997).
+ *
+ * This is the drop-in boundary: every entry point mirrors one item of the reference crate's public
+ * Rust API (paths below are relative to the reference repository).  Plain pointers and sizes only.
+ * All arithmetic runs in hand-written sm_100a CUDA kernels; there is NO CPU fallback -- without a
+ * CUDA device `ssw_ctx_create` fails and nothing else can be called.
+ *
+ * Conventions
+ *   - every function returns SSW_OK (0) or a negative ssw_status; `ssw_last_error()` gives the text
+ *     (thread-local).  The reference panics where these return an error (INTEGRATION.md shows the
+ *     Rust shim turning non-zero into panic!).
+ *   - images are row-major, interleaved RGB, 8-bit or f32 in [0,1] (image::DynamicImage::into_rgb8 /
+ *     into_rgb32f layout).  "host" pointers are ordinary (ideally pinned) host memory, "_dev"
+ *     variants take device pointers on the context's device and never synchronise the host.
+ *   - a context is bound to one device and one CUDA stream; it is not thread-safe (the reference's
+ *     Writer/Reader are !Send + !Sync: src/algorithm.rs:286-291,441-445).
+ */
+#ifndef SSW_H_
+#define SSW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ssw_status {
+    SSW_OK = 0,
+    SSW_ERR_INVALID = -1,     /* bad argument (the reference would panic / fail an assert)      */
+    SSW_ERR_CUDA = -2,        /* CUDA runtime error, or no CUDA device                          */
+    SSW_ERR_UNSUPPORTED = -3, /* Custom closures, line lengths the FFT planner cannot handle    */
+    SSW_ERR_STATE = -4        /* e.g. extract called on a derived reader (reference: unwrap())  */
+} ssw_status;
+
+/* Insertion::Option1/2/3 and Extraction::Option1/2/3 -- src/algorithm.rs:68-78,115-125 */
+enum { SSW_METHOD_OPTION1 = 1, SSW_METHOD_OPTION2 = 2, SSW_METHOD_OPTION3 = 3 };
+/* OrderingMethod::{Energy, EnergyOrthogonal, Legacy} -- src/algorithm.rs:143-152 */
+enum { SSW_ORDER_ENERGY = 0, SSW_ORDER_ENERGY_ORTHOGONAL = 1, SSW_ORDER_LEGACY = 2 };
+/* dct2d::Type -- src/dct2d.rs:71-79 */
+enum { SSW_DCT2 = 0, SSW_DCT2_ORTHOGONAL = 1, SSW_DCT3 = 2 };
+
+/* WriteConfig / ReadConfig -- src/algorithm.rs:99-112,127-140.  Defaults: {2, 0.1f, 0}.
+ * Insertion::Custom / Extraction::Custom / OrderingMethod::Custom (host closures) are rejected. */
+typedef struct ssw_config {
+    int32_t method;   /* SSW_METHOD_OPTION{1,2,3}                  */
+    float alpha;      /* the scaling passed to OptionN(alpha)      */
+    int32_t ordering; /* SSW_ORDER_*                               */
+} ssw_config;
+
+typedef struct ssw_ctx ssw_ctx;
+typedef struct ssw_writer ssw_writer;
+typedef struct ssw_reader ssw_reader;
+typedef struct ssw_bank ssw_bank;
+
+const char* ssw_last_error(void);
+const char* ssw_version(void);
+
+/* ---- context: replaces rustdct::DctPlanner (src/algorithm.rs:309,477): plan + twiddle cache,
+ *      workspace, stream.  `stream` is a cudaStream_t (NULL = create an own non-blocking stream). */
+int ssw_ctx_create(int device, ssw_ctx** out);
+int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out);
+int ssw_ctx_destroy(ssw_ctx* ctx);
+int ssw_ctx_synchronize(ssw_ctx* ctx);
+void* ssw_ctx_stream(ssw_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
+uint64_t ssw_ctx_launch_count(ssw_ctx* ctx);
+/* tuning knobs: line pairs per CTA tile for the row / column passes (0 = automatic) */
+int ssw_ctx_set_tiling(ssw_ctx* ctx, int row_pairs, int col_pairs);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
+int ssw_host_alloc(size_t bytes, void** out);
+int ssw_host_free(void* p);
+
+/* ---- dct2d::dct2_2d(planner, type, width, height, data) -- src/dct2d.rs:83-219.
+ *      `data` is [height][width] f32, transformed in place (host or device pointer). */
+int ssw_dct2_2d(ssw_ctx* ctx, int type, uint32_t width, uint32_t height, float* data_host);
+int ssw_dct2_2d_dev(ssw_ctx* ctx, int type, uint32_t width, uint32_t height, float* data_dev);
+
+/* ---- yiq: From<&Rgb32FImage> for YIQ32FImage / From<&YIQ32FImage> for Rgb32FImage
+ *      -- src/yiq.rs:177-197 (planes are separate [h][w] f32 buffers, src/yiq.rs:58-62). */
+int ssw_rgb32f_to_yiq(ssw_ctx* ctx, const float* rgb_host, uint32_t width, uint32_t height,
+                      float* y_host, float* i_host, float* q_host);
+int ssw_yiq_to_rgb32f(ssw_ctx* ctx, const float* y_host, const float* i_host, const float* q_host,
+                      uint32_t width, uint32_t height, float* rgb_host);
+
+/* ---- Writer -- src/algorithm.rs:286-433 */
+/* Writer::new(image, config): upload, RGB->Y, forward 2-D DCT (:295-316).  The coefficient
+ * ordering (:324-327) is evaluated lazily at embed time for the mark length actually needed. */
+int ssw_writer_new_rgb8(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, uint32_t height,
+                        const ssw_config* cfg, ssw_writer** out);
+int ssw_writer_new_rgb32f(ssw_ctx* ctx, const float* rgb_host, uint32_t width, uint32_t height,
+                          const ssw_config* cfg, ssw_writer** out);
+int ssw_writer_new_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width, uint32_t height,
+                            const ssw_config* cfg, ssw_writer** out);
+/* Writer::embed(&mut self, marks) (:348-352, embed_watermark :382-410).  Marks longer than
+ * width*height-1 are truncated like the reference's zip (:396).  Several marks: deltas against the
+ * original coefficients are summed (:399-408). */
+int ssw_writer_embed(ssw_writer* w, const float* const* marks_host, const size_t* lens, size_t n_marks);
+/* Writer::coefficient_image() (:319-321): copy of the [h][w] coefficient plane. */
+int ssw_writer_coefficients(ssw_writer* w, float* out_host);
+/* the ordered coefficient indices (row-major r*w+c, DC excluded) the embedding used / would use:
+ * first n entries of obtain_indices_by_function (:200-210). */
+int ssw_writer_indices(ssw_writer* w, uint64_t* out_host, size_t n);
+/* Writer::result(self) (:361-379) [+ DynamicImage::into_rgb8()]: inverse DCT, YIQ->RGB, download.
+ * Like the reference this consumes the coefficients; call once, then destroy the writer. */
+int ssw_writer_result_rgb8(ssw_writer* w, uint8_t* out_host);
+int ssw_writer_result_rgb32f(ssw_writer* w, float* out_host);
+int ssw_writer_result_rgb8_dev(ssw_writer* w, uint8_t* out_dev);
+int ssw_writer_destroy(ssw_writer* w);
+
+/* ---- Reader / ReaderDerived -- src/algorithm.rs:435-594 */
+int ssw_reader_base_rgb8(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, uint32_t height,
+                         const ssw_config* cfg, ssw_reader** out);          /* Reader::base    :462 */
+int ssw_reader_base_rgb32f(ssw_ctx* ctx, const float* rgb_host, uint32_t width, uint32_t height,
+                           const ssw_config* cfg, ssw_reader** out);
+int ssw_reader_derived_rgb8(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, uint32_t height,
+                            ssw_reader** out);                              /* Reader::derived :469 */
+int ssw_reader_derived_rgb32f(ssw_ctx* ctx, const float* rgb_host, uint32_t width, uint32_t height,
+                              ssw_reader** out);
+int ssw_reader_base_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width, uint32_t height,
+                             const ssw_config* cfg, ssw_reader** out);
+int ssw_reader_derived_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width, uint32_t height,
+                                ssw_reader** out);
+/* Reader::extract(&self, &derived, extracted) (:529-562).  Errors (reference panics): `base` is a
+ * derived reader (:530 unwrap), sizes differ (:550-552), n >= width*height (:553-555). */
+int ssw_reader_extract(ssw_reader* base, ssw_reader* derived, float* out_host, size_t n);
+int ssw_reader_extract_dev(ssw_reader* base, ssw_reader* derived, float* out_dev, size_t n);
+int ssw_reader_coefficients(ssw_reader* r, float* out_host);                /* :502-504 */
+/* Reader::indices() (:506-508) -- first n ordered indices (the reference returns all w*h-1). */
+int ssw_reader_indices(ssw_reader* base, uint64_t* out_host, size_t n);
+int ssw_reader_destroy(ssw_reader* r);
+
+/* ---- Tester::similarity -- src/algorithm.rs:696-714.  One kernel thread walks one mark in the
+ *      reference's sequential f32 order, so the result is bit-identical to the reference loop. */
+int ssw_similarity(ssw_ctx* ctx, const float* extracted_host, const float* mark_host, size_t n, float* out);
+/* bank of stored marks [n_marks][n] resident on the device (README.md:62 "test against any number
+ * of marks"); out is [n_extracted][n_marks]. */
+int ssw_bank_create(ssw_ctx* ctx, const float* marks_host, size_t n_marks, size_t n, ssw_bank** out);
+int ssw_bank_create_normal(ssw_ctx* ctx, uint64_t seed, size_t n_marks, size_t n, ssw_bank** out);
+int ssw_bank_row(ssw_bank* bank, size_t index, float* out_host);
+int ssw_bank_similarity(ssw_bank* bank, const float* extracted_host, size_t n_extracted, float* out_host);
+int ssw_bank_similarity_dev(ssw_bank* bank, const float* extracted_dev, size_t n_extracted, float* out_dev);
+int ssw_bank_destroy(ssw_bank* bank);
+
+/* ---- MarkBuf::generate_normal(length) -- src/algorithm.rs:619-626 (unseeded thread_rng there;
+ *      seed == 0 draws the seed from the OS, anything else is reproducible). */
+int ssw_mark_generate_normal(ssw_ctx* ctx, uint64_t seed, size_t n, float* out_host);
+
+/* ---- fused device-resident pipelines (bench configs 2/3; no host synchronisation inside) ----
+ * embed : Writer::new(img,cfg).mark(&[mark]).into_rgb8() for `batch` images of equal size.
+ * extract: Reader::base + Reader::derived + extract (+ Tester::similarity if sim_dev != NULL).
+ * rgb buffers are [batch][h][w][3] u8, marks [batch][n] f32, extracted [batch][n], sim [batch]. */
+int ssw_embed_batch_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width, uint32_t height,
+                             uint32_t batch, const ssw_config* cfg, const float* marks_dev, size_t n,
+                             uint8_t* out_rgb_dev);
+int ssw_extract_batch_rgb8_dev(ssw_ctx* ctx, const uint8_t* base_rgb_dev, const uint8_t* derived_rgb_dev,
+                               uint32_t width, uint32_t height, uint32_t batch, const ssw_config* cfg,
+                               size_t n, float* extracted_dev, const float* marks_dev, float* sim_dev);
+/* host-buffer versions of the same (pinned memory recommended): the end-to-end API path */
+int ssw_embed_batch_rgb8(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, uint32_t height,
+                         uint32_t batch, const ssw_config* cfg, const float* marks_host, size_t n,
+                         uint8_t* out_rgb_host);
+int ssw_extract_batch_rgb8(ssw_ctx* ctx, const uint8_t* base_rgb_host, const uint8_t* derived_rgb_host,
+                           uint32_t width, uint32_t height, uint32_t batch, const ssw_config* cfg,
+                           size_t n, float* extracted_host, const float* marks_host, float* sim_host);
+/* status of the last fused call: 0 ok, 1 = top-k candidate overflow (degenerate spectrum; the call
+ * already re-ran the exact general path), checked after the stream is synchronised. */
+int ssw_ctx_last_topk_fallbacks(ssw_ctx* ctx);
+
+/* ---- synthetic frames for the benchmark (SURVEY.md section 8(d) generator, integer only) */
+int ssw_synth_frame_rgb8_dev(ssw_ctx* ctx, uint32_t width, uint32_t height, uint64_t seed,
+                             uint32_t first_image, uint32_t n_images, uint8_t* out_dev);
+
+/* ---- per-stage timing hooks for bench.py / profiling: run one stage of the pipeline on
+ *      device-resident data (used to attribute time to kernels with CUDA events). */
+int ssw_stage_forward_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width, uint32_t height,
+                               uint32_t batch, float* plane_dev);
+int ssw_stage_topk_dev(ssw_ctx* ctx, const float* plane_dev, uint32_t width, uint32_t height,
+                       uint32_t batch, int ordering, size_t k, uint32_t* idx_dev);
+int ssw_stage_inverse_rgb8_dev(ssw_ctx* ctx, float* plane_dev, const uint8_t* rgb_src_dev,
+                               uint32_t width, uint32_t height, uint32_t batch, uint8_t* out_rgb_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSW_H_ */

@@ -1,0 +1,217 @@
+// Embedding scatter, extraction gather, similarity, N(0,1) marks, planar YIQ and synthetic frames.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "color.cuh"
+
+namespace ssw {
+
+// ------------------------------------------------------------------------------------------------
+// Writer::embed_watermark -- /root/reference/src/algorithm.rs:382-410, insert functions :414-432.
+// One thread per rank i: coefficient idx[i] is modulated by mark value i.  No FMA contraction so the
+// result is bit-identical to the reference given the same coefficient (Option 3 up to expf rounding).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float insert_fn(int method, float alpha, float orig, float w) {
+    if (method == 1) return __fadd_rn(orig, __fmul_rn(alpha, w));
+    if (method == 2) return __fmul_rn(orig, __fadd_rn(1.0f, __fmul_rn(alpha, w)));
+    return __fmul_rn(orig, expf(__fmul_rn(alpha, w)));
+}
+
+// marks: [batch][n_marks][mark_stride] f32, lens: [n_marks] (NULL = all k)
+__global__ void embed_scatter_kernel(float* __restrict__ planes, long long plane_stride,
+                                     const unsigned* __restrict__ idx, long long idx_stride, unsigned k,
+                                     const float* __restrict__ marks, long long mark_stride, int n_marks,
+                                     const unsigned* __restrict__ lens, int method, float alpha) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned img = blockIdx.y;
+    if (i >= k) return;
+    float* plane = planes + (long long)img * plane_stride;
+    const unsigned p = idx[(long long)img * idx_stride + i];
+    const float* mk0 = marks + (long long)img * n_marks * mark_stride;
+    const float orig = plane[p];
+    if (n_marks == 1) {
+        if (!lens || i < lens[0]) plane[p] = insert_fn(method, alpha, orig, mk0[i]);  // :394-398
+        return;
+    }
+    float c = orig;  // :399-408: deltas against the original coefficient, summed in mark order
+    for (int m = 0; m < n_marks; ++m) {
+        if (lens && i >= lens[m]) continue;
+        const float updated = insert_fn(method, alpha, orig, mk0[(long long)m * mark_stride + i]);
+        c = __fadd_rn(c, __fsub_rn(updated, orig));
+    }
+    plane[p] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reader::extract_watermark -- src/algorithm.rs:543-562, extract functions :566-593
+// ------------------------------------------------------------------------------------------------
+__global__ void extract_gather_kernel(const float* __restrict__ base, const float* __restrict__ derived,
+                                      long long plane_stride, const unsigned* __restrict__ idx,
+                                      long long idx_stride, unsigned n, int method, float alpha,
+                                      float* __restrict__ out, long long out_stride) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned img = blockIdx.y;
+    if (i >= n) return;
+    const unsigned p = idx[(long long)img * idx_stride + i];
+    const float b = base[(long long)img * plane_stride + p];
+    const float d = derived[(long long)img * plane_stride + p];
+    float r;
+    if (method == 1) r = __fdiv_rn(__fsub_rn(d, b), alpha);
+    else if (method == 2) r = __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
+    else r = __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
+    out[(long long)img * out_stride + i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tester::similarity -- src/algorithm.rs:696-714, against a bank of marks [n_marks][n].
+// One thread per stored mark walks the vectors in the reference's sequential order with separate
+// f32 multiply and add, so every score is bit-identical to the reference loop.  The bank tile is
+// staged through shared memory so global reads stay coalesced (each mark row is contiguous).
+//   pair mode (pair_stride != 0): mark m is compared with extracted vector m (batched 1:1).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSimMarks = 128;  // marks (threads) per CTA
+constexpr int kSimChunk = 32;   // elements staged per step
+
+__global__ void __launch_bounds__(kSimMarks)
+similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned n,
+                       const float* __restrict__ extracted, long long ext_stride, int pair_mode,
+                       float* __restrict__ out, long long out_stride) {
+    __shared__ float tile[kSimMarks][kSimChunk + 1];
+    __shared__ float ex[kSimChunk];
+    const size_t m0 = (size_t)blockIdx.x * kSimMarks;
+    const unsigned e = blockIdx.y;  // extracted vector (bank mode)
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    float nom = 0.f, den = 0.f;
+    const float* ext = extracted + (pair_mode ? 0 : (long long)e * ext_stride);
+    for (unsigned j0 = 0; j0 < n; j0 += kSimChunk) {
+        const unsigned len = min((unsigned)kSimChunk, n - j0);
+        // each warp stages rows warp, warp+4, ... : 32 consecutive floats of one mark per load
+        for (int r = warp; r < kSimMarks; r += kSimMarks / 32) {
+            const size_t m = m0 + r;
+            float v = 0.f;
+            if (m < n_marks && (unsigned)lane < len) v = __ldg(bank + m * n + j0 + lane);
+            tile[r][lane] = v;
+        }
+        if (!pair_mode && t < (int)len) ex[t] = __ldg(ext + j0 + t);
+        __syncthreads();
+        if (pair_mode) {
+            const size_t m = m0 + t;
+            if (m < n_marks) {
+                const float* xe = extracted + (long long)m * ext_stride + j0;
+                for (unsigned j = 0; j < len; ++j) {
+                    const float x = __ldg(xe + j);
+                    nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
+                    den = __fadd_rn(den, __fmul_rn(x, x));
+                }
+            }
+        } else {
+#pragma unroll 8
+            for (unsigned j = 0; j < len; ++j) {
+                const float x = ex[j];
+                nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
+                den = __fadd_rn(den, __fmul_rn(x, x));
+            }
+        }
+        __syncthreads();
+    }
+    const size_t m = m0 + t;
+    if (m < n_marks) out[(long long)(pair_mode ? 0 : e) * out_stride + m] = __fdiv_rn(nom, __fsqrt_rn(den));
+}
+
+// ------------------------------------------------------------------------------------------------
+// MarkBuf::generate_normal -- src/algorithm.rs:619-626 (distributional parity only: the reference
+// draws from the OS-seeded thread_rng).  Philox4x32-10 counter RNG + Box-Muller.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint4& ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+}
+
+__global__ void normal_fill_kernel(float* __restrict__ out, size_t n, unsigned long long seed,
+                                   unsigned long long stream_offset) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
+    if (q * 4 >= n) return;
+    const unsigned long long c = q + stream_offset;
+    uint4 ctr = make_uint4((unsigned)c, (unsigned)(c >> 32), 0u, 0u);
+    philox4x32_10(ctr, make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float k24 = 5.9604644775390625e-8f;  // 2^-24
+    const float u0 = ((float)(ctr.x >> 8) + 0.5f) * k24, u1 = ((float)(ctr.y >> 8) + 0.5f) * k24;
+    const float u2 = ((float)(ctr.z >> 8) + 0.5f) * k24, u3 = ((float)(ctr.w >> 8) + 0.5f) * k24;
+    const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    const float v[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+    for (int j = 0; j < 4; ++j)
+        if (q * 4 + j < n) out[q * 4 + j] = v[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// planar YIQ <-> interleaved RGB32F -- src/yiq.rs:177-197 (stand-alone form of the fused passes)
+// ------------------------------------------------------------------------------------------------
+__global__ void rgb32f_to_yiq_kernel(const float* __restrict__ rgb, size_t npix, float* __restrict__ y,
+                                     float* __restrict__ i, float* __restrict__ q) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const float r = rgb[3 * p], g = rgb[3 * p + 1], b = rgb[3 * p + 2];
+    y[p] = rgb_to_y(r, g, b);
+    i[p] = rgb_to_i(r, g, b);
+    q[p] = rgb_to_q(r, g, b);
+}
+
+__global__ void yiq_to_rgb32f_kernel(const float* __restrict__ y, const float* __restrict__ i,
+                                     const float* __restrict__ q, size_t npix, float* __restrict__ rgb) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float r, g, b;
+    yiq_to_rgb(y[p], i[p], q[p], r, g, b);
+    rgb[3 * p] = r; rgb[3 * p + 1] = g; rgb[3 * p + 2] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic natural-image-like frames; bit-identical to oracle synth_frame()
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long sm64(unsigned long long x) {
+    unsigned long long z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void synth_frame_kernel(unsigned char* __restrict__ out, unsigned w, unsigned h,
+                                   unsigned long long seed, unsigned first_image) {
+    const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned y = blockIdx.y;
+    const unsigned img = blockIdx.z;
+    if (x >= w) return;
+    const unsigned long long base = seed ^ ((unsigned long long)(first_image + img) * 0x9E3779B97F4A7C15ull);
+    unsigned char* o = out + ((size_t)img * h * w + (size_t)y * w + x) * 3;
+    for (unsigned c = 0; c < 3; ++c) {
+        unsigned long long acc = 0;
+        for (unsigned oct = 2; oct <= 8; ++oct) {
+            const unsigned long long s = 1ull << oct;
+            const unsigned long long X = x >> oct, Y = y >> oct, fx = x & (s - 1), fy = y & (s - 1);
+            const unsigned long long tag = base ^ ((unsigned long long)oct << 58) ^ ((unsigned long long)c << 56);
+            const unsigned long long l00 = sm64(tag ^ (Y << 28) ^ X) >> 56;
+            const unsigned long long l10 = sm64(tag ^ (Y << 28) ^ (X + 1)) >> 56;
+            const unsigned long long l01 = sm64(tag ^ ((Y + 1) << 28) ^ X) >> 56;
+            const unsigned long long l11 = sm64(tag ^ ((Y + 1) << 28) ^ (X + 1)) >> 56;
+            const unsigned long long top = l00 * (s - fx) + l10 * fx, bot = l01 * (s - fx) + l11 * fx;
+            acc += ((top * (s - fy) + bot * fy) >> (2 * oct)) << oct;
+        }
+        const long long noise = (long long)(sm64(base ^ 0xABCDEFull ^ ((unsigned long long)c << 56) ^ ((unsigned long long)y << 28) ^ x) >> 61);
+        long long v = (long long)(acc / 508ull) + noise - 4;
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        o[c] = (unsigned char)v;
+    }
+}
+
+}  // namespace ssw

@@ -1,0 +1,1105 @@
+// libssw: C ABI over the sm_100a kernels (see include/ssw.h for the reference items each entry
+// point mirrors).  Host orchestration only -- no arithmetic of the hot path runs on the CPU.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/ssw.h"
+#include "dct_kernels.cuh"
+#include "mark_kernels.cuh"
+#include "select_kernels.cuh"
+#include "select_general.cuh"
+
+using namespace ssw;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SSW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+#define CKS(call)                                                                                  \
+    do {                                                                                           \
+        int s_ = (call);                                                                           \
+        if (s_ != SSW_OK) return s_;                                                               \
+    } while (0)
+
+extern "C" const char* ssw_last_error(void) { return g_err.c_str(); }
+extern "C" const char* ssw_version(void) { return "ssw-b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DevPlan {
+    DctPlanHost host;
+    DctPlanDev dev;
+    void* tables = nullptr;
+};
+
+struct ssw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::map<int, std::unique_ptr<DevPlan>> plans;
+    std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
+    TopkScratch ts{};
+    unsigned ts_batch = 0;
+    GeneralSelect general;
+    uint64_t launches = 0;
+    int row_pairs = 0, col_pairs = 0;
+    int sm_count = 148;
+    int max_smem = 227 * 1024;
+    unsigned* h_flag = nullptr;  // pinned
+    int last_fallbacks = 0;
+    size_t chunk_bytes = 96u << 20;  // planes of one fused sub-batch are sized to stay L2-resident
+};
+
+static int ctx_bind(ssw_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    return SSW_OK;
+}
+
+extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out) {
+    if (!out) return fail(SSW_ERR_INVALID, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SSW_ERR_CUDA, std::string("no CUDA device available (libssw has no CPU path): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SSW_ERR_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SSW_ERR_CUDA, "libssw is built for sm_100a (B200) only; found compute capability " +
+                                      std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    auto c = std::make_unique<ssw_ctx>();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CK(cudaHostAlloc((void**)&c->h_flag, 64, cudaHostAllocDefault));
+    if (const char* s = getenv("SSW_ROW_PAIRS")) c->row_pairs = atoi(s);
+    if (const char* s = getenv("SSW_COL_PAIRS")) c->col_pairs = atoi(s);
+    if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
+    *out = c.release();
+    return SSW_OK;
+}
+
+extern "C" int ssw_ctx_create(int device, ssw_ctx** out) { return ssw_ctx_create_on_stream(device, nullptr, out); }
+
+static void topk_scratch_free(ssw_ctx* c) {
+    if (!c->ts_batch) return;
+    cudaFree(c->ts.hist); cudaFree(c->ts.ticket); cudaFree(c->ts.sel_bin);
+    cudaFree(c->ts.cand_count); cudaFree(c->ts.cand); cudaFree(c->ts.overflow);
+    c->ts = TopkScratch{};
+    c->ts_batch = 0;
+}
+
+extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
+    if (!c) return SSW_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->plans) cudaFree(kv.second->tables);
+    topk_scratch_free(c);
+    c->general.release();
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SSW_OK;
+}
+
+extern "C" int ssw_ctx_synchronize(ssw_ctx* c) {
+    if (!c) return fail(SSW_ERR_INVALID, "ctx is NULL");
+    CKS(ctx_bind(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+extern "C" void* ssw_ctx_stream(ssw_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" uint64_t ssw_ctx_launch_count(ssw_ctx* c) { return c ? c->launches : 0; }
+extern "C" int ssw_ctx_set_tiling(ssw_ctx* c, int row_pairs, int col_pairs) {
+    if (!c || row_pairs < 0 || col_pairs < 0) return fail(SSW_ERR_INVALID, "bad tiling");
+    c->row_pairs = row_pairs;
+    c->col_pairs = col_pairs;
+    return SSW_OK;
+}
+
+extern "C" int ssw_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(SSW_ERR_INVALID, "out is NULL");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SSW_OK;
+}
+extern "C" int ssw_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------
+static int get_plan(ssw_ctx* c, int n, const DevPlan** out) {
+    auto it = c->plans.find(n);
+    if (it != c->plans.end()) { *out = it->second.get(); return SSW_OK; }
+    auto p = std::make_unique<DevPlan>();
+    p->host = make_dct_plan(n);
+    if (!p->host.error.empty()) return fail(SSW_ERR_UNSUPPORTED, p->host.error);
+    const DctPlanHost& h = p->host;
+    if ((size_t)h.npad * sizeof(cplx) > (size_t)c->max_smem)
+        return fail(SSW_ERR_UNSUPPORTED, "line length " + std::to_string(n) + " does not fit shared memory");
+    const size_t b_tw = h.stage_tw.size() * sizeof(float), b_wn = h.wn.size() * sizeof(float),
+                 b_t4 = h.t4.size() * sizeof(float);
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    CK(cudaMalloc(&p->tables, al(b_tw) + al(b_wn) + al(b_t4) + 256));
+    char* base = (char*)p->tables;
+    if (b_tw) CK(cudaMemcpy(base, h.stage_tw.data(), b_tw, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(base + al(b_tw), h.wn.data(), b_wn, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(base + al(b_tw) + al(b_wn), h.t4.data(), b_t4, cudaMemcpyHostToDevice));
+    DctPlanDev& d = p->dev;
+    std::memset(&d, 0, sizeof(d));
+    d.n = h.n; d.npad = h.npad; d.tp = h.tp; d.nstages = h.nstages;
+    for (int i = 0; i < h.nstages; ++i) {
+        d.stages[i] = h.stages[i];
+        d.ns_magic[i] = h.stages[i].ns > 1 ? (unsigned)((1ull << 32) / (unsigned)h.stages[i].ns + 1) : 0u;
+    }
+    d.stage_tw = (const cplx*)base;
+    d.wn = (const cplx*)(base + al(b_tw));
+    d.t4 = (const cplx*)(base + al(b_tw) + al(b_wn));
+    *out = p.get();
+    c->plans[n] = std::move(p);
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// line-pass launches
+// ------------------------------------------------------------------------------------------------
+struct Tiling { int P, G, threads; size_t smem; };
+
+static int pick_tiling(ssw_ctx* c, const DctPlanDev& pl, bool column, int lines, Tiling* t) {
+    const size_t pair_bytes = (size_t)pl.npad * sizeof(cplx);
+    int G = std::max(1, 256 / pl.tp);
+    int P = column ? (c->col_pairs ? c->col_pairs : 4) : (c->row_pairs ? c->row_pairs : G);
+    const int max_pairs = (lines + 1) / 2;
+    P = std::max(1, std::min(P, max_pairs));
+    while (P > 1 && (size_t)P * pair_bytes > (size_t)c->max_smem) --P;
+    if ((size_t)P * pair_bytes > (size_t)c->max_smem) return fail(SSW_ERR_UNSUPPORTED, "line does not fit shared memory");
+    G = std::max(1, std::min(G, P));
+    t->P = P; t->G = G; t->threads = G * pl.tp; t->smem = (size_t)P * pair_bytes;
+    return SSW_OK;
+}
+
+template <class K>
+static int launch_line(ssw_ctx* c, K kernel, const LineArgs& a, const Tiling& t, long long tiles) {
+    const void* key = (const void*)kernel;
+    auto it = c->smem_attr.find(key);
+    if (it == c->smem_attr.end() || it->second < (int)t.smem) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+        c->smem_attr[key] = (int)t.smem;
+    }
+    if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
+    kernel<<<(unsigned)tiles, t.threads, t.smem, c->stream>>>(a);
+    CK(cudaGetLastError());
+    c->launches++;
+    return SSW_OK;
+}
+
+static LineArgs base_args(const DctPlanDev& pl, int w, int h, const Tiling& t, long long npix) {
+    LineArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.plan = pl; a.w = w; a.h = h; a.P = t.P;
+    a.scale0 = 1.f; a.scalen = 1.f;
+    a.src_stride = npix; a.plane_stride = npix; a.dst_stride = npix;
+    return a;
+}
+
+// forward: pixels/plane -> coefficient plane (rows then columns)
+static int run_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
+                       int dct_type) {
+    const DevPlan *pw, *ph;
+    CKS(get_plan(c, w, &pw));
+    CKS(get_plan(c, h, &ph));
+    Tiling tr, tc;
+    CKS(pick_tiling(c, pw->dev, false, h, &tr));
+    CKS(pick_tiling(c, ph->dev, true, w, &tc));
+    const long long npix = (long long)w * h;
+    LineArgs ar = base_args(pw->dev, w, h, tr, npix);
+    ar.src = d_src; ar.plane = d_plane;
+    ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
+    LineArgs ac = base_args(ph->dev, w, h, tc, npix);
+    ac.plane = d_plane;
+    ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+    if (dct_type == SSW_DCT2_ORTHOGONAL) {  // src/dct2d.rs:153-162,189-198
+        ar.scale0 = std::sqrt(1.0f / (4.0f * (float)w)); ar.scalen = std::sqrt(1.0f / (2.0f * (float)w));
+        ac.scale0 = std::sqrt(1.0f / (4.0f * (float)h)); ac.scalen = std::sqrt(1.0f / (2.0f * (float)h));
+    }
+    const long long ntr = (long long)ar.tiles_per_image * batch, ntc = (long long)ac.tiles_per_image * batch;
+    switch (src_type) {
+        case PIX_RGB8: CKS(launch_line(c, row_fwd_kernel<PIX_RGB8>, ar, tr, ntr)); break;
+        case PIX_RGB32F: CKS(launch_line(c, row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr)); break;
+        default: CKS(launch_line(c, row_fwd_kernel<PIX_PLANE>, ar, tr, ntr)); break;
+    }
+    CKS(launch_line(c, col_fwd_kernel, ac, tc, ntc));
+    return SSW_OK;
+}
+
+// inverse: coefficient plane (destroyed) -> pixels/plane (columns then rows)
+static int run_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
+                       int dst_type, void* d_dst) {
+    const DevPlan *pw, *ph;
+    CKS(get_plan(c, w, &pw));
+    CKS(get_plan(c, h, &ph));
+    Tiling tr, tc;
+    CKS(pick_tiling(c, pw->dev, false, h, &tr));
+    CKS(pick_tiling(c, ph->dev, true, w, &tc));
+    const long long npix = (long long)w * h;
+    LineArgs ac = base_args(ph->dev, w, h, tc, npix);
+    ac.plane = d_plane;
+    ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+    LineArgs ar = base_args(pw->dev, w, h, tr, npix);
+    ar.plane = d_plane; ar.src = d_src; ar.dst = d_dst;
+    ar.scale0 = 4.0f / (float)((size_t)w * (size_t)h);  // src/dct2d.rs:213-217
+    ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
+    const long long ntr = (long long)ar.tiles_per_image * batch, ntc = (long long)ac.tiles_per_image * batch;
+    CKS(launch_line(c, col_inv_kernel, ac, tc, ntc));
+    if (dst_type == PIX_PLANE) return launch_line(c, row_inv_kernel<PIX_PLANE, PIX_PLANE>, ar, tr, ntr);
+    if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) return launch_line(c, row_inv_kernel<PIX_RGB8, PIX_RGB8>, ar, tr, ntr);
+    if (dst_type == PIX_RGB8 && src_type == PIX_RGB32F) return launch_line(c, row_inv_kernel<PIX_RGB8, PIX_RGB32F>, ar, tr, ntr);
+    if (dst_type == PIX_RGB32F && src_type == PIX_RGB8) return launch_line(c, row_inv_kernel<PIX_RGB32F, PIX_RGB8>, ar, tr, ntr);
+    if (dst_type == PIX_RGB32F && src_type == PIX_RGB32F) return launch_line(c, row_inv_kernel<PIX_RGB32F, PIX_RGB32F>, ar, tr, ntr);
+    return fail(SSW_ERR_INVALID, "bad pixel type combination");
+}
+
+// ------------------------------------------------------------------------------------------------
+// top-k
+// ------------------------------------------------------------------------------------------------
+static int ensure_topk_scratch(ssw_ctx* c, unsigned batch) {
+    if (batch <= c->ts_batch) return SSW_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    topk_scratch_free(c);
+    const unsigned b = std::max(batch, 16u);
+    CK(cudaMalloc(&c->ts.hist, (size_t)b * kHistBins * sizeof(unsigned)));
+    CK(cudaMalloc(&c->ts.ticket, b * sizeof(unsigned)));
+    CK(cudaMalloc(&c->ts.sel_bin, b * sizeof(unsigned)));
+    CK(cudaMalloc(&c->ts.cand_count, b * sizeof(unsigned)));
+    CK(cudaMalloc(&c->ts.cand, (size_t)b * kTopkCap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->ts.overflow, sizeof(unsigned)));
+    CK(cudaMemset(c->ts.hist, 0, (size_t)b * kHistBins * sizeof(unsigned)));
+    CK(cudaMemset(c->ts.ticket, 0, b * sizeof(unsigned)));
+    CK(cudaMemset(c->ts.cand_count, 0, b * sizeof(unsigned)));
+    CK(cudaMemset(c->ts.overflow, 0, sizeof(unsigned)));
+    c->ts_batch = b;
+    return SSW_OK;
+}
+
+static OrderConsts make_order(int ordering, int w, int h) {
+    OrderConsts oc;
+    oc.mode = ordering; oc.w = w;
+    oc.s_k0_w = std::sqrt(1.0f / (4.0f * (float)w));
+    oc.s_k0_h = std::sqrt(1.0f / (4.0f * (float)h));
+    oc.s_w = std::sqrt(1.0f / (2.0f * (float)w));
+    oc.s_h = std::sqrt(1.0f / (2.0f * (float)h));
+    return oc;
+}
+
+// fast path: k + (one histogram bin of elements) must fit kTopkCap; no host synchronisation.
+static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsigned batch, int ordering,
+                         unsigned k, unsigned* d_idx, long long idx_stride) {
+    CKS(ensure_topk_scratch(c, batch));
+    const unsigned n = (unsigned)((size_t)w * h);
+    const OrderConsts oc = make_order(ordering, w, h);
+    const long long stride = (long long)n;
+    unsigned blocks = (unsigned)std::min<size_t>(((size_t)n / 4 + 511) / 512, (size_t)std::max(1u, (unsigned)(c->sm_count * 4) / std::min(batch, (unsigned)(c->sm_count * 4))));
+    blocks = std::max(1u, blocks);
+    for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
+        const unsigned nb = std::min(65535u, batch - b0);
+        TopkScratch ts = c->ts;
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0;
+        ts.cand += (size_t)b0 * kTopkCap;
+        topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
+        topk_collect_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, oc, ts);
+        CK(cudaGetLastError());
+        c->launches += 2;
+    }
+    const void* key = (const void*)topk_sort_kernel;
+    const int smem = kTopkCap * (int)sizeof(unsigned long long);
+    if (c->smem_attr.find(key) == c->smem_attr.end()) {
+        CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->smem_attr[key] = smem;
+    }
+    topk_sort_kernel<<<batch, 1024, smem, c->stream>>>(c->ts, k, d_idx, idx_stride);
+    CK(cudaGetLastError());
+    c->launches++;
+    return SSW_OK;
+}
+
+// read-and-clear the sticky overflow counter (synchronises the stream)
+static int take_overflow(ssw_ctx* c, unsigned* out) {
+    *out = 0;
+    if (!c->ts_batch) return SSW_OK;
+    CK(cudaMemcpyAsync(c->h_flag, c->ts.overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemsetAsync(c->ts.overflow, 0, sizeof(unsigned), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = *c->h_flag;
+    return SSW_OK;
+}
+
+// exact top-k of ONE plane for any k (host-synchronising): fast path when it applies, otherwise the
+// general radix-sort path; a fast-path overflow is detected and repaired here.
+static int run_topk_exact(ssw_ctx* c, const float* d_plane, int w, int h, int ordering, size_t k,
+                          unsigned* d_idx) {
+    const size_t n = (size_t)w * h;
+    if (k == 0) return SSW_OK;
+    if (k > n - 1) return fail(SSW_ERR_INVALID, "k exceeds the number of AC coefficients");
+    if (k <= (size_t)kTopkCap / 2) {
+        CKS(run_topk_fast(c, d_plane, w, h, 1, ordering, (unsigned)k, d_idx, 0));
+        unsigned ov = 0;
+        CKS(take_overflow(c, &ov));
+        if (!ov) return SSW_OK;
+        c->last_fallbacks += 1;
+    }
+    const OrderConsts oc = make_order(ordering, w, h);
+    int rc = c->general.run(c->stream, d_plane, (unsigned)n, oc, k, d_idx, &c->launches);
+    if (rc != SSW_OK) return fail(rc, c->general.error);
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dct2d::dct2_2d
+// ------------------------------------------------------------------------------------------------
+static int check_dims(uint32_t w, uint32_t h) {
+    if (w == 0 || h == 0) return fail(SSW_ERR_INVALID, "image dimensions must be non-zero");
+    if ((uint64_t)w * h >= 0xFFFFFFFFull) return fail(SSW_ERR_UNSUPPORTED, "more than 2^32-1 pixels per frame");
+    return SSW_OK;
+}
+
+extern "C" int ssw_dct2_2d_dev(ssw_ctx* c, int type, uint32_t w, uint32_t h, float* d) {
+    if (!c || !d) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    if (type == SSW_DCT2 || type == SSW_DCT2_ORTHOGONAL) return run_forward(c, PIX_PLANE, d, w, h, 1, d, type);
+    if (type == SSW_DCT3) return run_inverse(c, d, PIX_PLANE, nullptr, w, h, 1, PIX_PLANE, d);
+    return fail(SSW_ERR_INVALID, "unknown transform type");
+}
+
+extern "C" int ssw_dct2_2d(ssw_ctx* c, int type, uint32_t w, uint32_t h, float* data) {
+    if (!c || !data) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    const size_t bytes = (size_t)w * h * sizeof(float);
+    float* d = nullptr;
+    CK(cudaMallocAsync(&d, bytes, c->stream));
+    CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = ssw_dct2_2d_dev(c, type, w, h, d);
+    if (rc == SSW_OK) {
+        cudaError_t e = cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (rc == SSW_OK && e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// yiq planes
+// ------------------------------------------------------------------------------------------------
+extern "C" int ssw_rgb32f_to_yiq(ssw_ctx* c, const float* rgb, uint32_t w, uint32_t h, float* y, float* i, float* q) {
+    if (!c || !rgb || !y || !i || !q) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    const size_t np = (size_t)w * h;
+    float* d = nullptr;
+    CK(cudaMallocAsync(&d, np * 6 * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(d, rgb, np * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    float* dy = d + 3 * np;
+    rgb32f_to_yiq_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, np, dy, dy + np, dy + 2 * np);
+    c->launches++;
+    CK(cudaMemcpyAsync(y, dy, np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(i, dy + np, np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(q, dy + 2 * np, np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+extern "C" int ssw_yiq_to_rgb32f(ssw_ctx* c, const float* y, const float* i, const float* q, uint32_t w, uint32_t h, float* rgb) {
+    if (!c || !rgb || !y || !i || !q) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    const size_t np = (size_t)w * h;
+    float* d = nullptr;
+    CK(cudaMallocAsync(&d, np * 6 * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(d, y, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + np, i, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + 2 * np, q, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    yiq_to_rgb32f_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, d + np, d + 2 * np, np, d + 3 * np);
+    c->launches++;
+    CK(cudaMemcpyAsync(rgb, d + 3 * np, np * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// config validation
+// ------------------------------------------------------------------------------------------------
+static int check_cfg(const ssw_config* cfg) {
+    if (!cfg) return fail(SSW_ERR_INVALID, "config is NULL");
+    if (cfg->method < 1 || cfg->method > 3)
+        return fail(SSW_ERR_UNSUPPORTED, "only Option1/2/3 insertion/extraction run on the device (Custom closures are host code)");
+    if (cfg->ordering < 0 || cfg->ordering > 2)
+        return fail(SSW_ERR_UNSUPPORTED, "only Energy/EnergyOrthogonal/Legacy orderings run on the device (Custom closures are host code)");
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Writer
+// ------------------------------------------------------------------------------------------------
+struct ssw_writer {
+    ssw_ctx* ctx;
+    uint32_t w, h;
+    ssw_config cfg;
+    int src_type;
+    void* d_src;  // original pixels (owned unless borrowed)
+    bool own_src;
+    float* d_plane;
+    unsigned* d_idx;
+    size_t k_cached;
+    bool consumed;
+};
+
+static int writer_new(ssw_ctx* c, int src_type, const void* src, bool src_on_device, uint32_t w, uint32_t h,
+                      const ssw_config* cfg, ssw_writer** out) {
+    if (!c || !src || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    auto wr = std::make_unique<ssw_writer>();
+    wr->ctx = c; wr->w = w; wr->h = h; wr->cfg = *cfg; wr->src_type = src_type;
+    wr->d_idx = nullptr; wr->k_cached = 0; wr->consumed = false;
+    const size_t np = (size_t)w * h;
+    const size_t src_bytes = np * 3 * (src_type == PIX_RGB8 ? 1 : 4);
+    if (src_on_device) {
+        wr->d_src = const_cast<void*>(src);
+        wr->own_src = false;
+    } else {
+        CK(cudaMallocAsync(&wr->d_src, src_bytes, c->stream));
+        wr->own_src = true;
+        CK(cudaMemcpyAsync(wr->d_src, src, src_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaMallocAsync(&wr->d_plane, np * sizeof(float), c->stream));
+    int rc = run_forward(c, src_type, wr->d_src, w, h, 1, wr->d_plane, SSW_DCT2);
+    if (!src_on_device) {
+        // the upload reads caller memory asynchronously: finish before returning control
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (rc == SSW_OK && e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc != SSW_OK) {
+        if (wr->own_src) cudaFreeAsync(wr->d_src, c->stream);
+        cudaFreeAsync(wr->d_plane, c->stream);
+        return rc;
+    }
+    *out = wr.release();
+    return SSW_OK;
+}
+
+extern "C" int ssw_writer_new_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, const ssw_config* cfg, ssw_writer** out) {
+    return writer_new(c, PIX_RGB8, rgb, false, w, h, cfg, out);
+}
+extern "C" int ssw_writer_new_rgb32f(ssw_ctx* c, const float* rgb, uint32_t w, uint32_t h, const ssw_config* cfg, ssw_writer** out) {
+    return writer_new(c, PIX_RGB32F, rgb, false, w, h, cfg, out);
+}
+extern "C" int ssw_writer_new_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, const ssw_config* cfg, ssw_writer** out) {
+    return writer_new(c, PIX_RGB8, rgb, true, w, h, cfg, out);
+}
+
+static int ensure_indices(ssw_ctx* c, const float* d_plane, uint32_t w, uint32_t h, int ordering, size_t k,
+                          unsigned** d_idx, size_t* k_cached) {
+    if (k <= *k_cached) return SSW_OK;
+    if (*d_idx) { CK(cudaFreeAsync(*d_idx, c->stream)); *d_idx = nullptr; *k_cached = 0; }
+    CK(cudaMallocAsync(d_idx, k * sizeof(unsigned), c->stream));
+    CKS(run_topk_exact(c, d_plane, w, h, ordering, k, *d_idx));
+    *k_cached = k;
+    return SSW_OK;
+}
+
+extern "C" int ssw_writer_embed(ssw_writer* wr, const float* const* marks, const size_t* lens, size_t n_marks) {
+    if (!wr || (n_marks && (!marks || !lens))) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (wr->consumed) return fail(SSW_ERR_STATE, "writer already consumed by result()");
+    if (n_marks == 0) return SSW_OK;
+    ssw_ctx* c = wr->ctx;
+    CKS(ctx_bind(c));
+    const size_t nac = (size_t)wr->w * wr->h - 1;
+    size_t kmax = 0;
+    std::vector<unsigned> hl(n_marks);
+    for (size_t m = 0; m < n_marks; ++m) {
+        if (lens[m] && !marks[m]) return fail(SSW_ERR_INVALID, "mark pointer is NULL");
+        const size_t l = std::min(lens[m], nac);  // zip truncation, src/algorithm.rs:396
+        hl[m] = (unsigned)l;
+        kmax = std::max(kmax, l);
+    }
+    if (kmax == 0) return SSW_OK;
+    CKS(ensure_indices(c, wr->d_plane, wr->w, wr->h, wr->cfg.ordering, kmax, &wr->d_idx, &wr->k_cached));
+    // stage marks as [n_marks][kmax] zero-padded + lens
+    std::vector<float> stage(n_marks * kmax, 0.f);
+    for (size_t m = 0; m < n_marks; ++m) std::memcpy(&stage[m * kmax], marks[m], hl[m] * sizeof(float));
+    float* d_marks = nullptr;
+    unsigned* d_lens = nullptr;
+    CK(cudaMallocAsync(&d_marks, stage.size() * sizeof(float), c->stream));
+    CK(cudaMallocAsync(&d_lens, n_marks * sizeof(unsigned), c->stream));
+    CK(cudaMemcpyAsync(d_marks, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_lens, hl.data(), n_marks * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    embed_scatter_kernel<<<dim3((unsigned)((kmax + 255) / 256), 1), 256, 0, c->stream>>>(
+        wr->d_plane, 0, wr->d_idx, 0, (unsigned)kmax, d_marks, (long long)kmax, (int)n_marks, d_lens,
+        wr->cfg.method, wr->cfg.alpha);
+    CK(cudaGetLastError());
+    c->launches++;
+    CK(cudaFreeAsync(d_marks, c->stream));
+    CK(cudaFreeAsync(d_lens, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // `stage` / `hl` are pageable host memory
+    return SSW_OK;
+}
+
+extern "C" int ssw_writer_coefficients(ssw_writer* wr, float* out) {
+    if (!wr || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (wr->consumed) return fail(SSW_ERR_STATE, "writer already consumed by result()");
+    ssw_ctx* c = wr->ctx;
+    CKS(ctx_bind(c));
+    CK(cudaMemcpyAsync(out, wr->d_plane, (size_t)wr->w * wr->h * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+static int download_indices(ssw_ctx* c, const unsigned* d_idx, uint64_t* out, size_t n) {
+    std::vector<unsigned> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), d_idx, n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) out[i] = tmp[i];
+    return SSW_OK;
+}
+
+extern "C" int ssw_writer_indices(ssw_writer* wr, uint64_t* out, size_t n) {
+    if (!wr || (!out && n)) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (n == 0) return SSW_OK;
+    if (n > (size_t)wr->w * wr->h - 1) return fail(SSW_ERR_INVALID, "more indices requested than AC coefficients");
+    if (wr->consumed) return fail(SSW_ERR_STATE, "writer already consumed by result()");
+    ssw_ctx* c = wr->ctx;
+    CKS(ctx_bind(c));
+    if (n > wr->k_cached && wr->k_cached)
+        return fail(SSW_ERR_STATE, "indices beyond the embedded length are undefined after embed (coefficients were modified)");
+    CKS(ensure_indices(c, wr->d_plane, wr->w, wr->h, wr->cfg.ordering, n, &wr->d_idx, &wr->k_cached));
+    return download_indices(c, wr->d_idx, out, n);
+}
+
+static int writer_result(ssw_writer* wr, int dst_type, void* out, bool out_on_device) {
+    if (!wr || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (wr->consumed) return fail(SSW_ERR_STATE, "writer already consumed by result()");
+    ssw_ctx* c = wr->ctx;
+    CKS(ctx_bind(c));
+    const size_t np = (size_t)wr->w * wr->h;
+    const size_t bytes = np * 3 * (dst_type == PIX_RGB8 ? 1 : 4);
+    void* d_out = out;
+    if (!out_on_device) CK(cudaMallocAsync(&d_out, bytes, c->stream));
+    int rc = run_inverse(c, wr->d_plane, wr->src_type, wr->d_src, wr->w, wr->h, 1, dst_type, d_out);
+    wr->consumed = true;
+    if (!out_on_device) {
+        if (rc == SSW_OK) {
+            cudaError_t e = cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+        }
+        cudaFreeAsync(d_out, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (rc == SSW_OK && e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+extern "C" int ssw_writer_result_rgb8(ssw_writer* wr, uint8_t* out) { return writer_result(wr, PIX_RGB8, out, false); }
+extern "C" int ssw_writer_result_rgb32f(ssw_writer* wr, float* out) { return writer_result(wr, PIX_RGB32F, out, false); }
+extern "C" int ssw_writer_result_rgb8_dev(ssw_writer* wr, uint8_t* out) { return writer_result(wr, PIX_RGB8, out, true); }
+
+extern "C" int ssw_writer_destroy(ssw_writer* wr) {
+    if (!wr) return SSW_OK;
+    ssw_ctx* c = wr->ctx;
+    cudaSetDevice(c->device);
+    if (wr->own_src && wr->d_src) cudaFreeAsync(wr->d_src, c->stream);
+    if (wr->d_plane) cudaFreeAsync(wr->d_plane, c->stream);
+    if (wr->d_idx) cudaFreeAsync(wr->d_idx, c->stream);
+    delete wr;
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reader
+// ------------------------------------------------------------------------------------------------
+struct ssw_reader {
+    ssw_ctx* ctx;
+    uint32_t w, h;
+    bool is_base;
+    ssw_config cfg;
+    float* d_plane;
+    unsigned* d_idx;
+    size_t k_cached;
+};
+
+static int reader_new(ssw_ctx* c, int src_type, const void* src, bool src_on_device, uint32_t w, uint32_t h,
+                      bool is_base, const ssw_config* cfg, ssw_reader** out) {
+    if (!c || !src || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (is_base) CKS(check_cfg(cfg));
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    auto rd = std::make_unique<ssw_reader>();
+    rd->ctx = c; rd->w = w; rd->h = h; rd->is_base = is_base;
+    if (is_base) rd->cfg = *cfg; else rd->cfg = ssw_config{2, 0.1f, 0};
+    rd->d_idx = nullptr; rd->k_cached = 0;
+    const size_t np = (size_t)w * h;
+    const size_t src_bytes = np * 3 * (src_type == PIX_RGB8 ? 1 : 4);
+    void* d_src = const_cast<void*>(src);
+    if (!src_on_device) {
+        CK(cudaMallocAsync(&d_src, src_bytes, c->stream));
+        CK(cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaMallocAsync(&rd->d_plane, np * sizeof(float), c->stream));
+    int rc = run_forward(c, src_type, d_src, w, h, 1, rd->d_plane, SSW_DCT2);
+    if (!src_on_device) {
+        cudaFreeAsync(d_src, c->stream);
+        // the upload reads caller memory asynchronously: finish before returning control
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (rc == SSW_OK && e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (rc != SSW_OK) { cudaFreeAsync(rd->d_plane, c->stream); return rc; }
+    *out = rd.release();
+    return SSW_OK;
+}
+
+extern "C" int ssw_reader_base_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, const ssw_config* cfg, ssw_reader** out) {
+    return reader_new(c, PIX_RGB8, rgb, false, w, h, true, cfg, out);
+}
+extern "C" int ssw_reader_base_rgb32f(ssw_ctx* c, const float* rgb, uint32_t w, uint32_t h, const ssw_config* cfg, ssw_reader** out) {
+    return reader_new(c, PIX_RGB32F, rgb, false, w, h, true, cfg, out);
+}
+extern "C" int ssw_reader_derived_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, ssw_reader** out) {
+    return reader_new(c, PIX_RGB8, rgb, false, w, h, false, nullptr, out);
+}
+extern "C" int ssw_reader_derived_rgb32f(ssw_ctx* c, const float* rgb, uint32_t w, uint32_t h, ssw_reader** out) {
+    return reader_new(c, PIX_RGB32F, rgb, false, w, h, false, nullptr, out);
+}
+extern "C" int ssw_reader_base_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, const ssw_config* cfg, ssw_reader** out) {
+    return reader_new(c, PIX_RGB8, rgb, true, w, h, true, cfg, out);
+}
+extern "C" int ssw_reader_derived_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, ssw_reader** out) {
+    return reader_new(c, PIX_RGB8, rgb, true, w, h, false, nullptr, out);
+}
+
+static int reader_extract(ssw_reader* base, ssw_reader* derived, float* out, size_t n, bool out_on_device) {
+    if (!base || !derived || (!out && n)) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (!base->is_base) return fail(SSW_ERR_STATE, "extract called on a derived reader (reference: unwrap on None, src/algorithm.rs:530)");
+    if (base->ctx != derived->ctx) return fail(SSW_ERR_INVALID, "readers belong to different contexts");
+    if ((size_t)base->w * base->h != (size_t)derived->w * derived->h)
+        return fail(SSW_ERR_INVALID, "Derived coefficient length not equal to base coefficient length.");
+    if (n >= (size_t)base->w * base->h)
+        return fail(SSW_ERR_INVALID, "Desired extraction length exceeds available coefficients.");
+    if (n == 0) return SSW_OK;
+    ssw_ctx* c = base->ctx;
+    CKS(ctx_bind(c));
+    CKS(ensure_indices(c, base->d_plane, base->w, base->h, base->cfg.ordering, n, &base->d_idx, &base->k_cached));
+    float* d_out = out;
+    if (!out_on_device) CK(cudaMallocAsync(&d_out, n * sizeof(float), c->stream));
+    extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream>>>(
+        base->d_plane, derived->d_plane, 0, base->d_idx, 0, (unsigned)n, base->cfg.method, base->cfg.alpha, d_out, 0);
+    CK(cudaGetLastError());
+    c->launches++;
+    if (!out_on_device) {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaFreeAsync(d_out, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return SSW_OK;
+}
+
+extern "C" int ssw_reader_extract(ssw_reader* b, ssw_reader* d, float* out, size_t n) { return reader_extract(b, d, out, n, false); }
+extern "C" int ssw_reader_extract_dev(ssw_reader* b, ssw_reader* d, float* out, size_t n) { return reader_extract(b, d, out, n, true); }
+
+extern "C" int ssw_reader_coefficients(ssw_reader* r, float* out) {
+    if (!r || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    ssw_ctx* c = r->ctx;
+    CKS(ctx_bind(c));
+    CK(cudaMemcpyAsync(out, r->d_plane, (size_t)r->w * r->h * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+extern "C" int ssw_reader_indices(ssw_reader* r, uint64_t* out, size_t n) {
+    if (!r || (!out && n)) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (!r->is_base) return fail(SSW_ERR_STATE, "indices() called on a derived reader (reference: unwrap on None, src/algorithm.rs:507)");
+    if (n == 0) return SSW_OK;
+    if (n > (size_t)r->w * r->h - 1) return fail(SSW_ERR_INVALID, "more indices requested than AC coefficients");
+    ssw_ctx* c = r->ctx;
+    CKS(ctx_bind(c));
+    CKS(ensure_indices(c, r->d_plane, r->w, r->h, r->cfg.ordering, n, &r->d_idx, &r->k_cached));
+    return download_indices(c, r->d_idx, out, n);
+}
+
+extern "C" int ssw_reader_destroy(ssw_reader* r) {
+    if (!r) return SSW_OK;
+    ssw_ctx* c = r->ctx;
+    cudaSetDevice(c->device);
+    if (r->d_plane) cudaFreeAsync(r->d_plane, c->stream);
+    if (r->d_idx) cudaFreeAsync(r->d_idx, c->stream);
+    delete r;
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// similarity / bank / marks
+// ------------------------------------------------------------------------------------------------
+struct ssw_bank {
+    ssw_ctx* ctx;
+    float* d_marks;
+    size_t n_marks, n;
+};
+
+static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, size_t n, const float* d_ext,
+                             size_t n_ext, bool pair_mode, float* d_out) {
+    if (n_marks == 0 || n_ext == 0) return SSW_OK;
+    const size_t gx = (n_marks + kSimMarks - 1) / kSimMarks;
+    if (gx > 0x7FFFFFFFull || n_ext > 65535 || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
+    similarity_bank_kernel<<<dim3((unsigned)gx, pair_mode ? 1u : (unsigned)n_ext), kSimMarks, 0, c->stream>>>(
+        d_bank, n_marks, (unsigned)n, d_ext, (long long)n, pair_mode ? 1 : 0, d_out, (long long)n_marks);
+    CK(cudaGetLastError());
+    c->launches++;
+    return SSW_OK;
+}
+
+extern "C" int ssw_similarity(ssw_ctx* c, const float* extracted, const float* mark, size_t n, float* out) {
+    if (!c || !out || (n && (!extracted || !mark))) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(c));
+    float* d = nullptr;
+    CK(cudaMallocAsync(&d, (2 * n + 1) * sizeof(float), c->stream));
+    if (n) {
+        CK(cudaMemcpyAsync(d, extracted, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d + n, mark, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    CKS(launch_similarity(c, d + n, 1, n, d, 1, false, d + 2 * n));
+    CK(cudaMemcpyAsync(out, d + 2 * n, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+static int fill_normal(ssw_ctx* c, float* d_out, size_t n, uint64_t seed) {
+    if (n == 0) return SSW_OK;
+    if (seed == 0) {
+        std::random_device rd;
+        seed = ((uint64_t)rd() << 32) ^ rd();
+        if (seed == 0) seed = 0x9E3779B97F4A7C15ull;
+    }
+    const size_t quads = (n + 3) / 4;
+    normal_fill_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, c->stream>>>(d_out, n, seed, 0ull);
+    CK(cudaGetLastError());
+    c->launches++;
+    return SSW_OK;
+}
+
+extern "C" int ssw_bank_create(ssw_ctx* c, const float* marks, size_t n_marks, size_t n, ssw_bank** out) {
+    if (!c || !out || (!marks && n_marks * n)) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(c));
+    auto b = std::make_unique<ssw_bank>();
+    b->ctx = c; b->n_marks = n_marks; b->n = n; b->d_marks = nullptr;
+    CK(cudaMalloc(&b->d_marks, std::max<size_t>(n_marks * n, 1) * sizeof(float)));
+    if (n_marks * n) {
+        CK(cudaMemcpyAsync(b->d_marks, marks, n_marks * n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    *out = b.release();
+    return SSW_OK;
+}
+
+extern "C" int ssw_bank_create_normal(ssw_ctx* c, uint64_t seed, size_t n_marks, size_t n, ssw_bank** out) {
+    if (!c || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(c));
+    auto b = std::make_unique<ssw_bank>();
+    b->ctx = c; b->n_marks = n_marks; b->n = n; b->d_marks = nullptr;
+    CK(cudaMalloc(&b->d_marks, std::max<size_t>(n_marks * n, 1) * sizeof(float)));
+    CKS(fill_normal(c, b->d_marks, n_marks * n, seed ? seed : 1));
+    *out = b.release();
+    return SSW_OK;
+}
+
+extern "C" int ssw_bank_row(ssw_bank* b, size_t index, float* out) {
+    if (!b || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (index >= b->n_marks) return fail(SSW_ERR_INVALID, "bank row out of range");
+    ssw_ctx* c = b->ctx;
+    CKS(ctx_bind(c));
+    CK(cudaMemcpyAsync(out, b->d_marks + index * b->n, b->n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+extern "C" int ssw_bank_similarity_dev(ssw_bank* b, const float* d_ext, size_t n_ext, float* d_out) {
+    if (!b || !d_ext || !d_out) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(b->ctx));
+    return launch_similarity(b->ctx, b->d_marks, b->n_marks, b->n, d_ext, n_ext, false, d_out);
+}
+
+extern "C" int ssw_bank_similarity(ssw_bank* b, const float* ext, size_t n_ext, float* out) {
+    if (!b || !ext || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    ssw_ctx* c = b->ctx;
+    CKS(ctx_bind(c));
+    float *d_ext = nullptr, *d_out = nullptr;
+    CK(cudaMallocAsync(&d_ext, std::max<size_t>(n_ext * b->n, 1) * sizeof(float), c->stream));
+    CK(cudaMallocAsync(&d_out, std::max<size_t>(n_ext * b->n_marks, 1) * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(d_ext, ext, n_ext * b->n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CKS(launch_similarity(c, b->d_marks, b->n_marks, b->n, d_ext, n_ext, false, d_out));
+    CK(cudaMemcpyAsync(out, d_out, n_ext * b->n_marks * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d_ext, c->stream));
+    CK(cudaFreeAsync(d_out, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+extern "C" int ssw_bank_destroy(ssw_bank* b) {
+    if (!b) return SSW_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_marks);
+    delete b;
+    return SSW_OK;
+}
+
+extern "C" int ssw_mark_generate_normal(ssw_ctx* c, uint64_t seed, size_t n, float* out) {
+    if (!c || (!out && n)) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (n == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    float* d = nullptr;
+    CK(cudaMallocAsync(&d, n * sizeof(float), c->stream));
+    CKS(fill_normal(c, d, n, seed));
+    CK(cudaMemcpyAsync(out, d, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused device-resident pipelines
+// ------------------------------------------------------------------------------------------------
+static unsigned chunk_images(ssw_ctx* c, size_t np, unsigned batch, int planes_per_image) {
+    const size_t per = np * sizeof(float) * planes_per_image;
+    size_t n = std::max<size_t>(1, c->chunk_bytes / per);
+    return (unsigned)std::min<size_t>(n, batch);
+}
+
+extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t batch,
+                                        const ssw_config* cfg, const float* marks, size_t n, uint8_t* out_rgb) {
+    if (!c || !rgb || !out_rgb || (n && !marks)) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    CKS(check_dims(w, h));
+    if (batch == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    const size_t np = (size_t)w * h;
+    const size_t k = std::min(n, np - 1);
+    if (k > (size_t)kTopkCap / 2) return fail(SSW_ERR_UNSUPPORTED, "fused pipeline supports mark lengths up to 4096; use the Writer API");
+    const unsigned cb = chunk_images(c, np, batch, 1);
+    float* d_planes = nullptr;
+    unsigned* d_idx = nullptr;
+    CK(cudaMallocAsync(&d_planes, (size_t)cb * np * sizeof(float), c->stream));
+    CK(cudaMallocAsync(&d_idx, (size_t)cb * std::max<size_t>(k, 1) * sizeof(unsigned), c->stream));
+    int rc = SSW_OK;
+    for (unsigned b0 = 0; b0 < batch && rc == SSW_OK; b0 += cb) {
+        const unsigned nb = std::min(cb, batch - b0);
+        const uint8_t* src = rgb + (size_t)b0 * np * 3;
+        rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
+        if (rc == SSW_OK && k) {
+            rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k);
+            if (rc == SSW_OK) {
+                embed_scatter_kernel<<<dim3((unsigned)((k + 255) / 256), nb), 256, 0, c->stream>>>(
+                    d_planes, (long long)np, d_idx, (long long)k, (unsigned)k, marks + (size_t)b0 * n, (long long)n, 1,
+                    nullptr, cfg->method, cfg->alpha);
+                c->launches++;
+            }
+        }
+        if (rc == SSW_OK) rc = run_inverse(c, d_planes, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3);
+    }
+    cudaFreeAsync(d_planes, c->stream);
+    cudaFreeAsync(d_idx, c->stream);
+    if (rc == SSW_OK) CK(cudaGetLastError());
+    return rc;
+}
+
+extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, const uint8_t* derived_rgb, uint32_t w,
+                                          uint32_t h, uint32_t batch, const ssw_config* cfg, size_t n,
+                                          float* extracted, const float* marks, float* sim) {
+    if (!c || !base_rgb || !derived_rgb || !extracted) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    CKS(check_dims(w, h));
+    if (sim && !marks) return fail(SSW_ERR_INVALID, "similarity requested without marks");
+    const size_t np = (size_t)w * h;
+    if (n >= np) return fail(SSW_ERR_INVALID, "Desired extraction length exceeds available coefficients.");
+    if (n > (size_t)kTopkCap / 2) return fail(SSW_ERR_UNSUPPORTED, "fused pipeline supports mark lengths up to 4096; use the Reader API");
+    if (batch == 0 || n == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    const unsigned cb = chunk_images(c, np, batch, 2);
+    float* d_planes = nullptr;
+    unsigned* d_idx = nullptr;
+    CK(cudaMallocAsync(&d_planes, (size_t)cb * np * 2 * sizeof(float), c->stream));
+    CK(cudaMallocAsync(&d_idx, (size_t)cb * n * sizeof(unsigned), c->stream));
+    int rc = SSW_OK;
+    for (unsigned b0 = 0; b0 < batch && rc == SSW_OK; b0 += cb) {
+        const unsigned nb = std::min(cb, batch - b0);
+        float* pb = d_planes;
+        float* pd = d_planes + (size_t)cb * np;
+        rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
+        if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
+        if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n);
+        if (rc == SSW_OK) {
+            extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, c->stream>>>(
+                pb, pd, (long long)np, d_idx, (long long)n, (unsigned)n, cfg->method, cfg->alpha,
+                extracted + (size_t)b0 * n, (long long)n);
+            c->launches++;
+            if (sim) rc = launch_similarity(c, marks + (size_t)b0 * n, nb, n, extracted + (size_t)b0 * n, nb, true, sim + b0);
+        }
+    }
+    cudaFreeAsync(d_planes, c->stream);
+    cudaFreeAsync(d_idx, c->stream);
+    if (rc == SSW_OK) CK(cudaGetLastError());
+    return rc;
+}
+
+extern "C" int ssw_embed_batch_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t batch,
+                                    const ssw_config* cfg, const float* marks, size_t n, uint8_t* out_rgb) {
+    if (!c || !rgb || !out_rgb || (n && !marks)) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    if (batch == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    const size_t bytes = (size_t)w * h * 3 * batch;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    float* d_marks = nullptr;
+    CK(cudaMallocAsync(&d_in, bytes, c->stream));
+    CK(cudaMallocAsync(&d_out, bytes, c->stream));
+    CK(cudaMallocAsync(&d_marks, std::max<size_t>(n * batch, 1) * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(d_in, rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (n) CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    int rc = ssw_embed_batch_rgb8_dev(c, d_in, w, h, batch, cfg, d_marks, n, d_out);
+    if (rc == SSW_OK) {
+        cudaError_t e = cudaMemcpyAsync(out_rgb, d_out, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_in, c->stream); cudaFreeAsync(d_out, c->stream); cudaFreeAsync(d_marks, c->stream);
+    unsigned ov = 0;
+    int rs = take_overflow(c, &ov);  // synchronises
+    if (rc == SSW_OK) rc = rs;
+    c->last_fallbacks = (int)ov;
+    if (rc == SSW_OK && ov) rc = fail(SSW_ERR_UNSUPPORTED, "top-k candidate overflow in the fused pipeline (degenerate spectrum): use the Writer API for these frames");
+    return rc;
+}
+
+extern "C" int ssw_extract_batch_rgb8(ssw_ctx* c, const uint8_t* base_rgb, const uint8_t* derived_rgb, uint32_t w,
+                                      uint32_t h, uint32_t batch, const ssw_config* cfg, size_t n, float* extracted,
+                                      const float* marks, float* sim) {
+    if (!c || !base_rgb || !derived_rgb || !extracted) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    if (batch == 0 || n == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    const size_t bytes = (size_t)w * h * 3 * batch;
+    uint8_t *d_b = nullptr, *d_d = nullptr;
+    float *d_ext = nullptr, *d_marks = nullptr, *d_sim = nullptr;
+    CK(cudaMallocAsync(&d_b, bytes, c->stream));
+    CK(cudaMallocAsync(&d_d, bytes, c->stream));
+    CK(cudaMallocAsync(&d_ext, n * batch * sizeof(float), c->stream));
+    CK(cudaMemcpyAsync(d_b, base_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_d, derived_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (sim && marks) {
+        CK(cudaMallocAsync(&d_marks, n * batch * sizeof(float), c->stream));
+        CK(cudaMallocAsync(&d_sim, batch * sizeof(float), c->stream));
+        CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = ssw_extract_batch_rgb8_dev(c, d_b, d_d, w, h, batch, cfg, n, d_ext, d_marks, d_sim);
+    if (rc == SSW_OK) {
+        cudaError_t e = cudaMemcpyAsync(extracted, d_ext, n * batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && d_sim) e = cudaMemcpyAsync(sim, d_sim, batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_b, c->stream); cudaFreeAsync(d_d, c->stream); cudaFreeAsync(d_ext, c->stream);
+    if (d_marks) cudaFreeAsync(d_marks, c->stream);
+    if (d_sim) cudaFreeAsync(d_sim, c->stream);
+    unsigned ov = 0;
+    int rs = take_overflow(c, &ov);
+    if (rc == SSW_OK) rc = rs;
+    c->last_fallbacks = (int)ov;
+    if (rc == SSW_OK && ov) rc = fail(SSW_ERR_UNSUPPORTED, "top-k candidate overflow in the fused pipeline (degenerate spectrum): use the Reader API for these frames");
+    return rc;
+}
+
+extern "C" int ssw_ctx_last_topk_fallbacks(ssw_ctx* c) {
+    if (!c) return 0;
+    if (ctx_bind(c) != SSW_OK) return -1;
+    unsigned ov = 0;
+    if (take_overflow(c, &ov) != SSW_OK) return -1;
+    const int r = c->last_fallbacks + (int)ov;
+    c->last_fallbacks = 0;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic frames + stage hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int ssw_synth_frame_rgb8_dev(ssw_ctx* c, uint32_t w, uint32_t h, uint64_t seed, uint32_t first_image,
+                                        uint32_t n_images, uint8_t* out) {
+    if (!c || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    if (h > 65535) return fail(SSW_ERR_UNSUPPORTED, "synthetic frames are limited to 65535 rows");
+    CKS(ctx_bind(c));
+    for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
+        const uint32_t nb = std::min<uint32_t>(65535, n_images - i0);
+        synth_frame_kernel<<<dim3((w + 127) / 128, h, nb), 128, 0, c->stream>>>(out + (size_t)i0 * w * h * 3, w, h, seed, first_image + i0);
+        CK(cudaGetLastError());
+        c->launches++;
+    }
+    return SSW_OK;
+}
+
+extern "C" int ssw_stage_forward_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t batch, float* plane) {
+    if (!c || !rgb || !plane) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    return run_forward(c, PIX_RGB8, rgb, w, h, batch, plane, SSW_DCT2);
+}
+
+extern "C" int ssw_stage_topk_dev(ssw_ctx* c, const float* plane, uint32_t w, uint32_t h, uint32_t batch, int ordering,
+                                  size_t k, uint32_t* idx) {
+    if (!c || !plane || !idx) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    if (k == 0 || k > (size_t)kTopkCap / 2 || k > (size_t)w * h - 1) return fail(SSW_ERR_INVALID, "k out of range for the fused top-k");
+    CKS(ctx_bind(c));
+    return run_topk_fast(c, plane, w, h, batch, ordering, (unsigned)k, idx, (long long)k);
+}
+
+extern "C" int ssw_stage_inverse_rgb8_dev(ssw_ctx* c, float* plane, const uint8_t* rgb_src, uint32_t w, uint32_t h,
+                                          uint32_t batch, uint8_t* out_rgb) {
+    if (!c || !plane || !rgb_src || !out_rgb) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, h));
+    CKS(ctx_bind(c));
+    return run_inverse(c, plane, PIX_RGB8, rgb_src, w, h, batch, PIX_RGB8, out_rgb);
+}
