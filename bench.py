@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: Mpix/s of embed & extract (full-frame DCT +
+top-k) with the achieved fraction of the measured HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic
+input: embed a length-1000 N(0,1) mark into a frame (Writer::new(img,cfg).mark(&[mark]).into_rgb8())
+and extract + score it again (Reader::base / Reader::derived / extract / Tester::similarity).
+
+  workload c2 (default, BASELINE.json configs[1]): single synthetic 3840x2160 RGB8 frames, one frame
+      per step, cycling through a ring of distinct frames larger than L2.
+  workload c3 (configs[2]): batches of synthetic 1920x1080 frames, one batch per step.
+  N > 1: the units are independent frames -> every rank runs the same per-GPU workload on its own
+      frames, no data-path collective ("scaling": "weak").
+
+  value   device-resident throughput (inputs already in HBM), CUDA events on the library's stream
+  e2e     the same step through the host-buffer C-ABI calls (pinned host memory, H2D + D2H inside)
+  roofline / kernels   per-kernel CUDA-event attribution of the same steps (ssw_ctx_profile_*)
+  cpu_baseline         the oracle's C restatement of the reference path on 1 host core (rank 0, N=1)
+
+--impl reference times the reference's own CPU implementation of the path: the Rust crate cannot be
+built in this image (no cargo/rustc), so it is the oracle's C restatement that keeps the reference's
+structure (separate planes, per-line gather/scatter, FFT-DCT, full stable sort), one frame per host
+thread on all host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MARK_LEN = 1000
+ALPHA = 0.1
+WORKLOADS = {
+    # name: (w, h, frames per step, ring size (steps before inputs repeat), seed)
+    'c2': dict(w=3840, h=2160, batch=1, ring=8, seed=2,
+               name='single synthetic 3840x2160 RGB frame, mark length 1000, embed+extract'),
+    'c3': dict(w=1920, h=1080, batch=64, ring=2, seed=3,
+               name='batches of synthetic 1920x1080 RGB frames, mark length 1000, embed+extract'),
+}
+# ALGORITHMIC bytes per pixel of one launch over one frame (DESIGN.md "Kernels")
+# how many times one step runs each kernel over a full batch of frames (embed: 1 forward + 1 top-k +
+# 1 inverse; extract: 2 forwards + 1 top-k) -- used to turn "launches per step" into pixels per launch
+PASSES_PER_STEP = {'row_fwd_rgb8': 3, 'col_fwd': 3, 'col_inv': 1, 'row_inv_rgb8': 1, 'topk_hist': 2, 'topk_collect': 2,
+                   'fwd_rows': 3, 'fwd_cols': 3, 'fwd_cols_hist': 3, 'inv_cols': 1, 'inv_rows': 1, 'topk_select': 2}
+ALGO_BYTES_PER_PX = {
+    'row_fwd_rgb8': 7.0,    # 3 B RGB8 in, 4 B coefficient out
+    'col_fwd': 8.0, 'col_inv': 8.0,
+    'row_inv_rgb8': 10.0,   # 4 B coefficient + 3 B original RGB8 in, 3 B RGB8 out
+    'topk_hist': 4.0, 'topk_collect': 4.0,
+    'fwd_rows': 7.0, 'fwd_cols': 8.0, 'fwd_cols_hist': 8.0, 'inv_cols': 8.0, 'inv_rows': 10.0,
+    'topk_select': 4.0,
+}
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def load_traffic():
+    """dram bytes per launch from the committed ncu --set full capture (profiles/), if any"""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'dram_traffic.json')))
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's C restatement (test infrastructure, the checker)
+# ------------------------------------------------------------------------------------------------
+def _oracle_lib():
+    path = os.path.join(ROOT, 'oracle', 'liboracle.so')
+    if not os.path.exists(path):
+        subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle')])
+    lib = ctypes.CDLL(path)
+    return lib
+
+
+def _oracle_step(lib, frame, mark, out, ext):
+    h, w = frame.shape[:2]
+    sim = ctypes.c_float()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = lib.oracle_embed_rgb8(p(frame), w, h, p(mark), ctypes.c_size_t(MARK_LEN), 2, ctypes.c_float(ALPHA), 0,
+                               p(out), None, None, None)
+    rc |= lib.oracle_extract_rgb8(p(frame), p(out), w, h, ctypes.c_size_t(MARK_LEN), 2, ctypes.c_float(ALPHA), 0,
+                                  p(ext), p(mark), ctypes.byref(sim), None)
+    if rc != 0 or not (sim.value > 6.0):
+        raise RuntimeError('oracle step failed (rc %d, sim %r)' % (rc, sim.value))
+    return sim.value
+
+
+def _host_frames(wl, count, first=0):
+    """synthetic frames on the host without a GPU: tile the (slow, numpy) generator's output for a
+    small frame?  No -- frames must be the real workload; generate once per distinct frame."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ssw_oracle as so
+    return [so.synth_frame(wl['w'], wl['h'], wl['seed'], first + i) for i in range(count)]
+
+
+def cpu_baseline(wl, frames, marks, budget_s=25.0):
+    """oracle port on ONE core, bounded sample: whole frames of the workload until ~budget_s"""
+    lib = _oracle_lib()
+    out = np.empty_like(frames[0]); ext = np.empty(MARK_LEN, np.float32)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        _oracle_step(lib, frames[n % len(frames)], marks[n % len(marks)], out, ext)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt * (n + 1) / n > budget_s or n >= 64:
+            break
+    px = n * wl['w'] * wl['h']
+    return {'value': px / dt / 1e6, 'unit': 'Mpix/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d frame(s) of %dx%d embed+extract by oracle/ssw_oracle.c (restated reference, '
+                      'full stable sort), %.1f s' % (n, wl['w'], wl['h'], dt)}
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    lib = _oracle_lib()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    cores = max(1, min(cores, int(os.environ.get('SSW_REF_THREADS', cores)), 64))
+    # frames: generated on the GPU when there is one (bit-identical generator, see tests), else numpy
+    frames = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import spread_spectrum_watermarking_b200 as wm
+            ctx = wm.Context(0)
+            t = torch.empty((2, wl['h'], wl['w'], 3), dtype=torch.uint8, device='cuda:0')
+            wm._lib.check(wm.lib.ssw_synth_frame_rgb8_dev(ctx.handle, wl['w'], wl['h'], wl['seed'], 0, 2, t.data_ptr()))
+            ctx.synchronize()
+            frames = [f.copy() for f in t.cpu().numpy()]
+            ctx.close()
+    except Exception:
+        frames = None
+    if frames is None:
+        frames = _host_frames(wl, 2)
+    rng = np.random.default_rng(1000)
+    marks = [rng.standard_normal(MARK_LEN).astype(np.float32) for _ in range(2)]
+    bufs = [(np.empty_like(frames[0]), np.empty(MARK_LEN, np.float32)) for _ in range(cores)]
+
+    def one_step():
+        errs = []
+
+        def work(i):
+            try:
+                _oracle_step(lib, frames[i % 2], marks[i % 2], *bufs[i])
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return time.perf_counter() - t0
+
+    budget = float(os.environ.get('SSW_REF_BUDGET_S', '200'))
+    t_start = time.perf_counter()
+    est = one_step()  # warm-up step (also the calibration)
+    warm = 1
+    while warm < args.warmup and (time.perf_counter() - t_start) + est * (args.steps + 1) < budget:
+        one_step(); warm += 1
+    times = []
+    for _ in range(args.steps):
+        times.append(one_step())
+        if (time.perf_counter() - t_start) + est > budget:
+            break
+    k = len(times)
+    total = sum(times)
+    px = k * cores * wl['w'] * wl['h']
+    v = px / total / 1e6
+    sample = ('each step = %d frames (one per host thread) of %dx%d embed+extract by the restated reference '
+              '(oracle/ssw_oracle.c, full stable sort); %d of %d requested steps fitted the %.0f s budget'
+              % (cores, wl['w'], wl['h'], k, args.steps, budget))
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': v, 'unit': 'Mpix/s',
+        'n_gpus': args.gpus, 'steps': k, 'warmup': warm, 'ms_per_step': total / k * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': wl['name'], 'frame': [wl['w'], wl['h']], 'mark_len': MARK_LEN, 'alpha': ALPHA,
+                   'frames_per_step': cores},
+        'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import spread_spectrum_watermarking_b200 as wm
+    from spread_spectrum_watermarking_b200._lib import check, lib, ssw_config
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)' % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w, h, B, ring = wl['w'], wl['h'], wl['batch'], wl['ring']
+    npx = w * h
+    stream = torch.cuda.Stream()
+    ctx = wm.Context(local, stream=stream.cuda_stream)
+    cfg = ssw_config(2, ALPHA, 0)
+    pcfg = ctypes.byref(cfg)
+
+    # ---- synthetic inputs, resident in HBM; ring*B distinct frames per rank (> L2 for both workloads)
+    nfr = ring * B
+    frames = torch.empty((nfr, h, w, 3), dtype=torch.uint8, device='cuda')
+    check(lib.ssw_synth_frame_rgb8_dev(ctx.handle, w, h, wl['seed'], rank * nfr, nfr, frames.data_ptr()))
+    rng = np.random.default_rng(1000 + rank)
+    marks_h = rng.standard_normal((nfr, MARK_LEN)).astype(np.float32)
+    marks = torch.from_numpy(marks_h).cuda()
+    outs = torch.empty_like(frames)
+    ext = torch.empty((nfr, MARK_LEN), dtype=torch.float32, device='cuda')
+    sim = torch.zeros((nfr,), dtype=torch.float32, device='cuda')
+    ctx.synchronize()
+    fb = npx * 3  # bytes per frame
+
+    def embed(s):
+        o = (s % ring) * B
+        check(lib.ssw_embed_batch_rgb8_dev(ctx.handle, frames.data_ptr() + o * fb, w, h, B, pcfg,
+                                           marks.data_ptr() + o * MARK_LEN * 4, MARK_LEN, outs.data_ptr() + o * fb))
+
+    def extract(s):
+        o = (s % ring) * B
+        check(lib.ssw_extract_batch_rgb8_dev(ctx.handle, frames.data_ptr() + o * fb, outs.data_ptr() + o * fb, w, h, B, pcfg,
+                                             MARK_LEN, ext.data_ptr() + o * MARK_LEN * 4, marks.data_ptr() + o * MARK_LEN * 4,
+                                             sim.data_ptr() + o * 4))
+
+    def step(s):
+        embed(s); extract(s)
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(steps):
+            fn(warmup + s)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    K, W = args.steps, max(args.warmup, 3)
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count
+    ms_total = timed(step, K, W)
+    launches = (ctx.launch_count - l0) * K // (K + W)
+    clk = clocks.stop() if rank == 0 else None
+    ms_embed = timed(embed, K, 1)
+    ms_extract = timed(extract, K, 1)
+    fallbacks = ctx.last_topk_fallbacks()
+    sims = sim.cpu().numpy()[:min(nfr, (K + W) * B)]
+    if not (sims > 6.0).all() or fallbacks:
+        raise SystemExit('bench: extraction failed to detect the embedded marks (min sim %.2f, fallbacks %d)'
+                         % (float(sims.min()), fallbacks))
+    px_step = B * npx
+    value = world * px_step * K / (ms_total * 1e-3) / 1e6
+
+    # ---- per-kernel attribution (same steps, CUDA events around every launch on the library's stream)
+    barrier()
+    ctx.profile_begin()
+    for s in range(K):
+        step(W + s)
+    prof = ctx.profile_end()
+    peak, peak_src = load_peaks()
+    traffic = load_traffic()
+    kernels = []
+    for name, r in prof.items():
+        avg_us = r['ms'] / r['launches'] * 1e3
+        bpp = ALGO_BYTES_PER_PX.get(name)
+        ent = {'name': name, 'launches_per_step': r['launches'] / K, 'avg_us': round(avg_us, 2),
+               'share': 0.0, 'algo_bytes': None, 'gbs': None, 'frac': None}
+        if bpp:
+            ab = bpp * px_step * PASSES_PER_STEP.get(name, 1) * K / r['launches']   # bytes of ONE launch
+            ent.update(algo_bytes=ab, gbs=round(ab / (avg_us * 1e-6) / 1e9, 1), frac=round(ab / (avg_us * 1e-6) / 1e9 / peak, 4))
+        kernels.append(ent)
+    tot = sum(r['ms'] for r in prof.values()) or 1.0
+    for ent in kernels:
+        ent['share'] = round(prof[ent['name']]['ms'] / tot, 4)
+    kernels.sort(key=lambda e: -e['share'])
+    dom = next((e for e in kernels if e['frac'] is not None), None)
+    roofline = None
+    if dom:
+        roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': dom['frac'], 'traffic': traffic.get(dom['name']), 'peak_source': peak_src,
+                    'algo_bytes_per_launch': dom['algo_bytes'], 'avg_launch_us': dom['avg_us'], 'share_of_step': dom['share']}
+    step_algo = {'embed_bytes_per_px': 53.0, 'extract_bytes_per_px': 50.0}
+    whole = {'embed_gbs': round(53.0 * px_step * K / (ms_embed * 1e-3) / 1e9, 1),
+             'extract_gbs': round(50.0 * px_step * K / (ms_extract * 1e-3) / 1e9, 1)}
+    whole['embed_frac'] = round(whole['embed_gbs'] / peak, 4)
+    whole['extract_frac'] = round(whole['extract_gbs'] / peak, 4)
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory; H2D + D2H inside the timed region)
+    def pinned(nbytes, dtype, shape):
+        p = ctypes.c_void_p()
+        check(lib.ssw_host_alloc(nbytes, ctypes.byref(p)))
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+    e2e_ring = min(ring, 2)
+    hf, _p1 = pinned(e2e_ring * B * fb, np.uint8, (e2e_ring, B, h, w, 3))
+    ho, _p2 = pinned(e2e_ring * B * fb, np.uint8, (e2e_ring, B, h, w, 3))
+    hm, _p3 = pinned(e2e_ring * B * MARK_LEN * 4, np.float32, (e2e_ring, B, MARK_LEN))
+    he, _p4 = pinned(B * MARK_LEN * 4, np.float32, (B, MARK_LEN))
+    hs, _p5 = pinned(max(B * 4, 64), np.float32, (max(B, 16),))
+    hf[...] = frames[:e2e_ring * B].cpu().numpy().reshape(hf.shape)
+    hm[...] = marks_h[:e2e_ring * B].reshape(hm.shape)
+
+    def e2e_step(s):
+        r = s % e2e_ring
+        check(lib.ssw_embed_batch_rgb8(ctx.handle, hf[r].ctypes.data, w, h, B, pcfg, hm[r].ctypes.data, MARK_LEN, ho[r].ctypes.data))
+        check(lib.ssw_extract_batch_rgb8(ctx.handle, hf[r].ctypes.data, ho[r].ctypes.data, w, h, B, pcfg, MARK_LEN,
+                                         he.ctypes.data, hm[r].ctypes.data, hs.ctypes.data))
+
+    Ke = max(3, min(K, 20))
+    for s in range(3):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        e2e_step(3 + s)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    if not (hs[:B] > 6.0).all():
+        raise SystemExit('bench: e2e extraction failed to detect the embedded marks')
+    e2e = {'value': world * px_step * Ke / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s',
+           'h2d_bytes_per_step': B * (3 * fb + 2 * MARK_LEN * 4), 'd2h_bytes_per_step': B * (fb + MARK_LEN * 4 + 4),
+           'steps': Ke, 'ms_per_step': e2e_ms / Ke,
+           'api': 'ssw_embed_batch_rgb8 + ssw_extract_batch_rgb8 (pinned host buffers)'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        f0 = [frames[i].cpu().numpy() for i in range(min(2, nfr))]
+        cpu = cpu_baseline(wl, f0, [marks_h[i] for i in range(len(f0))])
+
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'frame': [w, h], 'frames_per_step': B, 'mark_len': MARK_LEN, 'alpha': ALPHA,
+                       'insertion': 'Option2', 'ordering': 'Energy',
+                       'l2': 'inputs larger than L2: ring of %d distinct frames (%.0f MB in + %.0f MB out per rank)'
+                             % (nfr, nfr * fb / 1e6, nfr * fb / 1e6),
+                       'parallelism': 'independent frames per GPU, no collective'},
+            'embed_mpix_s': world * px_step * K / (ms_embed * 1e-3) / 1e6,
+            'extract_mpix_s': world * px_step * K / (ms_extract * 1e-3) / 1e6,
+            'roofline': roofline, 'kernels': kernels, 'whole_step': dict(step_algo, **whole),
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk,
+            'min_similarity': float(sims.min()),
+        }), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        return run_reference(args, wl)
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:  # convenience: re-launch under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+               '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29533')] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, wl)
+
+
+if __name__ == '__main__':
+    main()

@@ -66,6 +66,11 @@ int ssw_ctx_synchronize(ssw_ctx* ctx);
 void* ssw_ctx_stream(ssw_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 uint64_t ssw_ctx_launch_count(ssw_ctx* ctx);
+/* per-kernel timing: between _begin and _end every kernel launch of this context is bracketed by
+ * CUDA events on the context's stream; _end writes {"kernel": {"launches": n, "ms": total}, ...}
+ * as JSON text into `json_out` (bench.py's roofline attribution). */
+int ssw_ctx_profile_begin(ssw_ctx* ctx);
+int ssw_ctx_profile_end(ssw_ctx* ctx, char* json_out, size_t cap);
 /* tuning knobs: line pairs per CTA tile for the row / column passes (0 = automatic) */
 int ssw_ctx_set_tiling(ssw_ctx* ctx, int row_pairs, int col_pairs);
 

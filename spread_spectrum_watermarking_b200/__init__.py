@@ -59,6 +59,16 @@ class Context:
     def launch_count(self):
         return int(lib.ssw_ctx_launch_count(self.handle))
 
+    def profile_begin(self):
+        check(lib.ssw_ctx_profile_begin(self.handle))
+
+    def profile_end(self):
+        """-> {kernel name: {'launches': n, 'ms': total}} for the launches since profile_begin()"""
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(lib.ssw_ctx_profile_end(self.handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def set_tiling(self, row_pairs=0, col_pairs=0):
         check(lib.ssw_ctx_set_tiling(self.handle, int(row_pairs), int(col_pairs)))
 

@@ -53,6 +53,8 @@ SIGNATURES = {
     'ssw_ctx_synchronize': (c_int, [_p]),
     'ssw_ctx_stream': (c_void_p, [_p]),
     'ssw_ctx_launch_count': (c_uint64, [_p]),
+    'ssw_ctx_profile_begin': (c_int, [_p]),
+    'ssw_ctx_profile_end': (c_int, [_p, c_char_p, c_size_t]),
     'ssw_ctx_set_tiling': (c_int, [_p, c_int, c_int]),
     'ssw_host_alloc': (c_int, [c_size_t, _pp]),
     'ssw_host_free': (c_int, [_p]),

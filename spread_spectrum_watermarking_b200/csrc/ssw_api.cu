@@ -66,6 +66,33 @@ struct ssw_ctx {
     unsigned* h_flag = nullptr;  // pinned
     int last_fallbacks = 0;
     size_t chunk_bytes = 96u << 20;  // planes of one fused sub-batch are sized to stay L2-resident
+    // per-kernel CUDA-event profiling (bench.py roofline attribution); off by default
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+// Counts a kernel launch and, when profiling is on, brackets it with CUDA events on the context's
+// stream (the stream the kernel is launched on).
+struct KScope {
+    ssw_ctx* c;
+    cudaEvent_t b = nullptr;
+    KScope(ssw_ctx* ctx, const char* name, int n_launch = 1) : c(ctx) {
+        c->launches += (uint64_t)n_launch;
+        if (!c->profiling) return;
+        while (c->ev_pool.size() < c->ev_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            c->ev_pool.push_back(e);
+        }
+        cudaEvent_t a = c->ev_pool[c->ev_used++];
+        b = c->ev_pool[c->ev_used++];
+        cudaEventRecord(a, c->stream);
+        c->prof.push_back({name, a, b});
+    }
+    ~KScope() { if (b) cudaEventRecord(b, c->stream); }
 };
 
 static int ctx_bind(ssw_ctx* c) {
@@ -127,6 +154,7 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     topk_scratch_free(c);
     c->general.release();
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SSW_OK;
@@ -144,6 +172,46 @@ extern "C" int ssw_ctx_set_tiling(ssw_ctx* c, int row_pairs, int col_pairs) {
     if (!c || row_pairs < 0 || col_pairs < 0) return fail(SSW_ERR_INVALID, "bad tiling");
     c->row_pairs = row_pairs;
     c->col_pairs = col_pairs;
+    return SSW_OK;
+}
+
+extern "C" int ssw_ctx_profile_begin(ssw_ctx* c) {
+    if (!c) return fail(SSW_ERR_INVALID, "ctx is NULL");
+    CKS(ctx_bind(c));
+    CK(cudaStreamSynchronize(c->stream));
+    c->prof.clear();
+    c->ev_used = 0;
+    c->profiling = true;
+    return SSW_OK;
+}
+
+extern "C" int ssw_ctx_profile_end(ssw_ctx* c, char* json_out, size_t cap) {
+    if (!c || !json_out || cap < 3) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(c));
+    c->profiling = false;
+    CK(cudaStreamSynchronize(c->stream));
+    std::map<std::string, std::pair<uint64_t, double>> agg;  // name -> (launches, ms)
+    for (const auto& r : c->prof) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, r.a, r.b));
+        auto& e = agg[r.name];
+        e.first += 1;
+        e.second += (double)ms;
+    }
+    c->prof.clear();
+    c->ev_used = 0;
+    std::string js = "{";
+    bool first = true;
+    for (const auto& kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+                 (unsigned long long)kv.second.first, kv.second.second);
+        js += tmp;
+        first = false;
+    }
+    js += "}";
+    if (js.size() + 1 > cap) return fail(SSW_ERR_INVALID, "profile buffer too small");
+    std::memcpy(json_out, js.c_str(), js.size() + 1);
     return SSW_OK;
 }
 
@@ -211,7 +279,7 @@ static int pick_tiling(ssw_ctx* c, const DctPlanDev& pl, bool column, int lines,
 }
 
 template <class K>
-static int launch_line(ssw_ctx* c, K kernel, const LineArgs& a, const Tiling& t, long long tiles) {
+static int launch_line(ssw_ctx* c, const char* name, K kernel, const LineArgs& a, const Tiling& t, long long tiles) {
     const void* key = (const void*)kernel;
     auto it = c->smem_attr.find(key);
     if (it == c->smem_attr.end() || it->second < (int)t.smem) {
@@ -219,9 +287,11 @@ static int launch_line(ssw_ctx* c, K kernel, const LineArgs& a, const Tiling& t,
         c->smem_attr[key] = (int)t.smem;
     }
     if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
-    kernel<<<(unsigned)tiles, t.threads, t.smem, c->stream>>>(a);
+    {
+        KScope ks(c, name);
+        kernel<<<(unsigned)tiles, t.threads, t.smem, c->stream>>>(a);
+    }
     CK(cudaGetLastError());
-    c->launches++;
     return SSW_OK;
 }
 
@@ -256,11 +326,11 @@ static int run_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h
     }
     const long long ntr = (long long)ar.tiles_per_image * batch, ntc = (long long)ac.tiles_per_image * batch;
     switch (src_type) {
-        case PIX_RGB8: CKS(launch_line(c, row_fwd_kernel<PIX_RGB8>, ar, tr, ntr)); break;
-        case PIX_RGB32F: CKS(launch_line(c, row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr)); break;
-        default: CKS(launch_line(c, row_fwd_kernel<PIX_PLANE>, ar, tr, ntr)); break;
+        case PIX_RGB8: CKS(launch_line(c, "row_fwd_rgb8", row_fwd_kernel<PIX_RGB8>, ar, tr, ntr)); break;
+        case PIX_RGB32F: CKS(launch_line(c, "row_fwd_rgb32f", row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr)); break;
+        default: CKS(launch_line(c, "row_fwd_plane", row_fwd_kernel<PIX_PLANE>, ar, tr, ntr)); break;
     }
-    CKS(launch_line(c, col_fwd_kernel, ac, tc, ntc));
+    CKS(launch_line(c, "col_fwd", col_fwd_kernel, ac, tc, ntc));
     return SSW_OK;
 }
 
@@ -282,12 +352,12 @@ static int run_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_s
     ar.scale0 = 4.0f / (float)((size_t)w * (size_t)h);  // src/dct2d.rs:213-217
     ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
     const long long ntr = (long long)ar.tiles_per_image * batch, ntc = (long long)ac.tiles_per_image * batch;
-    CKS(launch_line(c, col_inv_kernel, ac, tc, ntc));
-    if (dst_type == PIX_PLANE) return launch_line(c, row_inv_kernel<PIX_PLANE, PIX_PLANE>, ar, tr, ntr);
-    if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) return launch_line(c, row_inv_kernel<PIX_RGB8, PIX_RGB8>, ar, tr, ntr);
-    if (dst_type == PIX_RGB8 && src_type == PIX_RGB32F) return launch_line(c, row_inv_kernel<PIX_RGB8, PIX_RGB32F>, ar, tr, ntr);
-    if (dst_type == PIX_RGB32F && src_type == PIX_RGB8) return launch_line(c, row_inv_kernel<PIX_RGB32F, PIX_RGB8>, ar, tr, ntr);
-    if (dst_type == PIX_RGB32F && src_type == PIX_RGB32F) return launch_line(c, row_inv_kernel<PIX_RGB32F, PIX_RGB32F>, ar, tr, ntr);
+    CKS(launch_line(c, "col_inv", col_inv_kernel, ac, tc, ntc));
+    if (dst_type == PIX_PLANE) return launch_line(c, "row_inv_plane", row_inv_kernel<PIX_PLANE, PIX_PLANE>, ar, tr, ntr);
+    if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) return launch_line(c, "row_inv_rgb8", row_inv_kernel<PIX_RGB8, PIX_RGB8>, ar, tr, ntr);
+    if (dst_type == PIX_RGB8 && src_type == PIX_RGB32F) return launch_line(c, "row_inv_rgb8_src32f", row_inv_kernel<PIX_RGB8, PIX_RGB32F>, ar, tr, ntr);
+    if (dst_type == PIX_RGB32F && src_type == PIX_RGB8) return launch_line(c, "row_inv_rgb32f_src8", row_inv_kernel<PIX_RGB32F, PIX_RGB8>, ar, tr, ntr);
+    if (dst_type == PIX_RGB32F && src_type == PIX_RGB32F) return launch_line(c, "row_inv_rgb32f", row_inv_kernel<PIX_RGB32F, PIX_RGB32F>, ar, tr, ntr);
     return fail(SSW_ERR_INVALID, "bad pixel type combination");
 }
 
@@ -337,10 +407,9 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         TopkScratch ts = c->ts;
         ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0;
         ts.cand += (size_t)b0 * kTopkCap;
-        topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
-        topk_collect_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, oc, ts);
+        { KScope ks(c, "topk_hist"); topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts); }
+        { KScope ks(c, "topk_collect"); topk_collect_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, oc, ts); }
         CK(cudaGetLastError());
-        c->launches += 2;
     }
     const void* key = (const void*)topk_sort_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
@@ -348,9 +417,8 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    topk_sort_kernel<<<batch, 1024, smem, c->stream>>>(c->ts, k, d_idx, idx_stride);
+    { KScope ks(c, "topk_sort"); topk_sort_kernel<<<batch, 1024, smem, c->stream>>>(c->ts, k, d_idx, idx_stride); }
     CK(cudaGetLastError());
-    c->launches++;
     return SSW_OK;
 }
 
@@ -380,7 +448,8 @@ static int run_topk_exact(ssw_ctx* c, const float* d_plane, int w, int h, int or
         c->last_fallbacks += 1;
     }
     const OrderConsts oc = make_order(ordering, w, h);
-    int rc = c->general.run(c->stream, d_plane, (unsigned)n, oc, k, d_idx, &c->launches);
+    int rc;
+    { KScope ks(c, "general_select", 0); rc = c->general.run(c->stream, d_plane, (unsigned)n, oc, k, d_idx, &c->launches); }
     if (rc != SSW_OK) return fail(rc, c->general.error);
     return SSW_OK;
 }
@@ -434,8 +503,7 @@ extern "C" int ssw_rgb32f_to_yiq(ssw_ctx* c, const float* rgb, uint32_t w, uint3
     CK(cudaMallocAsync(&d, np * 6 * sizeof(float), c->stream));
     CK(cudaMemcpyAsync(d, rgb, np * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     float* dy = d + 3 * np;
-    rgb32f_to_yiq_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, np, dy, dy + np, dy + 2 * np);
-    c->launches++;
+    { KScope ks(c, "rgb32f_to_yiq"); rgb32f_to_yiq_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, np, dy, dy + np, dy + 2 * np); }
     CK(cudaMemcpyAsync(y, dy, np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(i, dy + np, np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(q, dy + 2 * np, np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -454,8 +522,7 @@ extern "C" int ssw_yiq_to_rgb32f(ssw_ctx* c, const float* y, const float* i, con
     CK(cudaMemcpyAsync(d, y, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d + np, i, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d + 2 * np, q, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    yiq_to_rgb32f_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, d + np, d + 2 * np, np, d + 3 * np);
-    c->launches++;
+    { KScope ks(c, "yiq_to_rgb32f"); yiq_to_rgb32f_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, d + np, d + 2 * np, np, d + 3 * np); }
     CK(cudaMemcpyAsync(rgb, d + 3 * np, np * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaFreeAsync(d, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -571,11 +638,13 @@ extern "C" int ssw_writer_embed(ssw_writer* wr, const float* const* marks, const
     CK(cudaMallocAsync(&d_lens, n_marks * sizeof(unsigned), c->stream));
     CK(cudaMemcpyAsync(d_marks, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_lens, hl.data(), n_marks * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
-    embed_scatter_kernel<<<dim3((unsigned)((kmax + 255) / 256), 1), 256, 0, c->stream>>>(
-        wr->d_plane, 0, wr->d_idx, 0, (unsigned)kmax, d_marks, (long long)kmax, (int)n_marks, d_lens,
-        wr->cfg.method, wr->cfg.alpha);
+    {
+        KScope ks(c, "embed_scatter");
+        embed_scatter_kernel<<<dim3((unsigned)((kmax + 255) / 256), 1), 256, 0, c->stream>>>(
+            wr->d_plane, 0, wr->d_idx, 0, (unsigned)kmax, d_marks, (long long)kmax, (int)n_marks, d_lens,
+            wr->cfg.method, wr->cfg.alpha);
+    }
     CK(cudaGetLastError());
-    c->launches++;
     CK(cudaFreeAsync(d_marks, c->stream));
     CK(cudaFreeAsync(d_lens, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // `stage` / `hl` are pageable host memory
@@ -727,10 +796,12 @@ static int reader_extract(ssw_reader* base, ssw_reader* derived, float* out, siz
     CKS(ensure_indices(c, base->d_plane, base->w, base->h, base->cfg.ordering, n, &base->d_idx, &base->k_cached));
     float* d_out = out;
     if (!out_on_device) CK(cudaMallocAsync(&d_out, n * sizeof(float), c->stream));
-    extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream>>>(
-        base->d_plane, derived->d_plane, 0, base->d_idx, 0, (unsigned)n, base->cfg.method, base->cfg.alpha, d_out, 0);
+    {
+        KScope ks(c, "extract_gather");
+        extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream>>>(
+            base->d_plane, derived->d_plane, 0, base->d_idx, 0, (unsigned)n, base->cfg.method, base->cfg.alpha, d_out, 0);
+    }
     CK(cudaGetLastError());
-    c->launches++;
     if (!out_on_device) {
         CK(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaFreeAsync(d_out, c->stream));
@@ -786,10 +857,12 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
     if (n_marks == 0 || n_ext == 0) return SSW_OK;
     const size_t gx = (n_marks + kSimMarks - 1) / kSimMarks;
     if (gx > 0x7FFFFFFFull || n_ext > 65535 || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
-    similarity_bank_kernel<<<dim3((unsigned)gx, pair_mode ? 1u : (unsigned)n_ext), kSimMarks, 0, c->stream>>>(
-        d_bank, n_marks, (unsigned)n, d_ext, (long long)n, pair_mode ? 1 : 0, d_out, (long long)n_marks);
+    {
+        KScope ks(c, pair_mode ? "similarity_pairs" : "similarity_bank");
+        similarity_bank_kernel<<<dim3((unsigned)gx, pair_mode ? 1u : (unsigned)n_ext), kSimMarks, 0, c->stream>>>(
+            d_bank, n_marks, (unsigned)n, d_ext, (long long)n, pair_mode ? 1 : 0, d_out, (long long)n_marks);
+    }
     CK(cudaGetLastError());
-    c->launches++;
     return SSW_OK;
 }
 
@@ -817,9 +890,8 @@ static int fill_normal(ssw_ctx* c, float* d_out, size_t n, uint64_t seed) {
         if (seed == 0) seed = 0x9E3779B97F4A7C15ull;
     }
     const size_t quads = (n + 3) / 4;
-    normal_fill_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, c->stream>>>(d_out, n, seed, 0ull);
+    { KScope ks(c, "normal_fill"); normal_fill_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, c->stream>>>(d_out, n, seed, 0ull); }
     CK(cudaGetLastError());
-    c->launches++;
     return SSW_OK;
 }
 
@@ -934,10 +1006,10 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
         if (rc == SSW_OK && k) {
             rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k);
             if (rc == SSW_OK) {
+                KScope ks(c, "embed_scatter");
                 embed_scatter_kernel<<<dim3((unsigned)((k + 255) / 256), nb), 256, 0, c->stream>>>(
                     d_planes, (long long)np, d_idx, (long long)k, (unsigned)k, marks + (size_t)b0 * n, (long long)n, 1,
                     nullptr, cfg->method, cfg->alpha);
-                c->launches++;
             }
         }
         if (rc == SSW_OK) rc = run_inverse(c, d_planes, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3);
@@ -974,10 +1046,12 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
         if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n);
         if (rc == SSW_OK) {
-            extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, c->stream>>>(
-                pb, pd, (long long)np, d_idx, (long long)n, (unsigned)n, cfg->method, cfg->alpha,
-                extracted + (size_t)b0 * n, (long long)n);
-            c->launches++;
+            {
+                KScope ks(c, "extract_gather");
+                extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, c->stream>>>(
+                    pb, pd, (long long)np, d_idx, (long long)n, (unsigned)n, cfg->method, cfg->alpha,
+                    extracted + (size_t)b0 * n, (long long)n);
+            }
             if (sim) rc = launch_similarity(c, marks + (size_t)b0 * n, nb, n, extracted + (size_t)b0 * n, nb, true, sim + b0);
         }
     }
@@ -1073,9 +1147,8 @@ extern "C" int ssw_synth_frame_rgb8_dev(ssw_ctx* c, uint32_t w, uint32_t h, uint
     CKS(ctx_bind(c));
     for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
         const uint32_t nb = std::min<uint32_t>(65535, n_images - i0);
-        synth_frame_kernel<<<dim3((w + 127) / 128, h, nb), 128, 0, c->stream>>>(out + (size_t)i0 * w * h * 3, w, h, seed, first_image + i0);
+        { KScope ks(c, "synth_frame"); synth_frame_kernel<<<dim3((w + 127) / 128, h, nb), 128, 0, c->stream>>>(out + (size_t)i0 * w * h * 3, w, h, seed, first_image + i0); }
         CK(cudaGetLastError());
-        c->launches++;
     }
     return SSW_OK;
 }
