@@ -1,0 +1,486 @@
+// Compile-time planned line kernels of the full-frame separable DCT ("fast path").
+//
+// Same arithmetic as dct_kernels.cuh (two real lines packed into one complex Stockham FFT, Makhoul
+// reordering, twiddle post/pre pass -- replaces /root/reference/src/dct2d.rs:129-206 and the rustdct
+// calls at :141-145,181-185, with the colour conversion of /root/reference/src/yiq.rs:177-197 fused
+// into the row passes), but the radix plan, the thread shape and every shared-memory offset are
+// template constants:
+//   * no padding for lengths with an odd first radix (its stride-R first-stage stores are conflict
+//     free), `a + a/16` padding for powers of two;
+//   * butterfly operands are addressed as base + immediate, twiddles as one coalesced __ldg each;
+//   * 128-bit global accesses: 4 pixels (12 B of RGB8, or a float4 of the plane) per thread and row.
+// The generic kernels stay as the fallback for every other length (e.g. 444 = 4*3*37).
+//
+// Every kernel is written as a sequence of barrier-separated PHASES over a per-thread register
+// state, `K::phase<PH>(args, smem, tile, tid, state)`.  The __global__ wrapper runs the phases with
+// __syncthreads() between them; tests/emul runs the very same phase functions on the CPU, one
+// thread after the other, so the index arithmetic is verified without a GPU.
+#pragma once
+#include "dct_kernels.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define SSW_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+#include <cmath>
+#define SSW_FMA(a, b, c) std::fmaf((a), (b), (c))
+#endif
+
+namespace ssw {
+namespace fast {
+
+struct FastArgs {
+    int w, h;            // frame size
+    const void* src;     // row_fwd: pixels / plane; row_inv (RGB8): original pixels for I,Q
+    float* plane;        // coefficient plane [h][w]
+    void* dst;           // row_inv destination
+    long long src_stride, plane_stride, dst_stride;  // per-image strides in pixels
+    int tiles_per_image;
+    float scale0, scalen;  // forward: factors for k == 0 / k > 0; inverse: scale0 = output scale
+    const cplx* tw;        // stage twiddles of the plan, layout per stage [r-1][k]
+    const cplx* t4;        // exp(-i*pi*k/(2N)), k < N
+};
+
+// ------------------------------------------------------------------------------------------------
+// plan: N = R0*R1*R2*R3 (unused trailing radices = 1), T threads cooperate on one line pair
+// ------------------------------------------------------------------------------------------------
+template <int N_, int T_, int R0_, int R1_, int R2_ = 1, int R3_ = 1>
+struct Plan {
+    static constexpr int N = N_, T = T_;
+    static constexpr int NST = R3_ > 1 ? 4 : (R2_ > 1 ? 3 : 2);
+    static_assert(R0_ * R1_ * R2_ * R3_ == N_, "radices must multiply to N");
+    static_assert(N_ % 4 == 0, "fast path needs N % 4 == 0 (4 pixels per thread)");
+    static_assert(T_ % 32 == 0, "whole warps per team");
+    static constexpr int radix(int s) { return s == 0 ? R0_ : s == 1 ? R1_ : s == 2 ? R2_ : R3_; }
+    static constexpr int ns(int s) { int p = 1; for (int i = 0; i < s; ++i) p *= radix(i); return p; }
+    static constexpr int tw_off(int s) { int o = 0; for (int i = 1; i < s; ++i) o += (radix(i) - 1) * ns(i); return o; }
+    static constexpr int TW_TOTAL = tw_off(NST);
+    static constexpr bool PAD = (R0_ % 2) == 0;
+    static SSW_HD int idx(int a) { return PAD ? a + (a >> 4) : a; }
+    static constexpr int LINE = PAD ? N_ + (N_ >> 4) : N_;
+    // pitch between the line pairs of one CTA (float2 units): even (16-byte alignment), == 4 mod 16
+    static constexpr int PITCH = LINE + ((4 - LINE % 16) + 16) % 16;
+};
+
+template <class P, int S>
+struct StageInfo {
+    static constexpr int R = P::radix(S), NS = P::ns(S), NB = P::N / R;
+    // blocks of 15 butterflies: give each block its own half-warp so no access straddles two blocks
+    static constexpr bool MAP16 = (NS == 15) && (NB > 15);
+    static constexpr int SLOTS = MAP16 ? (NB / 15) * 16 : NB;
+    static constexpr int ITER = (SLOTS + P::T - 1) / P::T;
+    static constexpr bool GUARD = (ITER * P::T != SLOTS);
+    static constexpr int TW = P::tw_off(S);
+};
+
+template <class P, int S = 0>
+struct MaxRegs {
+    static constexpr int here = (S < P::NST) ? StageInfo<P, S>::ITER * StageInfo<P, S>::R : 0;
+    static constexpr int rest = MaxRegs<P, S + 1>::value;
+    static constexpr int value = here > rest ? here : rest;
+};
+template <class P>
+struct MaxRegs<P, 4> { static constexpr int value = 0; };
+
+template <class P, int S>
+SSW_HD bool stage_map(int t, int it, int& j, int& k) {
+    using I = StageInfo<P, S>;
+    const int slot = t + it * P::T;
+    if constexpr (I::MAP16) {
+        const int blk = slot >> 4;
+        k = slot & 15;
+        j = blk * 15 + k;
+        return (k < 15) && (!I::GUARD || slot < I::SLOTS);
+    } else {
+        j = slot;
+        k = (I::NS == 1) ? 0 : ((I::NS >= I::NB) ? j : j % I::NS);
+        return !I::GUARD || slot < I::SLOTS;
+    }
+}
+
+template <class P, int S>
+SSW_HD void stage_load(const cplx* s, int t, cplx* v) {
+    using I = StageInfo<P, S>;
+#pragma unroll
+    for (int it = 0; it < I::ITER; ++it) {
+        int j, k;
+        if (stage_map<P, S>(t, it, j, k)) {
+#pragma unroll
+            for (int r = 0; r < I::R; ++r) v[it * I::R + r] = s[P::idx(j + r * I::NB)];
+        }
+    }
+}
+
+template <class P, int S>
+SSW_HD void stage_store(cplx* s, const cplx* tw, int t, cplx* v) {
+    using I = StageInfo<P, S>;
+#pragma unroll
+    for (int it = 0; it < I::ITER; ++it) {
+        int j, k;
+        if (stage_map<P, S>(t, it, j, k)) {
+            cplx* x = v + it * I::R;
+            if constexpr (I::NS > 1) {
+                const cplx* twk = tw + I::TW + k;
+#pragma unroll
+                for (int r = 1; r < I::R; ++r) x[r] = cmul(x[r], SSW_LDG(twk + (r - 1) * I::NS));
+            }
+            Dft<I::R>::run(x);
+            const int j0 = (j - k) * I::R + k;
+#pragma unroll
+            for (int r = 0; r < I::R; ++r) s[P::idx(j0 + r * I::NS)] = x[r];
+        }
+    }
+}
+
+// phases 1 .. 2*NST of every kernel: the FFT of the team's line pair
+template <class P, int PH>
+SSW_HD void fft_phase(cplx* s, const cplx* tw, int t, cplx* v) {
+    constexpr int S = (PH - 1) / 2;
+    if constexpr (((PH - 1) & 1) == 0) stage_load<P, S>(s, t, v);
+    else stage_store<P, S>(s, tw, t, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// colour helpers (bit-identical to color.cuh; the division by 255 is replaced by an exact
+// multiply + two fused corrections -- verified for all 256 inputs by the CPU test-suite)
+// ------------------------------------------------------------------------------------------------
+SSW_HD float u8_unit(unsigned v) {
+    const float x = (float)v;
+    const float c = 0.0039215688593685626983642578125f;  // fl32(1/255)
+    const float q = SSW_FMUL(x, c);
+    const float rem = SSW_FMA(-q, 255.0f, x);
+    return SSW_FMA(rem, c, q);
+}
+
+SSW_HD void unpack4(unsigned w0, unsigned w1, unsigned w2, unsigned* b) {
+    b[0] = w0 & 255u; b[1] = (w0 >> 8) & 255u; b[2] = (w0 >> 16) & 255u; b[3] = w0 >> 24;
+    b[4] = w1 & 255u; b[5] = (w1 >> 8) & 255u; b[6] = (w1 >> 16) & 255u; b[7] = w1 >> 24;
+    b[8] = w2 & 255u; b[9] = (w2 >> 8) & 255u; b[10] = (w2 >> 16) & 255u; b[11] = w2 >> 24;
+}
+
+// luma of 4 consecutive RGB8 pixels (12 bytes, 4-byte aligned)
+SSW_HD void luma4_rgb8(const unsigned* p, float* y) {
+    unsigned b[12];
+    unpack4(SSW_LDG(p), SSW_LDG(p + 1), SSW_LDG(p + 2), b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+}
+
+// 4 pixels: new luma y[4] + chroma of the original RGB8 pixels -> RGB8 (12 bytes)
+SSW_HD void recolour4_rgb8(const unsigned* src, const float* y, unsigned* dst) {
+    unsigned b[12], o[12];
+    unpack4(SSW_LDG(src), SSW_LDG(src + 1), SSW_LDG(src + 2), b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float r = u8_unit(b[3 * i]), g = u8_unit(b[3 * i + 1]), bl = u8_unit(b[3 * i + 2]);
+        const float ci = rgb_to_i(r, g, bl), cq = rgb_to_q(r, g, bl);
+        float ro, go, bo;
+        yiq_to_rgb(y[i], ci, cq, ro, go, bo);
+        o[3 * i] = unit_to_u8(ro); o[3 * i + 1] = unit_to_u8(go); o[3 * i + 2] = unit_to_u8(bo);
+    }
+    dst[0] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    dst[1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+    dst[2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);
+}
+
+struct f4 { float a, b, c, d; };  // 16-byte vector for host + device
+SSW_HD f4 ld4(const float* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    return f4{v.x, v.y, v.z, v.w};
+#else
+    return f4{p[0], p[1], p[2], p[3]};
+#endif
+}
+SSW_HD void st4(float* p, float a, float b, float c, float d) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+#else
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+
+// FFT-input positions of 4 consecutive samples m = 4u..4u+3 (Makhoul): 2u, N-1-2u, 2u+1, N-2-2u.
+// scatter (a_i, b_i) = sample i of line A / line B
+template <class P>
+SSW_HD void put4(cplx* s, int u, const float* a, const float* b) {
+    if constexpr (!P::PAD) {
+        st4(&s[2 * u].x, a[0], b[0], a[2], b[2]);
+        st4(&s[P::N - 2 - 2 * u].x, a[3], b[3], a[1], b[1]);
+    } else {
+        s[P::idx(2 * u)] = mk(a[0], b[0]);
+        s[P::idx(2 * u + 1)] = mk(a[2], b[2]);
+        s[P::idx(P::N - 2 - 2 * u)] = mk(a[3], b[3]);
+        s[P::idx(P::N - 1 - 2 * u)] = mk(a[1], b[1]);
+    }
+}
+template <class P>
+SSW_HD void get4(const cplx* s, int u, cplx* f) {  // f[i] = FFT value belonging to sample 4u+i
+    if constexpr (!P::PAD) {
+        const f4 lo = ld4(&s[2 * u].x), hi = ld4(&s[P::N - 2 - 2 * u].x);
+        f[0] = mk(lo.a, lo.b); f[2] = mk(lo.c, lo.d); f[3] = mk(hi.a, hi.b); f[1] = mk(hi.c, hi.d);
+    } else {
+        f[0] = s[P::idx(2 * u)]; f[2] = s[P::idx(2 * u + 1)];
+        f[3] = s[P::idx(P::N - 2 - 2 * u)]; f[1] = s[P::idx(P::N - 1 - 2 * u)];
+    }
+}
+
+template <class P>
+struct ThreadState { cplx v[MaxRegs<P>::value]; };
+
+// ------------------------------------------------------------------------------------------------
+// forward row pass: pixels / plane rows -> luma -> DCT-II along x -> coefficient plane
+// tile = G row pairs; team g (T threads) owns rows 2*(tile*G+g), +1
+// ------------------------------------------------------------------------------------------------
+template <class P_, int G_, int SRC_>
+struct RowFwd {
+    using P = P_;
+    static constexpr int G = G_, SRC = SRC_, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)w; return ((h + 1) / 2 + G - 1) / G; }
+
+    template <int PH>
+    static SSW_HD void phase(const FastArgs& a, cplx* smem, int tile, int tid, Thread& th) {
+        constexpr int N = P::N, T = P::T;
+        const int g = tid / T, t = tid - g * T;
+        cplx* s = smem + g * P::PITCH;
+        const int img = tile / a.tiles_per_image;
+        const int ra = 2 * ((tile - img * a.tiles_per_image) * G + g), rb = ra + 1;
+        if constexpr (PH == 0) {
+            const bool ha = ra < a.h, hb = rb < a.h;
+            for (int u = t; u < N / 4; u += T) {
+                float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
+                if constexpr (SRC == PIX_RGB8) {
+                    const unsigned char* base = (const unsigned char*)a.src + 3 * (img * a.src_stride + (long long)ra * N);
+                    if (ha) luma4_rgb8((const unsigned*)base + 3 * u, ya);
+                    if (hb) luma4_rgb8((const unsigned*)(base + 3 * N) + 3 * u, yb);
+                } else {
+                    const float* base = (const float*)a.src + img * a.src_stride + (long long)ra * N;
+                    if (ha) { const f4 v = ld4(base + 4 * u); ya[0] = v.a; ya[1] = v.b; ya[2] = v.c; ya[3] = v.d; }
+                    if (hb) { const f4 v = ld4(base + N + 4 * u); yb[0] = v.a; yb[1] = v.b; yb[2] = v.c; yb[3] = v.d; }
+                }
+                put4<P>(s, u, ya, yb);
+            }
+        } else if constexpr (PH < NPH - 1) {
+            fft_phase<P, PH>(s, a.tw, t, th.v);
+        } else {
+            if (ra >= a.h) return;
+            const bool hb = rb < a.h;
+            float* oa = a.plane + img * a.plane_stride + (long long)ra * N;
+            float* ob = oa + N;
+            for (int k = t; k <= N / 2; k += T) {
+                const int kr = k ? N - k : 0;
+                float xa, xb, ya, yb;
+                dct2_post(s[P::idx(k)], s[P::idx(kr)], SSW_LDG(&a.t4[k]), xa, xb, ya, yb);
+                const float sk = k ? a.scalen : a.scale0;
+                oa[k] = xa * sk;
+                if (hb) ob[k] = xb * sk;
+                if (k && kr != k) {
+                    oa[kr] = ya * a.scalen;
+                    if (hb) ob[kr] = yb * a.scalen;
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// inverse row pass: plane rows -> DCT-III along x -> scale -> plane | Y' + I,Q(original RGB8) -> RGB8
+// ------------------------------------------------------------------------------------------------
+template <class P_, int G_, int DST_>
+struct RowInv {
+    using P = P_;
+    static constexpr int G = G_, DST = DST_, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)w; return ((h + 1) / 2 + G - 1) / G; }
+
+    template <int PH>
+    static SSW_HD void phase(const FastArgs& a, cplx* smem, int tile, int tid, Thread& th) {
+        constexpr int N = P::N, T = P::T;
+        const int g = tid / T, t = tid - g * T;
+        cplx* s = smem + g * P::PITCH;
+        const int img = tile / a.tiles_per_image;
+        const int ra = 2 * ((tile - img * a.tiles_per_image) * G + g), rb = ra + 1;
+        const bool ha = ra < a.h, hb = rb < a.h;
+        if constexpr (PH == 0) {
+            const float* ia = a.plane + img * a.plane_stride + (long long)ra * N;
+            const float* ib = ia + N;
+            for (int k = t; k <= N / 2; k += T) {
+                const int kr = k ? N - k : 0;
+                const float pa = ha ? ia[k] : 0.f, pb = hb ? ib[k] : 0.f;
+                const float qa = (k && ha) ? ia[kr] : 0.f, qb = (k && hb) ? ib[kr] : 0.f;
+                cplx zk, zr;
+                dct3_pre(pa, pb, qa, qb, SSW_LDG(&a.t4[k]), zk, zr);
+                s[P::idx(k)] = zk;
+                if (k && kr != k) s[P::idx(kr)] = zr;
+            }
+        } else if constexpr (PH < NPH - 1) {
+            fft_phase<P, PH>(s, a.tw, t, th.v);
+        } else {
+            if (!ha) return;
+            const long long row = (long long)ra * N;
+            for (int u = t; u < N / 4; u += T) {
+                cplx f[4];
+                get4<P>(s, u, f);
+                float ya[4], yb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ya[i] = f[i].x * a.scale0; yb[i] = -f[i].y * a.scale0; }
+                if constexpr (DST == PIX_PLANE) {
+                    float* o = (float*)a.dst + img * a.dst_stride + row + 4 * u;
+                    st4(o, ya[0], ya[1], ya[2], ya[3]);
+                    if (hb) st4(o + N, yb[0], yb[1], yb[2], yb[3]);
+                } else {
+                    const unsigned char* sb = (const unsigned char*)a.src + 3 * (img * a.src_stride + row);
+                    unsigned char* db = (unsigned char*)a.dst + 3 * (img * a.dst_stride + row);
+                    unsigned o[3];
+                    recolour4_rgb8((const unsigned*)sb + 3 * u, ya, o);
+                    unsigned* d = (unsigned*)db + 3 * u;
+                    d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+                    if (hb) {
+                        recolour4_rgb8((const unsigned*)(sb + 3 * N) + 3 * u, yb, o);
+                        d = (unsigned*)(db + 3 * N) + 3 * u;
+                        d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// column passes, in place: tile = G column pairs = 2G adjacent columns (G even: 128-bit accesses);
+// a float2 of two adjacent columns in one row *is* one complex sample of the packed line pair
+// ------------------------------------------------------------------------------------------------
+template <class P_, int G_, bool INVERSE_>
+struct ColPass {
+    using P = P_;
+    static_assert(G_ % 2 == 0, "column tiles hold an even number of pairs");
+    static constexpr int G = G_, H = G_ / 2, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)h; return (w / 2 + G - 1) / G; }
+
+    // forward load / inverse store: e -> (row r, pair of pairs q), one float4 = 4 adjacent columns
+    template <int PH>
+    static SSW_HD void phase(const FastArgs& a, cplx* smem, int tile, int tid, Thread& th) {
+        constexpr int N = P::N, T = P::T;
+        const int w = a.w;
+        const int img = tile / a.tiles_per_image;
+        const int c0 = (tile - img * a.tiles_per_image) * 2 * G;
+        float* plane = a.plane + img * a.plane_stride;
+        if constexpr (PH > 0 && PH < NPH - 1) {
+            const int g = tid / T, t = tid - g * T;
+            fft_phase<P, PH>(smem + g * P::PITCH, a.tw, t, th.v);
+        } else if constexpr ((PH == 0) != INVERSE_) {
+            // sample-domain side: forward load (PH == 0) or inverse store (PH == NPH-1)
+            for (int e = tid; e < N * H; e += THREADS) {
+                const int r = e / H, q = e - r * H;
+                const int c = c0 + 4 * q;
+                if (c >= w) continue;
+                float* gp = plane + (long long)r * w + c;
+                cplx* s0 = smem + (2 * q) * P::PITCH + P::idx(makhoul(r, N));
+                if constexpr (!INVERSE_) {
+                    const f4 v = ld4(gp);
+                    s0[0] = mk(v.a, v.b);
+                    s0[P::PITCH] = mk(v.c, v.d);
+                } else {
+                    const cplx f0 = s0[0], f1 = s0[P::PITCH];
+                    st4(gp, f0.x * a.scale0, -f0.y * a.scale0, f1.x * a.scale0, -f1.y * a.scale0);
+                }
+            }
+            if (!INVERSE_ && c0 + 2 * G > w) {
+                // columns beyond the frame (last tile): keep the FFT input finite
+                for (int e = tid; e < N * H; e += THREADS) {
+                    const int r = e / H, q = e - r * H;
+                    if (c0 + 4 * q >= w) {
+                        cplx* s0 = smem + (2 * q) * P::PITCH + P::idx(r);
+                        s0[0] = mk(0.f, 0.f);
+                        s0[P::PITCH] = mk(0.f, 0.f);
+                    }
+                }
+            }
+        } else {
+            // coefficient-domain side: forward store (post pass) or inverse load (pre pass)
+            for (int e = tid; e < (N / 2 + 1) * H; e += THREADS) {
+                const int k = e / H, q = e - k * H;
+                const int c = c0 + 4 * q;
+                const int kr = k ? N - k : 0;
+                cplx* s0 = smem + (2 * q) * P::PITCH;
+                cplx* s1 = s0 + P::PITCH;
+                const cplx tw = SSW_LDG(&a.t4[k]);
+                if constexpr (!INVERSE_) {
+                    if (c >= w) continue;
+                    float xa0, xb0, ya0, yb0, xa1, xb1, ya1, yb1;
+                    dct2_post(s0[P::idx(k)], s0[P::idx(kr)], tw, xa0, xb0, ya0, yb0);
+                    dct2_post(s1[P::idx(k)], s1[P::idx(kr)], tw, xa1, xb1, ya1, yb1);
+                    const float sk = k ? a.scalen : a.scale0;
+                    st4(plane + (long long)k * w + c, xa0 * sk, xb0 * sk, xa1 * sk, xb1 * sk);
+                    if (k && kr != k)
+                        st4(plane + (long long)kr * w + c, ya0 * a.scalen, yb0 * a.scalen, ya1 * a.scalen, yb1 * a.scalen);
+                } else {
+                    f4 pv = f4{0.f, 0.f, 0.f, 0.f}, qv = f4{0.f, 0.f, 0.f, 0.f};
+                    if (c < w) {
+                        pv = ld4(plane + (long long)k * w + c);
+                        if (k) qv = ld4(plane + (long long)kr * w + c);
+                    }
+                    cplx zk, zr;
+                    dct3_pre(pv.a, pv.b, qv.a, qv.b, tw, zk, zr);
+                    s0[P::idx(k)] = zk;
+                    if (k && kr != k) s0[P::idx(kr)] = zr;
+                    dct3_pre(pv.c, pv.d, qv.c, qv.d, tw, zk, zr);
+                    s1[P::idx(k)] = zk;
+                    if (k && kr != k) s1[P::idx(kr)] = zr;
+                }
+            }
+        }
+    }
+};
+
+#if defined(__CUDACC__)
+template <class K>
+constexpr int min_blocks() {
+    // aim at 1024 resident threads per SM (64 registers each), bounded by shared memory
+    int by_threads = 1024 / K::THREADS;
+    int by_smem = (227 * 1024) / (K::SMEM + 1024);
+    int m = by_threads < by_smem ? by_threads : by_smem;
+    return m < 1 ? 1 : m;
+}
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel(const __grid_constant__ FastArgs a) {
+    extern __shared__ __align__(16) unsigned char fast_smem[];
+    typename K::Thread th;
+    static_for<K::NPH>([&](auto ph) {
+        constexpr int p = decltype(ph)::value;
+        K::template phase<p>(a, (cplx*)fast_smem, blockIdx.x, threadIdx.x, th);
+        if constexpr (p + 1 < K::NPH) __syncthreads();
+    });
+}
+#endif
+
+// host: stage twiddles of a plan, layout per stage s >= 1: [r-1][k], k < ns(s); exp(-2*pi*i*k*r/(ns*R))
+template <class P>
+inline void make_stage_twiddles(float* out /* 2*P::TW_TOTAL floats */) {
+    int o = 0;
+    for (int s = 1; s < P::NST; ++s) {
+        const int R = P::radix(s), ns = P::ns(s);
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < ns; ++k) {
+                const double ang = -2.0 * M_PI * (double)k * (double)r / ((double)ns * (double)R);
+                out[2 * o] = (float)std::cos(ang);
+                out[2 * o + 1] = (float)std::sin(ang);
+                ++o;
+            }
+    }
+}
+
+// the planned lengths: 4K / 1080p frames in both orientations (+ the reference fixture's width)
+using Plan3840 = Plan<3840, 256, 15, 16, 16>;
+using Plan2160 = Plan<2160, 192, 15, 12, 12>;
+using Plan1920 = Plan<1920, 128, 15, 16, 8>;
+using Plan1080 = Plan<1080, 96, 15, 6, 12>;
+using Plan640 = Plan<640, 64, 5, 8, 16>;
+
+}  // namespace fast
+}  // namespace ssw

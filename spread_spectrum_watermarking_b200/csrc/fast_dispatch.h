@@ -1,0 +1,27 @@
+// Length -> compile-time plan dispatch shared by libssw (ssw_api.cu) and tests/emul.
+#pragma once
+#include "dct_fast.cuh"
+
+namespace ssw {
+namespace fast {
+
+// default team counts per CTA: rows G pairs (one team each), columns G pairs = 2G adjacent columns
+template <class P> struct RowG { static constexpr int value = (P::T >= 192) ? 1 : 2; };
+constexpr int kColG = 4;
+
+template <class F>
+inline bool with_plan(int n, F&& f) {
+    switch (n) {
+        case 3840: f(Plan3840{}); return true;
+        case 2160: f(Plan2160{}); return true;
+        case 1920: f(Plan1920{}); return true;
+        case 1080: f(Plan1080{}); return true;
+        case 640: f(Plan640{}); return true;
+        default: return false;
+    }
+}
+
+inline bool has_plan(int n) { return with_plan(n, [](auto) {}); }
+
+}  // namespace fast
+}  // namespace ssw

@@ -15,6 +15,7 @@
 
 #include "../../include/ssw.h"
 #include "dct_kernels.cuh"
+#include "fast_dispatch.h"
 #include "mark_kernels.cuh"
 #include "select_kernels.cuh"
 #include "select_general.cuh"
@@ -56,6 +57,8 @@ struct ssw_ctx {
     bool own_stream = false;
     std::map<int, std::unique_ptr<DevPlan>> plans;
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
+    std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
+    bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -132,6 +135,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_ROW_PAIRS")) c->row_pairs = atoi(s);
     if (const char* s = getenv("SSW_COL_PAIRS")) c->col_pairs = atoi(s);
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
+    if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     *out = c.release();
     return SSW_OK;
 }
@@ -151,6 +155,7 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->plans) cudaFree(kv.second->tables);
+    for (auto& kv : c->fast_tw) cudaFree(kv.second);
     topk_scratch_free(c);
     c->general.release();
     if (c->h_flag) cudaFreeHost(c->h_flag);
@@ -304,55 +309,179 @@ static LineArgs base_args(const DctPlanDev& pl, int w, int h, const Tiling& t, l
     return a;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fast path: compile-time planned kernels (dct_fast.cuh) for the common frame sizes
+// ------------------------------------------------------------------------------------------------
+template <class P>
+static int fast_tables(ssw_ctx* c, const cplx** tw, const cplx** t4) {
+    const DevPlan* gp;
+    CKS(get_plan(c, P::N, &gp));  // the generic plan owns the exp(-i*pi*k/2N) table
+    *t4 = gp->dev.t4;
+    auto it = c->fast_tw.find(P::N);
+    if (it == c->fast_tw.end()) {
+        std::vector<float> h(2 * (size_t)P::TW_TOTAL + 2);
+        fast::make_stage_twiddles<P>(h.data());
+        void* d = nullptr;
+        CK(cudaMalloc(&d, h.size() * sizeof(float)));
+        CK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        it = c->fast_tw.emplace(P::N, d).first;
+    }
+    *tw = (const cplx*)it->second;
+    return SSW_OK;
+}
+
+template <class K>
+static int launch_fast(ssw_ctx* c, const char* name, fast::FastArgs a, int w, int h, int batch) {
+    CKS(fast_tables<typename K::P>(c, &a.tw, &a.t4));
+    a.tiles_per_image = K::tiles_per_image(w, h);
+    const long long tiles = (long long)a.tiles_per_image * batch;
+    if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
+    auto kernel = fast::fast_kernel<K>;
+    const void* key = (const void*)kernel;
+    if (c->smem_attr.find(key) == c->smem_attr.end()) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        c->smem_attr[key] = K::SMEM;
+    }
+    {
+        KScope ks(c, name);
+        kernel<<<(unsigned)tiles, K::THREADS, K::SMEM, c->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+static fast::FastArgs fast_args(int w, int h) {
+    fast::FastArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.w = w; a.h = h;
+    a.scale0 = 1.f; a.scalen = 1.f;
+    a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
+    return a;
+}
+
+static bool aligned(const void* p, size_t n) { return (((size_t)p) & (n - 1)) == 0; }
+
+// returns SSW_OK and sets *done when a fast kernel ran; *done = false -> caller uses the generic kernel
+static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
+                        float scale0, float scalen, bool* done) {
+    *done = false;
+    if (!c->use_fast || (src_type != PIX_RGB8 && src_type != PIX_PLANE)) return SSW_OK;
+    if (!aligned(d_plane, 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
+    int rc = SSW_OK;
+    *done = fast::with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        constexpr int G = fast::RowG<P>::value;
+        fast::FastArgs a = fast_args(w, h);
+        a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
+        if (src_type == PIX_RGB8) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+        else rc = launch_fast<fast::RowFwd<P, G, PIX_PLANE>>(c, "fwd_rows_plane", a, w, h, batch);
+    });
+    return rc;
+}
+
+static int fast_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen,
+                    bool* done) {
+    *done = false;
+    if (!c->use_fast || (w % 4) || !aligned(d_plane, 16)) return SSW_OK;
+    int rc = SSW_OK;
+    *done = fast::with_plan(h, [&](auto p) {
+        using P = decltype(p);
+        fast::FastArgs a = fast_args(w, h);
+        a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
+        if (inverse) rc = launch_fast<fast::ColPass<P, fast::kColG, true>>(c, "inv_cols", a, w, h, batch);
+        else rc = launch_fast<fast::ColPass<P, fast::kColG, false>>(c, "fwd_cols", a, w, h, batch);
+    });
+    return rc;
+}
+
+static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
+                        int dst_type, void* d_dst, float scale, bool* done) {
+    *done = false;
+    if (!c->use_fast || !aligned(d_plane, 16)) return SSW_OK;
+    const bool rgb8 = dst_type == PIX_RGB8 && src_type == PIX_RGB8 && aligned(d_src, 4) && aligned(d_dst, 4);
+    const bool plane = dst_type == PIX_PLANE && aligned(d_dst, 16);
+    if (!rgb8 && !plane) return SSW_OK;
+    int rc = SSW_OK;
+    *done = fast::with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        constexpr int G = fast::RowG<P>::value;
+        fast::FastArgs a = fast_args(w, h);
+        a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
+        if (rgb8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
+        else rc = launch_fast<fast::RowInv<P, G, PIX_PLANE>>(c, "inv_rows_plane", a, w, h, batch);
+    });
+    return rc;
+}
+
 // forward: pixels/plane -> coefficient plane (rows then columns)
 static int run_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
                        int dct_type) {
-    const DevPlan *pw, *ph;
-    CKS(get_plan(c, w, &pw));
-    CKS(get_plan(c, h, &ph));
-    Tiling tr, tc;
-    CKS(pick_tiling(c, pw->dev, false, h, &tr));
-    CKS(pick_tiling(c, ph->dev, true, w, &tc));
-    const long long npix = (long long)w * h;
-    LineArgs ar = base_args(pw->dev, w, h, tr, npix);
-    ar.src = d_src; ar.plane = d_plane;
-    ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
-    LineArgs ac = base_args(ph->dev, w, h, tc, npix);
-    ac.plane = d_plane;
-    ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+    float rs0 = 1.f, rsn = 1.f, cs0 = 1.f, csn = 1.f;
     if (dct_type == SSW_DCT2_ORTHOGONAL) {  // src/dct2d.rs:153-162,189-198
-        ar.scale0 = std::sqrt(1.0f / (4.0f * (float)w)); ar.scalen = std::sqrt(1.0f / (2.0f * (float)w));
-        ac.scale0 = std::sqrt(1.0f / (4.0f * (float)h)); ac.scalen = std::sqrt(1.0f / (2.0f * (float)h));
+        rs0 = std::sqrt(1.0f / (4.0f * (float)w)); rsn = std::sqrt(1.0f / (2.0f * (float)w));
+        cs0 = std::sqrt(1.0f / (4.0f * (float)h)); csn = std::sqrt(1.0f / (2.0f * (float)h));
     }
-    const long long ntr = (long long)ar.tiles_per_image * batch, ntc = (long long)ac.tiles_per_image * batch;
-    switch (src_type) {
-        case PIX_RGB8: CKS(launch_line(c, "row_fwd_rgb8", row_fwd_kernel<PIX_RGB8>, ar, tr, ntr)); break;
-        case PIX_RGB32F: CKS(launch_line(c, "row_fwd_rgb32f", row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr)); break;
-        default: CKS(launch_line(c, "row_fwd_plane", row_fwd_kernel<PIX_PLANE>, ar, tr, ntr)); break;
+    const long long npix = (long long)w * h;
+    bool done = false;
+    CKS(fast_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
+    if (!done) {
+        const DevPlan* pw;
+        CKS(get_plan(c, w, &pw));
+        Tiling tr;
+        CKS(pick_tiling(c, pw->dev, false, h, &tr));
+        LineArgs ar = base_args(pw->dev, w, h, tr, npix);
+        ar.src = d_src; ar.plane = d_plane; ar.scale0 = rs0; ar.scalen = rsn;
+        ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
+        const long long ntr = (long long)ar.tiles_per_image * batch;
+        switch (src_type) {
+            case PIX_RGB8: CKS(launch_line(c, "row_fwd_rgb8", row_fwd_kernel<PIX_RGB8>, ar, tr, ntr)); break;
+            case PIX_RGB32F: CKS(launch_line(c, "row_fwd_rgb32f", row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr)); break;
+            default: CKS(launch_line(c, "row_fwd_plane", row_fwd_kernel<PIX_PLANE>, ar, tr, ntr)); break;
+        }
     }
-    CKS(launch_line(c, "col_fwd", col_fwd_kernel, ac, tc, ntc));
+    CKS(fast_col(c, false, w, h, batch, d_plane, cs0, csn, &done));
+    if (!done) {
+        const DevPlan* ph;
+        CKS(get_plan(c, h, &ph));
+        Tiling tc;
+        CKS(pick_tiling(c, ph->dev, true, w, &tc));
+        LineArgs ac = base_args(ph->dev, w, h, tc, npix);
+        ac.plane = d_plane; ac.scale0 = cs0; ac.scalen = csn;
+        ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+        CKS(launch_line(c, "col_fwd", col_fwd_kernel, ac, tc, (long long)ac.tiles_per_image * batch));
+    }
     return SSW_OK;
 }
 
 // inverse: coefficient plane (destroyed) -> pixels/plane (columns then rows)
 static int run_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
                        int dst_type, void* d_dst) {
-    const DevPlan *pw, *ph;
-    CKS(get_plan(c, w, &pw));
-    CKS(get_plan(c, h, &ph));
-    Tiling tr, tc;
-    CKS(pick_tiling(c, pw->dev, false, h, &tr));
-    CKS(pick_tiling(c, ph->dev, true, w, &tc));
     const long long npix = (long long)w * h;
-    LineArgs ac = base_args(ph->dev, w, h, tc, npix);
-    ac.plane = d_plane;
-    ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+    const float out_scale = 4.0f / (float)((size_t)w * (size_t)h);  // src/dct2d.rs:213-217
+    bool done = false;
+    CKS(fast_col(c, true, w, h, batch, d_plane, 1.f, 1.f, &done));
+    if (!done) {
+        const DevPlan* ph;
+        CKS(get_plan(c, h, &ph));
+        Tiling tc;
+        CKS(pick_tiling(c, ph->dev, true, w, &tc));
+        LineArgs ac = base_args(ph->dev, w, h, tc, npix);
+        ac.plane = d_plane;
+        ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+        CKS(launch_line(c, "col_inv", col_inv_kernel, ac, tc, (long long)ac.tiles_per_image * batch));
+    }
+    CKS(fast_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
+    if (done) return SSW_OK;
+    const DevPlan* pw;
+    CKS(get_plan(c, w, &pw));
+    Tiling tr;
+    CKS(pick_tiling(c, pw->dev, false, h, &tr));
     LineArgs ar = base_args(pw->dev, w, h, tr, npix);
     ar.plane = d_plane; ar.src = d_src; ar.dst = d_dst;
-    ar.scale0 = 4.0f / (float)((size_t)w * (size_t)h);  // src/dct2d.rs:213-217
+    ar.scale0 = out_scale;
     ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
-    const long long ntr = (long long)ar.tiles_per_image * batch, ntc = (long long)ac.tiles_per_image * batch;
-    CKS(launch_line(c, "col_inv", col_inv_kernel, ac, tc, ntc));
+    const long long ntr = (long long)ar.tiles_per_image * batch;
     if (dst_type == PIX_PLANE) return launch_line(c, "row_inv_plane", row_inv_kernel<PIX_PLANE, PIX_PLANE>, ar, tr, ntr);
     if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) return launch_line(c, "row_inv_rgb8", row_inv_kernel<PIX_RGB8, PIX_RGB8>, ar, tr, ntr);
     if (dst_type == PIX_RGB8 && src_type == PIX_RGB32F) return launch_line(c, "row_inv_rgb8_src32f", row_inv_kernel<PIX_RGB8, PIX_RGB32F>, ar, tr, ntr);

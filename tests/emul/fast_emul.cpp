@@ -1,0 +1,126 @@
+// TEST INFRASTRUCTURE ONLY -- CPU execution of the fast-path kernel PHASES (csrc/dct_fast.cuh).
+//
+// The fast kernels are sequences of barrier-separated phases over a per-thread register state; the
+// __global__ wrapper runs phase p for all threads, __syncthreads(), phase p+1, ...  Here the same
+// phase functions are called for tid = 0..THREADS-1 in turn, with the per-thread states kept in an
+// array, which is an exact model of that execution.  Never linked into libssw.so; not a fallback.
+#include <cstring>
+#include <vector>
+
+#include "../../spread_spectrum_watermarking_b200/csrc/fast_dispatch.h"
+
+using namespace ssw;
+using namespace ssw::fast;
+
+namespace {
+
+template <class K>
+void emulate(const FastArgs& a, int ntiles) {
+    std::vector<cplx> smem(K::SMEM / sizeof(cplx) + 8);
+    std::vector<typename K::Thread> th(K::THREADS);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        static_for<K::NPH>([&](auto ph) {
+            constexpr int p = decltype(ph)::value;
+            for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<p>(a, smem.data(), tile, tid, th[tid]);
+        });
+    }
+}
+
+template <class P>
+struct Tables {
+    std::vector<float> tw, t4;
+    Tables() : tw(2 * (size_t)P::TW_TOTAL + 2), t4(2 * (size_t)P::N) {
+        make_stage_twiddles<P>(tw.data());
+        for (int j = 0; j < P::N; ++j) {
+            const double b = -M_PI * (double)j / (2.0 * (double)P::N);
+            t4[2 * j] = (float)std::cos(b);
+            t4[2 * j + 1] = (float)std::sin(b);
+        }
+    }
+};
+
+FastArgs base_args(int w, int h) {
+    FastArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.w = w; a.h = h;
+    a.scale0 = 1.f; a.scalen = 1.f;
+    a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emul_fast_has_plan(int n) { return has_plan(n) ? 1 : 0; }
+
+// src_type: 0 = RGB8, 2 = plane (PIX_*).  plane: [batch][h][w].  scale0/scalen: DCT2Orthogonal factors.
+int emul_fast_row_fwd(int src_type, const void* src, int w, int h, int batch, float* plane, float scale0, float scalen) {
+    return with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        constexpr int G = RowG<P>::value;
+        Tables<P> tb;
+        FastArgs a = base_args(w, h);
+        a.src = src; a.plane = plane; a.scale0 = scale0; a.scalen = scalen;
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+        if (src_type == PIX_RGB8) {
+            using K = RowFwd<P, G, PIX_RGB8>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        } else {
+            using K = RowFwd<P, G, PIX_PLANE>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        }
+    }) ? 0 : -2;
+}
+
+int emul_fast_col(int inverse, int w, int h, int batch, float* plane, float scale0, float scalen) {
+    if (w % 4) return -2;
+    return with_plan(h, [&](auto p) {
+        using P = decltype(p);
+        Tables<P> tb;
+        FastArgs a = base_args(w, h);
+        a.plane = plane; a.scale0 = scale0; a.scalen = scalen;
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+        if (inverse) {
+            using K = ColPass<P, kColG, true>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        } else {
+            using K = ColPass<P, kColG, false>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        }
+    }) ? 0 : -2;
+}
+
+// dst_type: 0 = RGB8 (src = original RGB8 pixels), 2 = plane
+int emul_fast_row_inv(int dst_type, float* plane, const void* src, int w, int h, int batch, void* dst, float scale) {
+    return with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        constexpr int G = RowG<P>::value;
+        Tables<P> tb;
+        FastArgs a = base_args(w, h);
+        a.src = src; a.plane = plane; a.dst = dst; a.scale0 = scale;
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+        if (dst_type == PIX_RGB8) {
+            using K = RowInv<P, G, PIX_RGB8>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        } else {
+            using K = RowInv<P, G, PIX_PLANE>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        }
+    }) ? 0 : -2;
+}
+
+// exactness of the division-free u8 -> [0,1] conversion: returns the number of mismatching inputs
+int emul_fast_u8_unit_mismatches(void) {
+    int bad = 0;
+    for (unsigned v = 0; v < 256; ++v) bad += (u8_unit(v) != u8_to_unit(v));
+    return bad;
+}
+
+}  // extern "C"

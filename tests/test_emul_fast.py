@@ -1,0 +1,93 @@
+"""The fast-path (compile-time planned) DCT kernel PHASES of csrc/dct_fast.cuh executed on the CPU
+(tests/emul/fast_emul.cpp) against the oracle.  Exercises the exact index arithmetic, radix plans
+and colour math of the device code in the GPU-less build container; test infrastructure only."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import ptr
+
+FAST = [3840, 2160, 1920, 1080, 640]
+f32 = ctypes.c_float
+
+
+def test_u8_unit_is_exact(emul):
+    assert emul.emul_fast_u8_unit_mismatches() == 0
+
+
+def test_plan_table(emul):
+    for n in FAST:
+        assert emul.emul_fast_has_plan(n) == 1
+    for n in (444, 37, 1000, 4096):
+        assert emul.emul_fast_has_plan(n) == 0
+
+
+def dct1d_rows(so, a, kind):
+    """reference 1-D pass along x for every row (scipy scaling, src/dct2d.rs:107-111)"""
+    import scipy.fft
+    a64 = a.astype(np.float64)
+    if kind == 'fwd':
+        return scipy.fft.dct(a64, type=2, axis=1)
+    return 0.25 * scipy.fft.dct(a64, type=3, axis=1)
+
+
+@pytest.mark.parametrize('n', FAST)
+@pytest.mark.parametrize('h', [5, 8])
+def test_row_passes_plane(emul, so, n, h):
+    rng = np.random.default_rng(n + h)
+    a = rng.random((2, h, n)).astype(np.float32)   # batch of 2
+    out = np.zeros_like(a)
+    assert emul.emul_fast_row_fwd(2, ptr(a), n, h, 2, ptr(out), f32(1.0), f32(1.0)) == 0
+    ref = dct1d_rows(so, a.reshape(2 * h, n), 'fwd').reshape(a.shape)
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    back = np.zeros_like(a)
+    c = ref.astype(np.float32)
+    assert emul.emul_fast_row_inv(2, ptr(c), None, n, h, 2, ptr(back), f32(2.0 / n)) == 0
+    assert np.abs(back - a).max() <= 3e-6
+
+
+@pytest.mark.parametrize('n', FAST)
+@pytest.mark.parametrize('w', [8, 20])
+def test_col_passes(emul, so, n, w):
+    rng = np.random.default_rng(n + w)
+    a = rng.random((2, n, w)).astype(np.float32)
+    f = a.copy()
+    assert emul.emul_fast_col(0, w, n, 2, ptr(f), f32(1.0), f32(1.0)) == 0
+    import scipy.fft
+    ref = scipy.fft.dct(a.astype(np.float64), type=2, axis=1)
+    assert np.abs(f - ref).max() <= 2e-6 * np.abs(ref).max()
+    b = ref.astype(np.float32)
+    assert emul.emul_fast_col(1, w, n, 2, ptr(b), f32(2.0 / n), f32(1.0)) == 0
+    assert np.abs(b - a).max() <= 3e-6
+
+
+def test_fused_rgb8_frame_1080_rows(emul, so):
+    """RGB8 -> luma -> row DCT and back through the recolouring store, on a 1920-wide strip"""
+    w, h = 1920, 6
+    rgb = so.synth_frame(w, h, seed=5)
+    plane = np.zeros((h, w), np.float32)
+    assert emul.emul_fast_row_fwd(0, ptr(rgb), w, h, 1, ptr(plane), f32(1.0), f32(1.0)) == 0
+    y, _, _ = so.rgb32f_to_yiq(so.rgb8_to_rgb32f(rgb))
+    ref = dct1d_rows(so, y, 'fwd')
+    assert np.abs(plane - ref).max() <= 2e-6 * np.abs(ref).max()
+    out = np.zeros_like(rgb)
+    assert emul.emul_fast_row_inv(0, ptr(plane.copy()), ptr(rgb), w, h, 1, ptr(out), f32(2.0 / w)) == 0
+    assert np.abs(out.astype(int) - rgb.astype(int)).max() <= 1
+    assert (out != rgb).mean() < 0.01
+
+
+def test_full_frame_640x1080_matches_oracle(emul, so):
+    """both passes of a frame whose width and height are planned lengths, odd tile counts included"""
+    w, h = 640, 1080
+    rgb = so.synth_frame(w, h, seed=9)
+    plane = np.zeros((h, w), np.float32)
+    assert emul.emul_fast_row_fwd(0, ptr(rgb), w, h, 1, ptr(plane), f32(1.0), f32(1.0)) == 0
+    assert emul.emul_fast_col(0, w, h, 1, ptr(plane), f32(1.0), f32(1.0)) == 0
+    ref, _, _ = so.forward(rgb)
+    tol = 1e-5 * np.abs(ref) + 1e-7 * np.abs(ref).max()
+    assert (np.abs(plane - ref) <= tol).all()
+    out = np.zeros_like(rgb)
+    assert emul.emul_fast_col(1, w, h, 1, ptr(plane), f32(1.0), f32(1.0)) == 0
+    assert emul.emul_fast_row_inv(0, ptr(plane), ptr(rgb), w, h, 1, ptr(out), f32(4.0 / (w * h))) == 0
+    assert np.abs(out.astype(int) - rgb.astype(int)).max() <= 1

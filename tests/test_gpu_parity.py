@@ -340,3 +340,28 @@ def test_embed_is_idempotent_on_zero_mark_and_deterministic(wm, ctx, so):
     assert (b1 == b2).all() and (b1 != f).any()
     e = wm.Reader.base(f, ctx=ctx).extract(wm.Reader.derived(b1, ctx=ctx), 1000)
     assert float(wm.Tester.new(e, ctx=ctx).similarity(m).similarity) > 25
+
+
+# ---------------------------------------------------------------------------- fast path vs generic kernels
+@pytest.mark.parametrize('w,h', [(1920, 1080), (3840, 2160), (640, 1080), (1080, 640), (2160, 3840), (1920, 37), (1000, 1080)])
+def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
+    """the compile-time planned kernels (dct_fast.cuh) against the generic line kernels on the same
+    frame: coefficients agree to FP32 rounding, and both reproduce the pixels within 1 LSB"""
+    rgb = so.synth_frame(w, h, seed=11)
+    monkeypatch.setenv('SSW_NO_FAST', '1')
+    cg = wm.Context(0)
+    monkeypatch.delenv('SSW_NO_FAST')
+    cf = wm.Context(0)
+    try:
+        wg, wf = wm.Writer.new(rgb, ctx=cg), wm.Writer.new(rgb, ctx=cf)
+        a, b = wg.coefficient_image(), wf.coefficient_image()
+        assert np.abs(a - b).max() <= 4e-7 * np.abs(a).max()
+        mark = np.random.default_rng(w + h).standard_normal(500).astype(np.float32)
+        og, of = wg.mark_rgb8([mark]), wf.mark_rgb8([mark])
+        d = np.abs(og.astype(int) - of.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02
+        if w * h <= 1920 * 1080:
+            ref, _, _ = so.embed(rgb, [mark])
+            assert np.abs(of.astype(int) - ref.astype(int)).max() <= 1
+    finally:
+        cg.close(); cf.close()
