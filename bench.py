@@ -401,6 +401,8 @@ def run_ours(args, wl):
                                          he.ctypes.data, hm[r].ctypes.data, hs.ctypes.data))
 
     Ke = max(3, min(K, 20))
+    if args.no_e2e:
+        Ke = 3
     for s in range(3):
         e2e_step(s)
     barrier()
@@ -454,6 +456,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='tuning runs: only 3 end-to-end steps')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':

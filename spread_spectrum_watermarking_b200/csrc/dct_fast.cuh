@@ -157,38 +157,24 @@ SSW_HD void unpack4(unsigned w0, unsigned w1, unsigned w2, unsigned* b) {
     b[8] = w2 & 255u; b[9] = (w2 >> 8) & 255u; b[10] = (w2 >> 16) & 255u; b[11] = w2 >> 24;
 }
 
-// luma of 4 consecutive RGB8 pixels (12 bytes, 4-byte aligned)
-SSW_HD void luma4_rgb8(const unsigned* p, float* y) {
-    unsigned b[12];
-    unpack4(SSW_LDG(p), SSW_LDG(p + 1), SSW_LDG(p + 2), b);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) y[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
-}
-
-// 4 pixels: new luma y[4] + chroma of the original RGB8 pixels -> RGB8 (12 bytes)
-SSW_HD void recolour4_rgb8(const unsigned* src, const float* y, unsigned* dst) {
-    unsigned b[12], o[12];
-    unpack4(SSW_LDG(src), SSW_LDG(src + 1), SSW_LDG(src + 2), b);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float r = u8_unit(b[3 * i]), g = u8_unit(b[3 * i + 1]), bl = u8_unit(b[3 * i + 2]);
-        const float ci = rgb_to_i(r, g, bl), cq = rgb_to_q(r, g, bl);
-        float ro, go, bo;
-        yiq_to_rgb(y[i], ci, cq, ro, go, bo);
-        o[3 * i] = unit_to_u8(ro); o[3 * i + 1] = unit_to_u8(go); o[3 * i + 2] = unit_to_u8(bo);
-    }
-    dst[0] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-    dst[1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
-    dst[2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);
-}
-
 struct f4 { float a, b, c, d; };  // 16-byte vector for host + device
+// streaming 128-bit / 32-bit global loads: read-only path, do not allocate in L1 (the twiddle tables live there)
 SSW_HD f4 ld4(const float* p) {
 #if defined(__CUDA_ARCH__)
-    const float4 v = *reinterpret_cast<const float4*>(p);
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return f4{v.x, v.y, v.z, v.w};
 #else
     return f4{p[0], p[1], p[2], p[3]};
+#endif
+}
+SSW_HD unsigned ldw(const unsigned* p) {
+#if defined(__CUDA_ARCH__)
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *p;
 #endif
 }
 SSW_HD void st4(float* p, float a, float b, float c, float d) {
@@ -197,6 +183,99 @@ SSW_HD void st4(float* p, float a, float b, float c, float d) {
 #else
     p[0] = a; p[1] = b; p[2] = c; p[3] = d;
 #endif
+}
+
+// round(clamp(v,0,1)*255) with ties away from zero, NaN -> 0: bit-identical to unit_to_u8(clamp01(v)).
+// s + 0.5 is exact for every f32 s in [0,255] except the largest float below 0.5, where round-to-
+// nearest would give 1.0; adding with round-toward-zero fixes exactly that case.
+SSW_HD unsigned unit_to_u8_fast(float v) {
+#if defined(__CUDA_ARCH__)
+    const float s = __fmul_rn(fminf(fmaxf(v, 0.0f), 1.0f), 255.0f);
+    return (unsigned)__float2int_rz(__fadd_rz(s, 0.5f));
+#else
+    float c = v;
+    if (!(c == c)) return 0u;
+    c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+    const float s = c * 255.0f;
+    const double d = (double)s + 0.5;  // exact
+    return (unsigned)(long long)d;     // truncation == round-toward-zero add followed by F2I.TRUNC
+#endif
+}
+
+// base pointer of image `img` inside a batch of pixel type TYPE (stride in pixels)
+template <int TYPE>
+SSW_HD const void* image_base(const void* p, long long img, long long stride) {
+    if constexpr (TYPE == PIX_RGB8) return (const unsigned char*)p + 3 * img * stride;
+    else if constexpr (TYPE == PIX_RGB32F) return (const float*)p + 3 * img * stride;
+    else return (const float*)p + img * stride;
+}
+
+// 4 pixels of one row -> luma
+template <int SRC>
+SSW_HD void load_luma4(const void* src, long long pix4 /* index of the first of 4 pixels */, float* y) {
+    if constexpr (SRC == PIX_RGB8) {
+        const unsigned* p = (const unsigned*)((const unsigned char*)src + 3 * pix4);
+        unsigned b[12];
+        unpack4(ldw(p), ldw(p + 1), ldw(p + 2), b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+    } else if constexpr (SRC == PIX_RGB32F) {
+        const float* p = (const float*)src + 3 * pix4;
+        const f4 v0 = ld4(p), v1 = ld4(p + 4), v2 = ld4(p + 8);
+        y[0] = rgb_to_y(v0.a, v0.b, v0.c); y[1] = rgb_to_y(v0.d, v1.a, v1.b);
+        y[2] = rgb_to_y(v1.c, v1.d, v2.a); y[3] = rgb_to_y(v2.b, v2.c, v2.d);
+    } else {
+        const f4 v = ld4((const float*)src + pix4);
+        y[0] = v.a; y[1] = v.b; y[2] = v.c; y[3] = v.d;
+    }
+}
+
+// 4 pixels of one row: new luma y[4] (+ chroma of the original pixels) -> destination
+template <int DST, int SRC>
+SSW_HD void store_pix4(const void* src, void* dst, long long pix4, const float* y) {
+    if constexpr (DST == PIX_PLANE) {
+        st4((float*)dst + pix4, y[0], y[1], y[2], y[3]);
+    } else {
+        float c[12];
+        if constexpr (SRC == PIX_RGB8) {
+            const unsigned* p = (const unsigned*)((const unsigned char*)src + 3 * pix4);
+            unsigned b[12];
+            unpack4(ldw(p), ldw(p + 1), ldw(p + 2), b);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) c[i] = u8_unit(b[i]);
+        } else {
+            const float* p = (const float*)src + 3 * pix4;
+            const f4 v0 = ld4(p), v1 = ld4(p + 4), v2 = ld4(p + 8);
+            c[0] = v0.a; c[1] = v0.b; c[2] = v0.c; c[3] = v0.d; c[4] = v1.a; c[5] = v1.b;
+            c[6] = v1.c; c[7] = v1.d; c[8] = v2.a; c[9] = v2.b; c[10] = v2.c; c[11] = v2.d;
+        }
+        float o[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float ci = rgb_to_i(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+            const float cq = rgb_to_q(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+            // src/yiq.rs:163-165 rows of YIQ_TO_RGB_MATRIX, (m0*y + m1*i) + m2*q, m0 == 1
+            o[3 * i] = SSW_FADD(SSW_FADD(y[i], SSW_FMUL(0.948262f, ci)), SSW_FMUL(0.624013f, cq));
+            o[3 * i + 1] = SSW_FADD(SSW_FADD(y[i], SSW_FMUL(-0.276066f, ci)), SSW_FMUL(-0.639810f, cq));
+            o[3 * i + 2] = SSW_FADD(SSW_FADD(y[i], SSW_FMUL(-1.105450f, ci)), SSW_FMUL(1.729860f, cq));
+        }
+        if constexpr (DST == PIX_RGB8) {
+            unsigned q[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) q[i] = unit_to_u8_fast(o[i]);
+            unsigned* d = (unsigned*)((unsigned char*)dst + 3 * pix4);
+            d[0] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+            d[1] = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+            d[2] = q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24);
+        } else {
+            float* d = (float*)dst + 3 * pix4;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) o[i] = clamp01(o[i]);
+            st4(d, o[0], o[1], o[2], o[3]);
+            st4(d + 4, o[4], o[5], o[6], o[7]);
+            st4(d + 8, o[8], o[9], o[10], o[11]);
+        }
+    }
 }
 
 // FFT-input positions of 4 consecutive samples m = 4u..4u+3 (Makhoul): 2u, N-1-2u, 2u+1, N-2-2u.
@@ -216,8 +295,9 @@ SSW_HD void put4(cplx* s, int u, const float* a, const float* b) {
 template <class P>
 SSW_HD void get4(const cplx* s, int u, cplx* f) {  // f[i] = FFT value belonging to sample 4u+i
     if constexpr (!P::PAD) {
-        const f4 lo = ld4(&s[2 * u].x), hi = ld4(&s[P::N - 2 - 2 * u].x);
-        f[0] = mk(lo.a, lo.b); f[2] = mk(lo.c, lo.d); f[3] = mk(hi.a, hi.b); f[1] = mk(hi.c, hi.d);
+        const float* lo = &s[2 * u].x;
+        const float* hi = &s[P::N - 2 - 2 * u].x;
+        f[0] = mk(lo[0], lo[1]); f[2] = mk(lo[2], lo[3]); f[3] = mk(hi[0], hi[1]); f[1] = mk(hi[2], hi[3]);
     } else {
         f[0] = s[P::idx(2 * u)]; f[2] = s[P::idx(2 * u + 1)];
         f[3] = s[P::idx(P::N - 2 - 2 * u)]; f[1] = s[P::idx(P::N - 1 - 2 * u)];
@@ -236,6 +316,7 @@ struct RowFwd {
     using P = P_;
     static constexpr int G = G_, SRC = SRC_, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
     static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
+    static constexpr int MINB = 0;
     using Thread = ThreadState<P_>;
     static int tiles_per_image(int w, int h) { (void)w; return ((h + 1) / 2 + G - 1) / G; }
 
@@ -248,18 +329,17 @@ struct RowFwd {
         const int ra = 2 * ((tile - img * a.tiles_per_image) * G + g), rb = ra + 1;
         if constexpr (PH == 0) {
             const bool ha = ra < a.h, hb = rb < a.h;
-            for (int u = t; u < N / 4; u += T) {
-                float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
-                if constexpr (SRC == PIX_RGB8) {
-                    const unsigned char* base = (const unsigned char*)a.src + 3 * (img * a.src_stride + (long long)ra * N);
-                    if (ha) luma4_rgb8((const unsigned*)base + 3 * u, ya);
-                    if (hb) luma4_rgb8((const unsigned*)(base + 3 * N) + 3 * u, yb);
-                } else {
-                    const float* base = (const float*)a.src + img * a.src_stride + (long long)ra * N;
-                    if (ha) { const f4 v = ld4(base + 4 * u); ya[0] = v.a; ya[1] = v.b; ya[2] = v.c; ya[3] = v.d; }
-                    if (hb) { const f4 v = ld4(base + N + 4 * u); yb[0] = v.a; yb[1] = v.b; yb[2] = v.c; yb[3] = v.d; }
+            const void* src = image_base<SRC>(a.src, img, a.src_stride);
+            const long long rowa = (long long)ra * N;
+#pragma unroll
+            for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
+                const int u = t + it * T;
+                if (u < N / 4) {
+                    float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (ha) load_luma4<SRC>(src, rowa + 4 * u, ya);
+                    if (hb) load_luma4<SRC>(src, rowa + N + 4 * u, yb);
+                    put4<P>(s, u, ya, yb);
                 }
-                put4<P>(s, u, ya, yb);
             }
         } else if constexpr (PH < NPH - 1) {
             fft_phase<P, PH>(s, a.tw, t, th.v);
@@ -268,6 +348,7 @@ struct RowFwd {
             const bool hb = rb < a.h;
             float* oa = a.plane + img * a.plane_stride + (long long)ra * N;
             float* ob = oa + N;
+#pragma unroll 4
             for (int k = t; k <= N / 2; k += T) {
                 const int kr = k ? N - k : 0;
                 float xa, xb, ya, yb;
@@ -285,13 +366,14 @@ struct RowFwd {
 };
 
 // ------------------------------------------------------------------------------------------------
-// inverse row pass: plane rows -> DCT-III along x -> scale -> plane | Y' + I,Q(original RGB8) -> RGB8
+// inverse row pass: plane rows -> DCT-III along x -> scale -> plane | Y' + I,Q(original pixels) -> RGB
 // ------------------------------------------------------------------------------------------------
-template <class P_, int G_, int DST_>
+template <class P_, int G_, int DST_, int SRC_>
 struct RowInv {
     using P = P_;
-    static constexpr int G = G_, DST = DST_, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int G = G_, DST = DST_, SRC = SRC_, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
     static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
+    static constexpr int MINB = 0;
     using Thread = ThreadState<P_>;
     static int tiles_per_image(int w, int h) { (void)w; return ((h + 1) / 2 + G - 1) / G; }
 
@@ -306,6 +388,7 @@ struct RowInv {
         if constexpr (PH == 0) {
             const float* ia = a.plane + img * a.plane_stride + (long long)ra * N;
             const float* ib = ia + N;
+#pragma unroll 4
             for (int k = t; k <= N / 2; k += T) {
                 const int kr = k ? N - k : 0;
                 const float pa = ha ? ia[k] : 0.f, pb = hb ? ib[k] : 0.f;
@@ -319,29 +402,20 @@ struct RowInv {
             fft_phase<P, PH>(s, a.tw, t, th.v);
         } else {
             if (!ha) return;
+            const void* src = (DST == PIX_PLANE) ? nullptr : image_base<SRC>(a.src, img, a.src_stride);
+            void* dst = const_cast<void*>(image_base<DST>(a.dst, img, a.dst_stride));
             const long long row = (long long)ra * N;
-            for (int u = t; u < N / 4; u += T) {
-                cplx f[4];
-                get4<P>(s, u, f);
-                float ya[4], yb[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { ya[i] = f[i].x * a.scale0; yb[i] = -f[i].y * a.scale0; }
-                if constexpr (DST == PIX_PLANE) {
-                    float* o = (float*)a.dst + img * a.dst_stride + row + 4 * u;
-                    st4(o, ya[0], ya[1], ya[2], ya[3]);
-                    if (hb) st4(o + N, yb[0], yb[1], yb[2], yb[3]);
-                } else {
-                    const unsigned char* sb = (const unsigned char*)a.src + 3 * (img * a.src_stride + row);
-                    unsigned char* db = (unsigned char*)a.dst + 3 * (img * a.dst_stride + row);
-                    unsigned o[3];
-                    recolour4_rgb8((const unsigned*)sb + 3 * u, ya, o);
-                    unsigned* d = (unsigned*)db + 3 * u;
-                    d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
-                    if (hb) {
-                        recolour4_rgb8((const unsigned*)(sb + 3 * N) + 3 * u, yb, o);
-                        d = (unsigned*)(db + 3 * N) + 3 * u;
-                        d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
-                    }
+            for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
+                const int u = t + it * T;
+                if (u < N / 4) {
+                    cplx f[4];
+                    get4<P>(s, u, f);
+                    float ya[4], yb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ya[i] = f[i].x * a.scale0; yb[i] = -f[i].y * a.scale0; }
+                    store_pix4<DST, SRC>(src, dst, row + 4 * u, ya);
+                    if (hb) store_pix4<DST, SRC>(src, dst, row + N + 4 * u, yb);
                 }
             }
         }
@@ -350,18 +424,20 @@ struct RowInv {
 
 // ------------------------------------------------------------------------------------------------
 // column passes, in place: tile = G column pairs = 2G adjacent columns (G even: 128-bit accesses);
-// a float2 of two adjacent columns in one row *is* one complex sample of the packed line pair
+// a float2 of two adjacent columns in one row *is* one complex sample of the packed line pair.
+// TEAMS teams of T threads transform the G pairs in G/TEAMS rounds.
 // ------------------------------------------------------------------------------------------------
-template <class P_, int G_, bool INVERSE_>
+template <class P_, int G_, int TEAMS_, bool INVERSE_, int MINB_ = 0>
 struct ColPass {
     using P = P_;
-    static_assert(G_ % 2 == 0, "column tiles hold an even number of pairs");
-    static constexpr int G = G_, H = G_ / 2, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
+    static_assert(G_ % 2 == 0 && G_ % TEAMS_ == 0, "column tiles: even number of pairs, whole rounds");
+    static constexpr int G = G_, H = G_ / 2, TEAMS = TEAMS_, ROUNDS = G_ / TEAMS_, THREADS = TEAMS_ * P_::T;
+    static constexpr int NPH = 2 + 2 * P_::NST * ROUNDS;
     static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
+    static constexpr int MINB = MINB_;
     using Thread = ThreadState<P_>;
     static int tiles_per_image(int w, int h) { (void)h; return (w / 2 + G - 1) / G; }
 
-    // forward load / inverse store: e -> (row r, pair of pairs q), one float4 = 4 adjacent columns
     template <int PH>
     static SSW_HD void phase(const FastArgs& a, cplx* smem, int tile, int tid, Thread& th) {
         constexpr int N = P::N, T = P::T;
@@ -370,23 +446,27 @@ struct ColPass {
         const int c0 = (tile - img * a.tiles_per_image) * 2 * G;
         float* plane = a.plane + img * a.plane_stride;
         if constexpr (PH > 0 && PH < NPH - 1) {
+            constexpr int RD = (PH - 1) / (2 * P::NST), SUB = (PH - 1) % (2 * P::NST) + 1;
             const int g = tid / T, t = tid - g * T;
-            fft_phase<P, PH>(smem + g * P::PITCH, a.tw, t, th.v);
+            fft_phase<P, SUB>(smem + (RD * TEAMS + g) * P::PITCH, a.tw, t, th.v);
         } else if constexpr ((PH == 0) != INVERSE_) {
             // sample-domain side: forward load (PH == 0) or inverse store (PH == NPH-1)
-            for (int e = tid; e < N * H; e += THREADS) {
+#pragma unroll
+            for (int it = 0; it < (N * H + THREADS - 1) / THREADS; ++it) {
+                const int e = tid + it * THREADS;
                 const int r = e / H, q = e - r * H;
                 const int c = c0 + 4 * q;
-                if (c >= w) continue;
-                float* gp = plane + (long long)r * w + c;
-                cplx* s0 = smem + (2 * q) * P::PITCH + P::idx(makhoul(r, N));
-                if constexpr (!INVERSE_) {
-                    const f4 v = ld4(gp);
-                    s0[0] = mk(v.a, v.b);
-                    s0[P::PITCH] = mk(v.c, v.d);
-                } else {
-                    const cplx f0 = s0[0], f1 = s0[P::PITCH];
-                    st4(gp, f0.x * a.scale0, -f0.y * a.scale0, f1.x * a.scale0, -f1.y * a.scale0);
+                if (e < N * H && c < w) {
+                    float* gp = plane + (long long)r * w + c;
+                    cplx* s0 = smem + (2 * q) * P::PITCH + P::idx(makhoul(r, N));
+                    if constexpr (!INVERSE_) {
+                        const f4 v = ld4(gp);
+                        s0[0] = mk(v.a, v.b);
+                        s0[P::PITCH] = mk(v.c, v.d);
+                    } else {
+                        const cplx f0 = s0[0], f1 = s0[P::PITCH];
+                        st4(gp, f0.x * a.scale0, -f0.y * a.scale0, f1.x * a.scale0, -f1.y * a.scale0);
+                    }
                 }
             }
             if (!INVERSE_ && c0 + 2 * G > w) {
@@ -402,6 +482,7 @@ struct ColPass {
             }
         } else {
             // coefficient-domain side: forward store (post pass) or inverse load (pre pass)
+#pragma unroll 4
             for (int e = tid; e < (N / 2 + 1) * H; e += THREADS) {
                 const int k = e / H, q = e - k * H;
                 const int c = c0 + 4 * q;
@@ -440,6 +521,7 @@ struct ColPass {
 #if defined(__CUDACC__)
 template <class K>
 constexpr int min_blocks() {
+    if (K::MINB > 0) return K::MINB;
     // aim at 1024 resident threads per SM (64 registers each), bounded by shared memory
     int by_threads = 1024 / K::THREADS;
     int by_smem = (227 * 1024) / (K::SMEM + 1024);

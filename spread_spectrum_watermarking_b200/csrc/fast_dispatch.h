@@ -7,7 +7,8 @@ namespace fast {
 
 // default team counts per CTA: rows G pairs (one team each), columns G pairs = 2G adjacent columns
 template <class P> struct RowG { static constexpr int value = (P::T >= 192) ? 1 : 2; };
-constexpr int kColG = 4;
+constexpr int kColG = 4;      // column pairs per CTA (8 adjacent columns = one 32-byte sector per row)
+constexpr int kColTeams = 2;  // teams transforming them (G / TEAMS rounds)
 
 template <class F>
 inline bool with_plan(int n, F&& f) {

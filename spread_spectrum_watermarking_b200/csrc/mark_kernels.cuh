@@ -78,6 +78,7 @@ similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned 
                        const float* __restrict__ extracted, long long ext_stride, int pair_mode,
                        float* __restrict__ out, long long out_stride) {
     __shared__ float tile[kSimMarks][kSimChunk + 1];
+    __shared__ float etile[kSimMarks][kSimChunk + 1];  // pair mode: extracted vector m next to mark m
     __shared__ float ex[kSimChunk];
     const size_t m0 = (size_t)blockIdx.x * kSimMarks;
     const unsigned e = blockIdx.y;  // extracted vector (bank mode)
@@ -85,33 +86,37 @@ similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned 
     const int lane = t & 31, warp = t >> 5;
     float nom = 0.f, den = 0.f;
     const float* ext = extracted + (pair_mode ? 0 : (long long)e * ext_stride);
+    const int rows = (int)min((size_t)kSimMarks, n_marks - m0);
     for (unsigned j0 = 0; j0 < n; j0 += kSimChunk) {
         const unsigned len = min((unsigned)kSimChunk, n - j0);
         // each warp stages rows warp, warp+4, ... : 32 consecutive floats of one mark per load
-        for (int r = warp; r < kSimMarks; r += kSimMarks / 32) {
+        for (int r = warp; r < rows; r += kSimMarks / 32) {
             const size_t m = m0 + r;
-            float v = 0.f;
-            if (m < n_marks && (unsigned)lane < len) v = __ldg(bank + m * n + j0 + lane);
+            float v = 0.f, x = 0.f;
+            if ((unsigned)lane < len) {
+                v = __ldg(bank + m * n + j0 + lane);
+                if (pair_mode) x = __ldg(extracted + (long long)m * ext_stride + j0 + lane);
+            }
             tile[r][lane] = v;
+            if (pair_mode) etile[r][lane] = x;
         }
         if (!pair_mode && t < (int)len) ex[t] = __ldg(ext + j0 + t);
         __syncthreads();
-        if (pair_mode) {
-            const size_t m = m0 + t;
-            if (m < n_marks) {
-                const float* xe = extracted + (long long)m * ext_stride + j0;
+        if (t < rows) {
+            if (pair_mode) {
+#pragma unroll 8
                 for (unsigned j = 0; j < len; ++j) {
-                    const float x = __ldg(xe + j);
+                    const float x = etile[t][j];
                     nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
                     den = __fadd_rn(den, __fmul_rn(x, x));
                 }
-            }
-        } else {
+            } else {
 #pragma unroll 8
-            for (unsigned j = 0; j < len; ++j) {
-                const float x = ex[j];
-                nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
-                den = __fadd_rn(den, __fmul_rn(x, x));
+                for (unsigned j = 0; j < len; ++j) {
+                    const float x = ex[j];
+                    nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
+                    den = __fadd_rn(den, __fmul_rn(x, x));
+                }
             }
         }
         __syncthreads();

@@ -59,6 +59,7 @@ struct ssw_ctx {
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
+    int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -136,6 +137,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_COL_PAIRS")) c->col_pairs = atoi(s);
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
+    if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     *out = c.release();
     return SSW_OK;
 }
@@ -366,7 +368,7 @@ static bool aligned(const void* p, size_t n) { return (((size_t)p) & (n - 1)) ==
 static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
                         float scale0, float scalen, bool* done) {
     *done = false;
-    if (!c->use_fast || (src_type != PIX_RGB8 && src_type != PIX_PLANE)) return SSW_OK;
+    if (!c->use_fast) return SSW_OK;
     if (!aligned(d_plane, 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
     int rc = SSW_OK;
     *done = fast::with_plan(w, [&](auto p) {
@@ -375,9 +377,28 @@ static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int 
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
         if (src_type == PIX_RGB8) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+        else if (src_type == PIX_RGB32F) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB32F>>(c, "fwd_rows_rgb32f", a, w, h, batch);
         else rc = launch_fast<fast::RowFwd<P, G, PIX_PLANE>>(c, "fwd_rows_plane", a, w, h, batch);
     });
     return rc;
+}
+
+template <class P, bool INV>
+static int launch_col_variant(ssw_ctx* c, const fast::FastArgs& a, int w, int h, int batch) {
+    const char* name = INV ? "inv_cols" : "fwd_cols";
+#ifdef SSW_TUNE
+    switch (c->col_variant) {
+        case 1: return launch_fast<fast::ColPass<P, 4, 4, INV>>(c, name, a, w, h, batch);
+        case 2: return launch_fast<fast::ColPass<P, 4, 1, INV>>(c, name, a, w, h, batch);
+        case 3: return launch_fast<fast::ColPass<P, 8, 4, INV>>(c, name, a, w, h, batch);
+        case 4: return launch_fast<fast::ColPass<P, 8, 2, INV>>(c, name, a, w, h, batch);
+        case 5: return launch_fast<fast::ColPass<P, 2, 2, INV>>(c, name, a, w, h, batch);
+        case 6: return launch_fast<fast::ColPass<P, 4, 2, INV, 3>>(c, name, a, w, h, batch);
+        case 7: return launch_fast<fast::ColPass<P, 2, 1, INV>>(c, name, a, w, h, batch);
+        default: break;
+    }
+#endif
+    return launch_fast<fast::ColPass<P, fast::kColG, fast::kColTeams, INV>>(c, name, a, w, h, batch);
 }
 
 static int fast_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen,
@@ -389,8 +410,8 @@ static int fast_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_
         using P = decltype(p);
         fast::FastArgs a = fast_args(w, h);
         a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
-        if (inverse) rc = launch_fast<fast::ColPass<P, fast::kColG, true>>(c, "inv_cols", a, w, h, batch);
-        else rc = launch_fast<fast::ColPass<P, fast::kColG, false>>(c, "fwd_cols", a, w, h, batch);
+        if (inverse) rc = launch_col_variant<P, true>(c, a, w, h, batch);
+        else rc = launch_col_variant<P, false>(c, a, w, h, batch);
     });
     return rc;
 }
@@ -399,17 +420,23 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
                         int dst_type, void* d_dst, float scale, bool* done) {
     *done = false;
     if (!c->use_fast || !aligned(d_plane, 16)) return SSW_OK;
-    const bool rgb8 = dst_type == PIX_RGB8 && src_type == PIX_RGB8 && aligned(d_src, 4) && aligned(d_dst, 4);
-    const bool plane = dst_type == PIX_PLANE && aligned(d_dst, 16);
-    if (!rgb8 && !plane) return SSW_OK;
+    if (dst_type == PIX_PLANE) {
+        if (!aligned(d_dst, 16)) return SSW_OK;
+    } else {
+        if (src_type == PIX_PLANE) return SSW_OK;
+        if (!aligned(d_dst, dst_type == PIX_RGB8 ? 4 : 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
+    }
     int rc = SSW_OK;
     *done = fast::with_plan(w, [&](auto p) {
         using P = decltype(p);
         constexpr int G = fast::RowG<P>::value;
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
-        if (rgb8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
-        else rc = launch_fast<fast::RowInv<P, G, PIX_PLANE>>(c, "inv_rows_plane", a, w, h, batch);
+        if (dst_type == PIX_PLANE) rc = launch_fast<fast::RowInv<P, G, PIX_PLANE, PIX_PLANE>>(c, "inv_rows_plane", a, w, h, batch);
+        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
+        else if (dst_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB32F>>(c, "inv_rows_src32f", a, w, h, batch);
+        else if (src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB32F, PIX_RGB8>>(c, "inv_rows_rgb32f_src8", a, w, h, batch);
+        else rc = launch_fast<fast::RowInv<P, G, PIX_RGB32F, PIX_RGB32F>>(c, "inv_rows_rgb32f", a, w, h, batch);
     });
     return rc;
 }

@@ -54,7 +54,7 @@ extern "C" {
 
 int emul_fast_has_plan(int n) { return has_plan(n) ? 1 : 0; }
 
-// src_type: 0 = RGB8, 2 = plane (PIX_*).  plane: [batch][h][w].  scale0/scalen: DCT2Orthogonal factors.
+// src_type: 0 = RGB8, 1 = RGB32F, 2 = plane (PIX_*).  plane: [batch][h][w].  scale0/scalen: DCT2Orthogonal factors.
 int emul_fast_row_fwd(int src_type, const void* src, int w, int h, int batch, float* plane, float scale0, float scalen) {
     return with_plan(w, [&](auto p) {
         using P = decltype(p);
@@ -65,6 +65,10 @@ int emul_fast_row_fwd(int src_type, const void* src, int w, int h, int batch, fl
         a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
         if (src_type == PIX_RGB8) {
             using K = RowFwd<P, G, PIX_RGB8>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate<K>(a, a.tiles_per_image * batch);
+        } else if (src_type == PIX_RGB32F) {
+            using K = RowFwd<P, G, PIX_RGB32F>;
             a.tiles_per_image = K::tiles_per_image(w, h);
             emulate<K>(a, a.tiles_per_image * batch);
         } else {
@@ -84,19 +88,19 @@ int emul_fast_col(int inverse, int w, int h, int batch, float* plane, float scal
         a.plane = plane; a.scale0 = scale0; a.scalen = scalen;
         a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
         if (inverse) {
-            using K = ColPass<P, kColG, true>;
+            using K = ColPass<P, kColG, kColTeams, true>;
             a.tiles_per_image = K::tiles_per_image(w, h);
             emulate<K>(a, a.tiles_per_image * batch);
         } else {
-            using K = ColPass<P, kColG, false>;
+            using K = ColPass<P, kColG, kColTeams, false>;
             a.tiles_per_image = K::tiles_per_image(w, h);
             emulate<K>(a, a.tiles_per_image * batch);
         }
     }) ? 0 : -2;
 }
 
-// dst_type: 0 = RGB8 (src = original RGB8 pixels), 2 = plane
-int emul_fast_row_inv(int dst_type, float* plane, const void* src, int w, int h, int batch, void* dst, float scale) {
+// dst_type / src_type: 0 = RGB8, 1 = RGB32F (src = original pixels), dst_type 2 = plane
+int emul_fast_row_inv(int dst_type, int src_type, float* plane, const void* src, int w, int h, int batch, void* dst, float scale) {
     return with_plan(w, [&](auto p) {
         using P = decltype(p);
         constexpr int G = RowG<P>::value;
@@ -104,15 +108,16 @@ int emul_fast_row_inv(int dst_type, float* plane, const void* src, int w, int h,
         FastArgs a = base_args(w, h);
         a.src = src; a.plane = plane; a.dst = dst; a.scale0 = scale;
         a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
-        if (dst_type == PIX_RGB8) {
-            using K = RowInv<P, G, PIX_RGB8>;
+        auto run = [&](auto k) {
+            using K = decltype(k);
             a.tiles_per_image = K::tiles_per_image(w, h);
             emulate<K>(a, a.tiles_per_image * batch);
-        } else {
-            using K = RowInv<P, G, PIX_PLANE>;
-            a.tiles_per_image = K::tiles_per_image(w, h);
-            emulate<K>(a, a.tiles_per_image * batch);
-        }
+        };
+        if (dst_type == PIX_PLANE) run(RowInv<P, G, PIX_PLANE, PIX_PLANE>{});
+        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) run(RowInv<P, G, PIX_RGB8, PIX_RGB8>{});
+        else if (dst_type == PIX_RGB8) run(RowInv<P, G, PIX_RGB8, PIX_RGB32F>{});
+        else if (src_type == PIX_RGB8) run(RowInv<P, G, PIX_RGB32F, PIX_RGB8>{});
+        else run(RowInv<P, G, PIX_RGB32F, PIX_RGB32F>{});
     }) ? 0 : -2;
 }
 
@@ -120,6 +125,13 @@ int emul_fast_row_inv(int dst_type, float* plane, const void* src, int w, int h,
 int emul_fast_u8_unit_mismatches(void) {
     int bad = 0;
     for (unsigned v = 0; v < 256; ++v) bad += (u8_unit(v) != u8_to_unit(v));
+    return bad;
+}
+
+// unit_to_u8_fast against the reference-faithful unit_to_u8(clamp01(v)) for a caller-supplied list
+int emul_fast_unit_to_u8_mismatches(const float* v, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; ++i) bad += (unit_to_u8_fast(v[i]) != unit_to_u8(v[i]));
     return bad;
 }
 

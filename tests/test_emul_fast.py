@@ -16,6 +16,17 @@ def test_u8_unit_is_exact(emul):
     assert emul.emul_fast_u8_unit_mismatches() == 0
 
 
+def test_unit_to_u8_fast_is_exact(emul):
+    rng = np.random.default_rng(0)
+    k = np.arange(0, 256, dtype=np.float64)
+    halves = ((k + 0.5) / 255.0).astype(np.float32)
+    edge = np.concatenate([np.nextafter(halves, np.float32(0)), halves, np.nextafter(halves, np.float32(2))])
+    tiny = np.array([0.5 / 255, np.nextafter(np.float32(0.5 / 255), np.float32(0)), 0.49999997 / 255, 0.0, -0.0, 1.0, -1.0, 2.0,
+                     np.nan, np.inf, -np.inf, 1e-30, 0.0019607842], np.float32)
+    v = np.concatenate([rng.random(200000).astype(np.float32) * 1.2 - 0.1, edge.astype(np.float32), tiny]).astype(np.float32)
+    assert emul.emul_fast_unit_to_u8_mismatches(ptr(v), len(v)) == 0
+
+
 def test_plan_table(emul):
     for n in FAST:
         assert emul.emul_fast_has_plan(n) == 1
@@ -43,7 +54,7 @@ def test_row_passes_plane(emul, so, n, h):
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
     back = np.zeros_like(a)
     c = ref.astype(np.float32)
-    assert emul.emul_fast_row_inv(2, ptr(c), None, n, h, 2, ptr(back), f32(2.0 / n)) == 0
+    assert emul.emul_fast_row_inv(2, 2, ptr(c), None, n, h, 2, ptr(back), f32(2.0 / n)) == 0
     assert np.abs(back - a).max() <= 3e-6
 
 
@@ -72,7 +83,7 @@ def test_fused_rgb8_frame_1080_rows(emul, so):
     ref = dct1d_rows(so, y, 'fwd')
     assert np.abs(plane - ref).max() <= 2e-6 * np.abs(ref).max()
     out = np.zeros_like(rgb)
-    assert emul.emul_fast_row_inv(0, ptr(plane.copy()), ptr(rgb), w, h, 1, ptr(out), f32(2.0 / w)) == 0
+    assert emul.emul_fast_row_inv(0, 0, ptr(plane.copy()), ptr(rgb), w, h, 1, ptr(out), f32(2.0 / w)) == 0
     assert np.abs(out.astype(int) - rgb.astype(int)).max() <= 1
     assert (out != rgb).mean() < 0.01
 
@@ -89,5 +100,26 @@ def test_full_frame_640x1080_matches_oracle(emul, so):
     assert (np.abs(plane - ref) <= tol).all()
     out = np.zeros_like(rgb)
     assert emul.emul_fast_col(1, w, h, 1, ptr(plane), f32(1.0), f32(1.0)) == 0
-    assert emul.emul_fast_row_inv(0, ptr(plane), ptr(rgb), w, h, 1, ptr(out), f32(4.0 / (w * h))) == 0
+    assert emul.emul_fast_row_inv(0, 0, ptr(plane), ptr(rgb), w, h, 1, ptr(out), f32(4.0 / (w * h))) == 0
     assert np.abs(out.astype(int) - rgb.astype(int)).max() <= 1
+
+
+def test_rgb32f_rows_match_rgb8_rows(emul, so):
+    """RGB32F pixels (u8/255 done by the caller, like into_rgb32f) give the same coefficients and the
+    RGB32F destination is the clamped float image whose into_rgb8 equals the fused RGB8 store"""
+    w, h = 1080, 4
+    rgb = so.synth_frame(w, h, seed=6)
+    rgbf = so.rgb8_to_rgb32f(rgb)
+    p8 = np.zeros((h, w), np.float32); p32 = np.zeros((h, w), np.float32)
+    assert emul.emul_fast_row_fwd(0, ptr(rgb), w, h, 1, ptr(p8), f32(1.0), f32(1.0)) == 0
+    assert emul.emul_fast_row_fwd(1, ptr(rgbf), w, h, 1, ptr(p32), f32(1.0), f32(1.0)) == 0
+    assert (p8 == p32).all()
+    p8[:, 1:8] *= 1.6  # perturb so that the output differs from the input
+    o8 = np.zeros_like(rgb); o32 = np.zeros_like(rgbf); o8b = np.zeros_like(rgb); o32b = np.zeros_like(rgbf)
+    s = f32(2.0 / w)
+    assert emul.emul_fast_row_inv(0, 0, ptr(p8.copy()), ptr(rgb), w, h, 1, ptr(o8), s) == 0
+    assert emul.emul_fast_row_inv(1, 0, ptr(p8.copy()), ptr(rgb), w, h, 1, ptr(o32), s) == 0
+    assert emul.emul_fast_row_inv(0, 1, ptr(p8.copy()), ptr(rgbf), w, h, 1, ptr(o8b), s) == 0
+    assert emul.emul_fast_row_inv(1, 1, ptr(p8.copy()), ptr(rgbf), w, h, 1, ptr(o32b), s) == 0
+    assert (so.rgb32f_to_rgb8(o32) == o8).all() and (o8b == o8).all() and (o32b == o32).all()
+    assert o32.min() >= 0.0 and o32.max() <= 1.0 and (o8 != rgb).any()
