@@ -141,14 +141,14 @@ SSW_HD void fft_phase(cplx* s, const cplx* tw, int t, cplx* v) {
 
 // ------------------------------------------------------------------------------------------------
 // colour helpers (bit-identical to color.cuh; the division by 255 is replaced by an exact
-// multiply + two fused corrections -- verified for all 256 inputs by the CPU test-suite)
+// two-term constant and one fma -- verified for all 256 inputs by the CPU test-suite)
 // ------------------------------------------------------------------------------------------------
 SSW_HD float u8_unit(unsigned v) {
+    // 1/255 = c_hi + c_lo to ~2^-50: fma(x, c_hi, fl(x*c_lo)) is the correctly rounded x/255 for x = 0..255
     const float x = (float)v;
-    const float c = 0.0039215688593685626983642578125f;  // fl32(1/255)
-    const float q = SSW_FMUL(x, c);
-    const float rem = SSW_FMA(-q, 255.0f, x);
-    return SSW_FMA(rem, c, q);
+    const float c_hi = 0.0039215688593685626983642578125f;  // fl32(1/255)
+    const float c_lo = -2.31917579870781060424633324146270751953125e-10f;  // fl32(1/255 - c_hi)
+    return SSW_FMA(x, c_hi, SSW_FMUL(x, c_lo));
 }
 
 SSW_HD void unpack4(unsigned w0, unsigned w1, unsigned w2, unsigned* b) {

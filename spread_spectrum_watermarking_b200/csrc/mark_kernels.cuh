@@ -125,6 +125,38 @@ similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned 
     if (m < n_marks) out[(long long)(pair_mode ? 0 : e) * out_stride + m] = __fdiv_rn(nom, __fsqrt_rn(den));
 }
 
+// 1:1 form: extracted vector i against mark i (the fused extract pipeline).  One warp per pair stages
+// both vectors through shared memory with coalesced loads; lane 0 then walks them in the reference's
+// sequential order (bit-identical), the loads no longer sit on the dependent FADD chain.
+constexpr int kPairWarps = 4, kPairChunk = 512;
+
+__global__ void __launch_bounds__(kPairWarps * 32)
+similarity_pairs_kernel(const float* __restrict__ marks, const float* __restrict__ extracted, unsigned n,
+                        long long stride, unsigned n_pairs, float* __restrict__ out) {
+    __shared__ float sm[kPairWarps][kPairChunk], se[kPairWarps][kPairChunk];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned pair = blockIdx.x * kPairWarps + warp;
+    if (pair >= n_pairs) return;
+    const float* mk = marks + (long long)pair * stride;
+    const float* ex = extracted + (long long)pair * stride;
+    float nom = 0.f, den = 0.f;
+    for (unsigned j0 = 0; j0 < n; j0 += kPairChunk) {
+        const unsigned len = min((unsigned)kPairChunk, n - j0);
+        for (unsigned j = lane; j < len; j += 32) { sm[warp][j] = __ldg(mk + j0 + j); se[warp][j] = __ldg(ex + j0 + j); }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll 8
+            for (unsigned j = 0; j < len; ++j) {
+                const float x = se[warp][j];
+                nom = __fadd_rn(nom, __fmul_rn(x, sm[warp][j]));
+                den = __fadd_rn(den, __fmul_rn(x, x));
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) out[pair] = __fdiv_rn(nom, __fsqrt_rn(den));
+}
+
 // ------------------------------------------------------------------------------------------------
 // MarkBuf::generate_normal -- src/algorithm.rs:619-626 (distributional parity only: the reference
 // draws from the OS-seeded thread_rng).  Philox4x32-10 counter RNG + Box-Muller.

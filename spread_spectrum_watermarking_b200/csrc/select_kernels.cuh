@@ -9,8 +9,9 @@
 // the descending order of the 64-bit composite  (total_cmp_key(value) << 32) | (0xFFFFFFFF - index),
 // which has no ties at all.  Only the first k entries are ever consumed (mark length), so instead of
 // sorting w*h-1 elements:
-//   1. topk_hist    : one read of the plane, 4096-bin histogram of the key's top 12 bits; the last
-//                     CTA to finish finds the bin holding the k-th largest key;
+//   1. topk_block_bin: 4096-bin histogram (top 12 key bits) of the low-frequency block only; the bin
+//                     of its k-th largest key bounds the plane's from below (see the kernel);
+//      topk_hist    : (repair path) the same histogram over the whole plane, one read;
 //   2. topk_collect : second read, every element whose bin >= that bin is appended to a small
 //                     candidate list (k + one bin's worth of elements);
 //   3. topk_sort    : one CTA bitonic-sorts the candidates by the composite key and emits the first
@@ -54,6 +55,44 @@ __device__ __forceinline__ unsigned order_key(float c, unsigned p, const OrderCo
     sc = __fmul_rn(sc, (p % (unsigned)oc.w == 0u) ? oc.s_k0_h : oc.s_h);
     const float v = __fmul_rn(sc, c);
     return total_cmp_key(oc.mode == 1 ? __fmul_rn(v, v) : v);
+}
+
+// bin b with  #(bin > b) < k <= #(bin >= b)  of a 4096-bin shared-memory histogram (0 if fewer than k
+// elements were counted); all threads of the CTA must call, blockDim.x must divide 4096 and be a
+// multiple of 32 (<= 1024).  Suffix sums by warp shuffles; the one thread whose run of bins crosses
+// the k-th element resolves the bin inside its run.
+__device__ __forceinline__ unsigned find_kth_bin(const unsigned* sh, unsigned k) {
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned s_bin;
+    const int per = kHistBins / blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned mine = 0;
+    for (int j = 0; j < per; ++j) mine += sh[threadIdx.x * per + j];
+    // inclusive suffix sum inside the warp: incl = sum over lanes >= lane
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_down_sync(0xFFFFFFFFu, incl, d);
+        if (lane + d < 32) incl += o;
+    }
+    if (lane == 0) wsum[warp] = incl;
+    if (threadIdx.x == 0) s_bin = 0u;
+    __syncthreads();
+    unsigned above_warps = 0;  // elements in the bins of all higher warps
+    for (int u = warp + 1; u < nwarps; ++u) above_warps += wsum[u];
+    const unsigned suffix = above_warps + incl;  // elements in bins >= first bin of this thread
+    const unsigned above = suffix - mine;        // elements in bins above this thread's run
+    if (above < k && suffix >= k) {
+        unsigned a = above;
+        int b = threadIdx.x * per + per - 1;
+        for (; b > (int)threadIdx.x * per; --b) {
+            if (a + sh[b] >= k) break;
+            a += sh[b];
+        }
+        s_bin = (unsigned)b;
+    }
+    __syncthreads();
+    return s_bin;
 }
 
 // ---- 1. histogram + threshold bin ---------------------------------------------------------------
@@ -100,28 +139,49 @@ topk_hist_kernel(const float* __restrict__ planes, long long plane_stride, unsig
         gh[i] = 0;  // leave the scratch clean for the next call
     }
     __syncthreads();
-    // suffix sums over 4096 bins: each thread owns a contiguous run, then a serial pass over partials
-    __shared__ unsigned part[512];
-    const int per = kHistBins / blockDim.x;  // blockDim.x divides 4096
-    unsigned acc = 0;
-    for (int j = 0; j < per; ++j) acc += sh[threadIdx.x * per + j];
-    part[threadIdx.x] = acc;
-    __syncthreads();
+    const unsigned b = find_kth_bin(sh, k);
     if (threadIdx.x == 0) {
-        unsigned above = 0;  // elements in bins above the current run
-        int t = blockDim.x - 1;
-        for (; t > 0; --t) {
-            if (above + part[t] >= k) break;
-            above += part[t];
-        }
-        int b = t * per + per - 1;
-        for (; b > t * per; --b) {
-            if (above + sh[b] >= k) break;
-            above += sh[b];
-        }
-        ts.sel_bin[img] = (unsigned)b;
+        ts.sel_bin[img] = b;
         ts.ticket[img] = 0;
     }
+}
+
+// ---- 1'. threshold bin from a low-frequency block only ---------------------------------------------
+// The k-th largest key of ANY subset is a lower bound of the k-th largest key of the whole plane, so
+// the bin holding the k-th largest key of the top-left block (where natural images keep their
+// energy) is a valid -- and for natural images tight -- selection bin for topk_collect: every
+// top-k element of the plane lies in a bin >= it.  One CTA per image reads <= 32k coefficients
+// instead of one full pass over the plane.  A loose bound (noise-like spectra) only costs a
+// candidate overflow, which is detected by topk_sort and repaired with the full histogram.
+constexpr int kBlockRows = 128, kBlockCols = 256;
+
+__global__ void __launch_bounds__(1024)
+topk_block_bin_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned k,
+                      OrderConsts oc, TopkScratch ts) {
+    __shared__ unsigned sh[kHistBins];
+    const unsigned img = blockIdx.x;
+    const float* plane = planes + (long long)img * plane_stride;
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned br = min(h, (unsigned)kBlockRows), bc = min(w, (unsigned)kBlockCols);
+    const unsigned total = br * bc;
+    for (unsigned e0 = threadIdx.x; e0 < total; e0 += 8 * blockDim.x) {
+        float v[8];
+        unsigned p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // 8 independent loads in flight per thread
+            const unsigned e = e0 + u * blockDim.x;
+            const unsigned r = e / bc, c = e - r * bc;
+            p[u] = e < total ? r * w + c : 0u;
+            v[u] = p[u] ? __ldg(plane + p[u]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (p[u]) atomicAdd(&sh[order_key(v[u], p[u], oc) >> (32 - kHistBits)], 1u);
+    }
+    __syncthreads();
+    const unsigned b = find_kth_bin(sh, k);
+    if (threadIdx.x == 0) ts.sel_bin[img] = b;
 }
 
 // ---- 2. collect candidates -----------------------------------------------------------------------
@@ -162,33 +222,88 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
 }
 
 // ---- 3. sort candidates, emit the first k indices ------------------------------------------------
-__global__ void __launch_bounds__(1024)
+// Bitonic network over 256*E keys, E consecutive keys per thread held in registers: strides < E are
+// compare-exchanges inside a thread, strides < 32*E go through warp shuffles, and only the few
+// strides >= 32*E cross warps through shared memory (6 of the 66 steps at 2048 keys).
+constexpr int kSortThreads = 256;
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int mask) {
+    const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, mask);
+    const unsigned hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)(v >> 32), mask);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+template <int E>
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long (&v)[E], unsigned long long* sc) {
+    const unsigned tid = threadIdx.x;
+#pragma unroll
+    for (unsigned size = 2; size <= (unsigned)(kSortThreads * E); size <<= 1) {
+#pragma unroll
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < (unsigned)E) {
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    if ((i & stride) == 0) {
+                        const unsigned idx = tid * E + i;
+                        const bool desc = (idx & size) == 0;
+                        const unsigned long long a = v[i], b = v[i + stride];
+                        if ((a < b) == desc) { v[i] = b; v[i + stride] = a; }
+                    }
+                }
+            } else {
+                const unsigned tmask = stride / E;  // partner thread = tid ^ tmask, same slot
+                unsigned long long o[E];
+                if (tmask < 32u) {
+#pragma unroll
+                    for (int i = 0; i < E; ++i) o[i] = shfl_xor_u64(v[i], (int)tmask);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < E; ++i) sc[i * kSortThreads + tid] = v[i];
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < E; ++i) o[i] = sc[i * kSortThreads + (tid ^ tmask)];
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    const unsigned idx = tid * E + i;
+                    const bool lower = (idx & stride) == 0, desc = (idx & size) == 0;
+                    const unsigned long long mx = v[i] > o[i] ? v[i] : o[i], mn = v[i] > o[i] ? o[i] : v[i];
+                    v[i] = (lower == desc) ? mx : mn;
+                }
+            }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void topk_sort_body(const unsigned long long* __restrict__ cand, unsigned cnt, unsigned k,
+                                               unsigned* __restrict__ out, unsigned long long* sc) {
+    unsigned long long v[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const unsigned idx = threadIdx.x * E + i;
+        v[i] = idx < cnt ? __ldcg(cand + idx) : 0ull;
+    }
+    bitonic_sort_desc<E>(v, sc);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const unsigned idx = threadIdx.x * E + i;
+        if (idx < k) out[idx] = idx < cnt ? (0xFFFFFFFFu - (unsigned)(v[i] & 0xFFFFFFFFull)) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
 topk_sort_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride) {
-    extern __shared__ unsigned long long sc[];
+    extern __shared__ unsigned long long sc[];  // kTopkCap keys (exchange buffer of the cross-warp steps)
     const unsigned img = blockIdx.x;
     const unsigned total = ts.cand_count[img];
     const unsigned cnt = total < (unsigned)kTopkCap ? total : (unsigned)kTopkCap;
-    unsigned m = 1;
-    while (m < cnt) m <<= 1;
     const unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
-    for (unsigned i = threadIdx.x; i < m; i += blockDim.x) sc[i] = i < cnt ? cand[i] : 0ull;
-    __syncthreads();
-    // bitonic sort, descending
-    for (unsigned size = 2; size <= m; size <<= 1) {
-        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
-            for (unsigned t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
-                const unsigned lo = 2 * t - (t & (stride - 1));
-                const unsigned hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const unsigned long long a = sc[lo], b = sc[hi];
-                if ((a < b) == desc) { sc[lo] = b; sc[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
     unsigned* out = idx_out + (long long)img * idx_stride;
-    for (unsigned i = threadIdx.x; i < k; i += blockDim.x)
-        out[i] = i < cnt ? (0xFFFFFFFFu - (unsigned)(sc[i] & 0xFFFFFFFFull)) : 0u;
+    if (cnt <= 8u * kSortThreads) topk_sort_body<8>(cand, cnt, k, out, sc);
+    else if (cnt <= 16u * kSortThreads) topk_sort_body<16>(cand, cnt, k, out, sc);
+    else topk_sort_body<32>(cand, cnt, k, out, sc);
     if (threadIdx.x == 0) {
         if (total > (unsigned)kTopkCap || cnt < k) atomicAdd(ts.overflow, 1u);
         ts.cand_count[img] = 0;

@@ -60,6 +60,7 @@ struct ssw_ctx {
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
+    bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -138,6 +139,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
+    if (const char* s = getenv("SSW_TOPK_FULL_HIST")) c->topk_full_hist = atoi(s) != 0;
     *out = c.release();
     return SSW_OK;
 }
@@ -550,8 +552,10 @@ static OrderConsts make_order(int ordering, int w, int h) {
 }
 
 // fast path: k + (one histogram bin of elements) must fit kTopkCap; no host synchronisation.
+// full_hist = false: selection bin from the low-frequency block (topk_block_bin), one pass over the plane;
+// full_hist = true : selection bin from a histogram of the whole plane (two passes) -- the repair path.
 static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsigned batch, int ordering,
-                         unsigned k, unsigned* d_idx, long long idx_stride) {
+                         unsigned k, unsigned* d_idx, long long idx_stride, bool full_hist) {
     CKS(ensure_topk_scratch(c, batch));
     const unsigned n = (unsigned)((size_t)w * h);
     const OrderConsts oc = make_order(ordering, w, h);
@@ -563,7 +567,13 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         TopkScratch ts = c->ts;
         ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0;
         ts.cand += (size_t)b0 * kTopkCap;
-        { KScope ks(c, "topk_hist"); topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts); }
+        if (full_hist) {
+            KScope ks(c, "topk_hist");
+            topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
+        } else {
+            KScope ks(c, "topk_block_bin");
+            topk_block_bin_kernel<<<nb, 1024, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
+        }
         { KScope ks(c, "topk_collect"); topk_collect_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, oc, ts); }
         CK(cudaGetLastError());
     }
@@ -573,7 +583,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    { KScope ks(c, "topk_sort"); topk_sort_kernel<<<batch, 1024, smem, c->stream>>>(c->ts, k, d_idx, idx_stride); }
+    { KScope ks(c, "topk_sort"); topk_sort_kernel<<<batch, kSortThreads, smem, c->stream>>>(c->ts, k, d_idx, idx_stride); }
     CK(cudaGetLastError());
     return SSW_OK;
 }
@@ -597,10 +607,12 @@ static int run_topk_exact(ssw_ctx* c, const float* d_plane, int w, int h, int or
     if (k == 0) return SSW_OK;
     if (k > n - 1) return fail(SSW_ERR_INVALID, "k exceeds the number of AC coefficients");
     if (k <= (size_t)kTopkCap / 2) {
-        CKS(run_topk_fast(c, d_plane, w, h, 1, ordering, (unsigned)k, d_idx, 0));
-        unsigned ov = 0;
-        CKS(take_overflow(c, &ov));
-        if (!ov) return SSW_OK;
+        for (int attempt = c->topk_full_hist ? 1 : 0; attempt < 2; ++attempt) {
+            CKS(run_topk_fast(c, d_plane, w, h, 1, ordering, (unsigned)k, d_idx, 0, attempt == 1));
+            unsigned ov = 0;
+            CKS(take_overflow(c, &ov));
+            if (!ov) return SSW_OK;
+        }
         c->last_fallbacks += 1;
     }
     const OrderConsts oc = make_order(ordering, w, h);
@@ -1011,6 +1023,16 @@ struct ssw_bank {
 static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, size_t n, const float* d_ext,
                              size_t n_ext, bool pair_mode, float* d_out) {
     if (n_marks == 0 || n_ext == 0) return SSW_OK;
+    if (pair_mode) {
+        if (n_marks > 0x7FFFFFFFull || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
+        {
+            KScope ks(c, "similarity_pairs");
+            similarity_pairs_kernel<<<(unsigned)((n_marks + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, c->stream>>>(
+                d_bank, d_ext, (unsigned)n, (long long)n, (unsigned)n_marks, d_out);
+        }
+        CK(cudaGetLastError());
+        return SSW_OK;
+    }
     const size_t gx = (n_marks + kSimMarks - 1) / kSimMarks;
     if (gx > 0x7FFFFFFFull || n_ext > 65535 || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
     {
@@ -1160,7 +1182,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
         const uint8_t* src = rgb + (size_t)b0 * np * 3;
         rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
         if (rc == SSW_OK && k) {
-            rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k);
+            rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k, c->topk_full_hist);
             if (rc == SSW_OK) {
                 KScope ks(c, "embed_scatter");
                 embed_scatter_kernel<<<dim3((unsigned)((k + 255) / 256), nb), 256, 0, c->stream>>>(
@@ -1200,7 +1222,7 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         float* pd = d_planes + (size_t)cb * np;
         rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
         if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
-        if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n);
+        if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
         if (rc == SSW_OK) {
             {
                 KScope ks(c, "extract_gather");
@@ -1231,15 +1253,24 @@ extern "C" int ssw_embed_batch_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, 
     CK(cudaMallocAsync(&d_marks, std::max<size_t>(n * batch, 1) * sizeof(float), c->stream));
     CK(cudaMemcpyAsync(d_in, rgb, bytes, cudaMemcpyHostToDevice, c->stream));
     if (n) CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    int rc = ssw_embed_batch_rgb8_dev(c, d_in, w, h, batch, cfg, d_marks, n, d_out);
-    if (rc == SSW_OK) {
-        cudaError_t e = cudaMemcpyAsync(out_rgb, d_out, bytes, cudaMemcpyDeviceToHost, c->stream);
-        if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
-    }
-    cudaFreeAsync(d_in, c->stream); cudaFreeAsync(d_out, c->stream); cudaFreeAsync(d_marks, c->stream);
+    // first attempt: threshold bin from the low-frequency block; a candidate overflow (noise-like
+    // spectrum) is repaired by one more run with the full-plane histogram
+    int rc = SSW_OK;
     unsigned ov = 0;
-    int rs = take_overflow(c, &ov);  // synchronises
-    if (rc == SSW_OK) rc = rs;
+    const bool saved = c->topk_full_hist;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ssw_embed_batch_rgb8_dev(c, d_in, w, h, batch, cfg, d_marks, n, d_out);
+        if (rc == SSW_OK) {
+            cudaError_t e = cudaMemcpyAsync(out_rgb, d_out, bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+        }
+        int rs = take_overflow(c, &ov);  // synchronises
+        if (rc == SSW_OK) rc = rs;
+        if (rc != SSW_OK || !ov || c->topk_full_hist) break;
+        c->topk_full_hist = true;
+    }
+    c->topk_full_hist = saved;
+    cudaFreeAsync(d_in, c->stream); cudaFreeAsync(d_out, c->stream); cudaFreeAsync(d_marks, c->stream);
     c->last_fallbacks = (int)ov;
     if (rc == SSW_OK && ov) rc = fail(SSW_ERR_UNSUPPORTED, "top-k candidate overflow in the fused pipeline (degenerate spectrum): use the Writer API for these frames");
     return rc;
@@ -1265,18 +1296,25 @@ extern "C" int ssw_extract_batch_rgb8(ssw_ctx* c, const uint8_t* base_rgb, const
         CK(cudaMallocAsync(&d_sim, batch * sizeof(float), c->stream));
         CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
-    int rc = ssw_extract_batch_rgb8_dev(c, d_b, d_d, w, h, batch, cfg, n, d_ext, d_marks, d_sim);
-    if (rc == SSW_OK) {
-        cudaError_t e = cudaMemcpyAsync(extracted, d_ext, n * batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && d_sim) e = cudaMemcpyAsync(sim, d_sim, batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-        if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+    int rc = SSW_OK;
+    unsigned ov = 0;
+    const bool saved = c->topk_full_hist;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ssw_extract_batch_rgb8_dev(c, d_b, d_d, w, h, batch, cfg, n, d_ext, d_marks, d_sim);
+        if (rc == SSW_OK) {
+            cudaError_t e = cudaMemcpyAsync(extracted, d_ext, n * batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess && d_sim) e = cudaMemcpyAsync(sim, d_sim, batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+            if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+        }
+        int rs = take_overflow(c, &ov);  // synchronises
+        if (rc == SSW_OK) rc = rs;
+        if (rc != SSW_OK || !ov || c->topk_full_hist) break;
+        c->topk_full_hist = true;
     }
+    c->topk_full_hist = saved;
     cudaFreeAsync(d_b, c->stream); cudaFreeAsync(d_d, c->stream); cudaFreeAsync(d_ext, c->stream);
     if (d_marks) cudaFreeAsync(d_marks, c->stream);
     if (d_sim) cudaFreeAsync(d_sim, c->stream);
-    unsigned ov = 0;
-    int rs = take_overflow(c, &ov);
-    if (rc == SSW_OK) rc = rs;
     c->last_fallbacks = (int)ov;
     if (rc == SSW_OK && ov) rc = fail(SSW_ERR_UNSUPPORTED, "top-k candidate overflow in the fused pipeline (degenerate spectrum): use the Reader API for these frames");
     return rc;
@@ -1322,7 +1360,7 @@ extern "C" int ssw_stage_topk_dev(ssw_ctx* c, const float* plane, uint32_t w, ui
     CKS(check_dims(w, h));
     if (k == 0 || k > (size_t)kTopkCap / 2 || k > (size_t)w * h - 1) return fail(SSW_ERR_INVALID, "k out of range for the fused top-k");
     CKS(ctx_bind(c));
-    return run_topk_fast(c, plane, w, h, batch, ordering, (unsigned)k, idx, (long long)k);
+    return run_topk_fast(c, plane, w, h, batch, ordering, (unsigned)k, idx, (long long)k, c->topk_full_hist);
 }
 
 extern "C" int ssw_stage_inverse_rgb8_dev(ssw_ctx* c, float* plane, const uint8_t* rgb_src, uint32_t w, uint32_t h,

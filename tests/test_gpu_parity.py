@@ -224,7 +224,9 @@ def test_general_topk_full_ordering_and_ties(wm, ctx, so):
     flat = np.full((64, 64, 3), 128, np.uint8)                  # every AC coefficient ~0: ties everywhere
     r2 = wm.Reader.base(flat, ctx=ctx)
     assert (r2.indices(100) == so.obtain_indices(r2.coefficients(), k=100)).all()
-    assert (r2.indices(5000) == so.obtain_indices(r2.coefficients(), k=5000)).all()
+    assert (r2.indices(4000) == so.obtain_indices(r2.coefficients(), k=4000)).all()
+    with pytest.raises(wm.SswError):   # only 64*64-1 AC coefficients exist
+        r2.indices(5000)
 
 
 def test_rgb32f_entry_points(wm, ctx, so):
@@ -301,7 +303,7 @@ def test_fused_batch_embed_extract(wm, ctx, so, w, h, B):
     ctx.synchronize()
     assert ctx.last_topk_fallbacks() == 0
     sims = sim.cpu().numpy()
-    assert (sims > 20).all(), sims
+    assert (sims > 12).all(), sims   # oracle: 16.7 / 18.2 on the small 640x444 frames, ~30 at 1080p and 4K
     last = B - 1   # check the last image of the batch against the oracle end to end
     f = frames[last].cpu().numpy()
     ref_img, ref_idx, _ = so.embed(f, [mk_h[last]])
@@ -364,4 +366,25 @@ def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
             ref, _, _ = so.embed(rgb, [mark])
             assert np.abs(of.astype(int) - ref.astype(int)).max() <= 1
     finally:
+        wg = wf = None  # writers must go before their contexts
+        import gc
+        gc.collect()
         cg.close(); cf.close()
+
+
+def test_topk_block_bound_is_repaired_on_flat_spectra(wm, ctx, so):
+    """white-noise frame: the low-frequency block's k-th key is a loose lower bound, the candidate list
+    overflows and the full-plane histogram (then, if needed, the general sort) takes over -- the
+    ordering must still be the exact one, through the Reader API and through the fused host API"""
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    r = wm.Reader.base(noise, ctx=ctx)
+    c = r.coefficients()
+    assert (r.indices(1000) == so.obtain_indices(c, k=1000)).all()
+    mark = rng.standard_normal(1000).astype(np.float32)
+    api = wm.Writer.new(noise, ctx=ctx).mark_rgb8([mark])
+    out = np.empty_like(noise)
+    cfg = wm._lib.ssw_config(2, 0.1, 0)
+    wm._lib.check(wm.lib.ssw_embed_batch_rgb8(ctx.handle, noise.ctypes.data, 1920, 1080, 1, ctypes.byref(cfg),
+                                              mark.ctypes.data, 1000, out.ctypes.data))
+    assert (out == api).all()
