@@ -41,16 +41,20 @@ sys.path.insert(0, ROOT)
 
 MARK_LEN = 1000
 ALPHA = 0.1
+BANK_MARKS = 100000   # BASELINE.json configs[4]: bank of 100k stored marks of length 1000
 WORKLOADS = {
     # name: (w, h, frames per step, ring size (steps before inputs repeat), seed)
     'c2': dict(w=3840, h=2160, batch=1, ring=8, seed=2,
                name='single synthetic 3840x2160 RGB frame, mark length 1000, embed+extract'),
     'c3': dict(w=1920, h=1080, batch=64, ring=2, seed=3,
                name='batches of synthetic 1920x1080 RGB frames, mark length 1000, embed+extract'),
+    'c5': dict(w=3840, h=2160, batch=1, ring=8, seed=5,
+               name='extraction on 3840x2160 frames + similarity against a bank of 100k stored marks (length 1000)'),
 }
 # ALGORITHMIC bytes per pixel of one launch over one frame (DESIGN.md "Kernels")
 # how many times one step runs each kernel over a full batch of frames (embed: 1 forward + 1 top-k +
 # 1 inverse; extract: 2 forwards + 1 top-k) -- used to turn "launches per step" into pixels per launch
+PASSES_PER_STEP_C5 = {'fwd_rows': 2, 'fwd_cols': 2, 'topk_collect': 1, 'topk_hist': 1}
 PASSES_PER_STEP = {'row_fwd_rgb8': 3, 'col_fwd': 3, 'col_inv': 1, 'row_inv_rgb8': 1, 'topk_hist': 2, 'topk_collect': 2,
                    'fwd_rows': 3, 'fwd_cols': 3, 'fwd_cols_hist': 3, 'inv_cols': 1, 'inv_rows': 1, 'topk_select': 2}
 ALGO_BYTES_PER_PX = {
@@ -306,7 +310,27 @@ def run_ours(args, wl):
                                              MARK_LEN, ext.data_ptr() + o * MARK_LEN * 4, marks.data_ptr() + o * MARK_LEN * 4,
                                              sim.data_ptr() + o * 4))
 
+    bank = None
+    if args.workload == 'c5':
+        # every frame of the ring carries bank row (17 + 1000*i); a step = extract + score against the bank
+        bank = wm.Bank.normal(wl['seed'], BANK_MARKS, MARK_LEN, ctx=ctx)
+        for i in range(nfr):
+            marks_h[i] = bank.row(17 + 1000 * i)
+        marks = torch.from_numpy(marks_h).cuda()
+        scores = torch.empty((BANK_MARKS,), dtype=torch.float32, device='cuda')
+        for i in range(ring):
+            embed(i)
+        ctx.synchronize()
+
+    def extract_bank(s):
+        o = (s % ring) * B
+        check(lib.ssw_extract_batch_rgb8_dev(ctx.handle, frames.data_ptr() + o * fb, outs.data_ptr() + o * fb, w, h, B, pcfg,
+                                             MARK_LEN, ext.data_ptr() + o * MARK_LEN * 4, None, None))
+        check(lib.ssw_bank_similarity_dev(bank.handle, ext.data_ptr() + o * MARK_LEN * 4, 1, scores.data_ptr()))
+
     def step(s):
+        if bank is not None:
+            return extract_bank(s)
         embed(s); extract(s)
 
     def timed(fn, steps, warmup):
@@ -338,6 +362,12 @@ def run_ours(args, wl):
     ms_extract = timed(extract, K, 1)
     fallbacks = ctx.last_topk_fallbacks()
     sims = sim.cpu().numpy()[:min(nfr, (K + W) * B)]
+    if bank is not None:
+        last = (W + K - 1) % ring
+        sc = scores.cpu().numpy()
+        if int(sc.argmax()) != 17 + 1000 * last or not sc.max() > 6.0 or (np.sort(sc)[-2] > 6.0):
+            raise SystemExit('bench c5: the bank search did not single out the embedded mark (argmax %d, max %.2f)'
+                             % (int(sc.argmax()), float(sc.max())))
     if not (sims > 6.0).all() or fallbacks:
         raise SystemExit('bench: extraction failed to detect the embedded marks (min sim %.2f, fallbacks %d)'
                          % (float(sims.min()), fallbacks))
@@ -356,10 +386,17 @@ def run_ours(args, wl):
     for name, r in prof.items():
         avg_us = r['ms'] / r['launches'] * 1e3
         bpp = ALGO_BYTES_PER_PX.get(name)
+        if bank is not None and name == 'similarity_bank':   # 4 B per bank element + the scores
+            ab = 4.0 * BANK_MARKS * MARK_LEN + 4.0 * BANK_MARKS
+            kernels.append({'name': name, 'launches_per_step': r['launches'] / K, 'avg_us': round(avg_us, 2), 'share': 0.0,
+                            'algo_bytes': ab, 'gbs': round(ab / (avg_us * 1e-6) / 1e9, 1),
+                            'frac': round(ab / (avg_us * 1e-6) / 1e9 / peak, 4)})
+            continue
         ent = {'name': name, 'launches_per_step': r['launches'] / K, 'avg_us': round(avg_us, 2),
                'share': 0.0, 'algo_bytes': None, 'gbs': None, 'frac': None}
         if bpp:
-            ab = bpp * px_step * PASSES_PER_STEP.get(name, 1) * K / r['launches']   # bytes of ONE launch
+            passes = (PASSES_PER_STEP_C5 if bank is not None else PASSES_PER_STEP).get(name, 1)
+            ab = bpp * px_step * passes * K / r['launches']   # bytes of ONE launch
             ent.update(algo_bytes=ab, gbs=round(ab / (avg_us * 1e-6) / 1e9, 1), frac=round(ab / (avg_us * 1e-6) / 1e9 / peak, 4))
         kernels.append(ent)
     tot = sum(r['ms'] for r in prof.values()) or 1.0
@@ -391,11 +428,20 @@ def run_ours(args, wl):
     hm, _p3 = pinned(e2e_ring * B * MARK_LEN * 4, np.float32, (e2e_ring, B, MARK_LEN))
     he, _p4 = pinned(B * MARK_LEN * 4, np.float32, (B, MARK_LEN))
     hs, _p5 = pinned(max(B * 4, 64), np.float32, (max(B, 16),))
+    hsc = np.empty(BANK_MARKS, np.float32)
+    if bank is not None:
+        ho[...] = outs[:e2e_ring * B].cpu().numpy().reshape(ho.shape)
     hf[...] = frames[:e2e_ring * B].cpu().numpy().reshape(hf.shape)
     hm[...] = marks_h[:e2e_ring * B].reshape(hm.shape)
 
     def e2e_step(s):
         r = s % e2e_ring
+        if bank is not None:   # host frames in, 100k scores out
+            check(lib.ssw_extract_batch_rgb8(ctx.handle, hf[r].ctypes.data, ho[r].ctypes.data, w, h, B, pcfg, MARK_LEN,
+                                             he.ctypes.data, None, None))
+            check(lib.ssw_bank_similarity(bank.handle, he.ctypes.data, 1, hsc.ctypes.data))
+            hs[0] = hsc.max()
+            return
         check(lib.ssw_embed_batch_rgb8(ctx.handle, hf[r].ctypes.data, w, h, B, pcfg, hm[r].ctypes.data, MARK_LEN, ho[r].ctypes.data))
         check(lib.ssw_extract_batch_rgb8(ctx.handle, hf[r].ctypes.data, ho[r].ctypes.data, w, h, B, pcfg, MARK_LEN,
                                          he.ctypes.data, hm[r].ctypes.data, hs.ctypes.data))
@@ -418,12 +464,14 @@ def run_ours(args, wl):
     if not (hs[:B] > 6.0).all():
         raise SystemExit('bench: e2e extraction failed to detect the embedded marks')
     e2e = {'value': world * px_step * Ke / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s',
-           'h2d_bytes_per_step': B * (3 * fb + 2 * MARK_LEN * 4), 'd2h_bytes_per_step': B * (fb + MARK_LEN * 4 + 4),
+           'h2d_bytes_per_step': B * (3 * fb + 2 * MARK_LEN * 4) if bank is None else B * 2 * fb + MARK_LEN * 4,
+           'd2h_bytes_per_step': B * (fb + MARK_LEN * 4 + 4) if bank is None else B * MARK_LEN * 4 + BANK_MARKS * 4,
            'steps': Ke, 'ms_per_step': e2e_ms / Ke,
-           'api': 'ssw_embed_batch_rgb8 + ssw_extract_batch_rgb8 (pinned host buffers)'}
+           'api': ('ssw_embed_batch_rgb8 + ssw_extract_batch_rgb8 (pinned host buffers)' if bank is None else
+                   'ssw_extract_batch_rgb8 + ssw_bank_similarity (host buffers)')}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and bank is None:
         f0 = [frames[i].cpu().numpy() for i in range(min(2, nfr))]
         cpu = cpu_baseline(wl, f0, [marks_h[i] for i in range(len(f0))])
 
@@ -443,6 +491,8 @@ def run_ours(args, wl):
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk,
             'min_similarity': float(sims.min()),
         }), flush=True)
+    if bank is not None:
+        bank.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

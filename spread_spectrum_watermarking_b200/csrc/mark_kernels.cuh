@@ -68,61 +68,78 @@ __global__ void extract_gather_kernel(const float* __restrict__ base, const floa
 // One thread per stored mark walks the vectors in the reference's sequential order with separate
 // f32 multiply and add, so every score is bit-identical to the reference loop.  The bank tile is
 // staged through shared memory so global reads stay coalesced (each mark row is contiguous).
-//   pair mode (pair_stride != 0): mark m is compared with extracted vector m (batched 1:1).
+// The mark-independent denominator is computed once per extracted vector (similarity_den_kernel).
 // ------------------------------------------------------------------------------------------------
 constexpr int kSimMarks = 128;  // marks (threads) per CTA
 constexpr int kSimChunk = 32;   // elements staged per step
 
+// sum of squares of each extracted vector in the reference's sequential f32 order (the denominator of
+// every score of that vector; src/algorithm.rs:709 accumulates it inside the same loop)
+__global__ void __launch_bounds__(128)
+similarity_den_kernel(const float* __restrict__ extracted, unsigned n, long long ext_stride,
+                      unsigned n_ext, float* __restrict__ den) {
+    __shared__ float se[4][512];   // one warp per vector: coalesced staging, lane 0 walks it in order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned e = blockIdx.x * 4 + warp;
+    if (e >= n_ext) return;
+    const float* x = extracted + (long long)e * ext_stride;
+    float d = 0.f;
+    for (unsigned j0 = 0; j0 < n; j0 += 512) {
+        const unsigned len = min(512u, n - j0);
+        for (unsigned j = lane; j < len; j += 32) se[warp][j] = __ldg(x + j0 + j);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll 8
+            for (unsigned j = 0; j < len; ++j) { const float v = se[warp][j]; d = __fadd_rn(d, __fmul_rn(v, v)); }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) den[e] = d;
+}
+
 __global__ void __launch_bounds__(kSimMarks)
 similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned n,
-                       const float* __restrict__ extracted, long long ext_stride, int pair_mode,
+                       const float* __restrict__ extracted, long long ext_stride, const float* __restrict__ den,
                        float* __restrict__ out, long long out_stride) {
     __shared__ float tile[kSimMarks][kSimChunk + 1];
-    __shared__ float etile[kSimMarks][kSimChunk + 1];  // pair mode: extracted vector m next to mark m
     __shared__ float ex[kSimChunk];
     const size_t m0 = (size_t)blockIdx.x * kSimMarks;
-    const unsigned e = blockIdx.y;  // extracted vector (bank mode)
+    const unsigned e = blockIdx.y;  // extracted vector
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
-    float nom = 0.f, den = 0.f;
-    const float* ext = extracted + (pair_mode ? 0 : (long long)e * ext_stride);
+    constexpr int kRowsPerWarp = kSimMarks / (kSimMarks / 32);  // rows staged by each warp per chunk (32)
+    const float* ext = extracted + (long long)e * ext_stride;
     const int rows = (int)min((size_t)kSimMarks, n_marks - m0);
+    float nom = 0.f;
+    float pre[kRowsPerWarp];  // next chunk, prefetched while the current one is consumed
+    float pre_ex = 0.f;
+    auto fetch = [&](unsigned j0) {
+        const unsigned len = min((unsigned)kSimChunk, n - j0);
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) {
+            const int r = warp + i * (kSimMarks / 32);
+            pre[i] = (r < rows && (unsigned)lane < len) ? __ldg(bank + (m0 + r) * n + j0 + lane) : 0.f;
+        }
+        pre_ex = (t < (int)len) ? __ldg(ext + j0 + t) : 0.f;
+    };
+    fetch(0);
     for (unsigned j0 = 0; j0 < n; j0 += kSimChunk) {
         const unsigned len = min((unsigned)kSimChunk, n - j0);
-        // each warp stages rows warp, warp+4, ... : 32 consecutive floats of one mark per load
-        for (int r = warp; r < rows; r += kSimMarks / 32) {
-            const size_t m = m0 + r;
-            float v = 0.f, x = 0.f;
-            if ((unsigned)lane < len) {
-                v = __ldg(bank + m * n + j0 + lane);
-                if (pair_mode) x = __ldg(extracted + (long long)m * ext_stride + j0 + lane);
-            }
-            tile[r][lane] = v;
-            if (pair_mode) etile[r][lane] = x;
-        }
-        if (!pair_mode && t < (int)len) ex[t] = __ldg(ext + j0 + t);
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) tile[warp + i * (kSimMarks / 32)][lane] = pre[i];
+        if (t < kSimChunk) ex[t] = pre_ex;
         __syncthreads();
-        if (t < rows) {
-            if (pair_mode) {
-#pragma unroll 8
-                for (unsigned j = 0; j < len; ++j) {
-                    const float x = etile[t][j];
-                    nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
-                    den = __fadd_rn(den, __fmul_rn(x, x));
-                }
-            } else {
-#pragma unroll 8
-                for (unsigned j = 0; j < len; ++j) {
-                    const float x = ex[j];
-                    nom = __fadd_rn(nom, __fmul_rn(x, tile[t][j]));
-                    den = __fadd_rn(den, __fmul_rn(x, x));
-                }
-            }
+        if (j0 + kSimChunk < n) fetch(j0 + kSimChunk);
+        if (len == (unsigned)kSimChunk) {
+#pragma unroll
+            for (int j = 0; j < kSimChunk; ++j) nom = __fadd_rn(nom, __fmul_rn(ex[j], tile[t][j]));
+        } else {
+            for (unsigned j = 0; j < len; ++j) nom = __fadd_rn(nom, __fmul_rn(ex[j], tile[t][j]));
         }
         __syncthreads();
     }
     const size_t m = m0 + t;
-    if (m < n_marks) out[(long long)(pair_mode ? 0 : e) * out_stride + m] = __fdiv_rn(nom, __fsqrt_rn(den));
+    if (m < n_marks) out[(long long)e * out_stride + m] = __fdiv_rn(nom, __fsqrt_rn(__ldg(den + e)));
 }
 
 // 1:1 form: extracted vector i against mark i (the fused extract pipeline).  One warp per pair stages

@@ -1035,12 +1035,19 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
     }
     const size_t gx = (n_marks + kSimMarks - 1) / kSimMarks;
     if (gx > 0x7FFFFFFFull || n_ext > 65535 || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
+    float* d_den = nullptr;
+    CK(cudaMallocAsync(&d_den, n_ext * sizeof(float), c->stream));
     {
-        KScope ks(c, pair_mode ? "similarity_pairs" : "similarity_bank");
-        similarity_bank_kernel<<<dim3((unsigned)gx, pair_mode ? 1u : (unsigned)n_ext), kSimMarks, 0, c->stream>>>(
-            d_bank, n_marks, (unsigned)n, d_ext, (long long)n, pair_mode ? 1 : 0, d_out, (long long)n_marks);
+        KScope ks(c, "similarity_den");
+        similarity_den_kernel<<<(unsigned)((n_ext + 3) / 4), 128, 0, c->stream>>>(d_ext, (unsigned)n, (long long)n, (unsigned)n_ext, d_den);
+    }
+    {
+        KScope ks(c, "similarity_bank");
+        similarity_bank_kernel<<<dim3((unsigned)gx, (unsigned)n_ext), kSimMarks, 0, c->stream>>>(
+            d_bank, n_marks, (unsigned)n, d_ext, (long long)n, d_den, d_out, (long long)n_marks);
     }
     CK(cudaGetLastError());
+    CK(cudaFreeAsync(d_den, c->stream));
     return SSW_OK;
 }
 

@@ -388,3 +388,26 @@ def test_topk_block_bound_is_repaired_on_flat_spectra(wm, ctx, so):
     wm._lib.check(wm.lib.ssw_embed_batch_rgb8(ctx.handle, noise.ctypes.data, 1920, 1080, 1, ctypes.byref(cfg),
                                               mark.ctypes.data, 1000, out.ctypes.data))
     assert (out == api).all()
+
+
+def test_bank_100k_marks_at_full_size(wm, ctx, so):
+    """BASELINE config 5 at full size: 100 000 stored marks x 1000 (400 MB on the device).  Sampled scores
+    are bit-identical to the sequential f32 loop (src/algorithm.rs:696-714); linearity of the numerator
+    in the extracted vector is the size-independent check over all scores."""
+    bank = wm.Bank.normal(5, 100000, 1000, ctx=ctx)
+    rng = np.random.default_rng(8)
+    e = rng.standard_normal((2, 1000)).astype(np.float32)
+    e[1] = bank.row(4242) * 0.9 + 0.3 * e[1]          # a noisy copy of one stored mark
+    s = bank.similarity(e)
+    assert s.shape == (2, 100000)
+    for j in (0, 1, 127, 128, 4242, 50000, 99871, 99999):
+        row = bank.row(j)
+        for i in range(2):
+            assert float(s[i, j]) == float(so.similarity(e[i], row)), (i, j)
+    assert int(s[1].argmax()) == 4242 and s[1, 4242] > 25 and np.sort(s[1])[-2] < 6
+    assert np.abs(s[0]).max() < 6                      # unrelated vector: nothing exceeds 6 sigma
+    both = bank.similarity((e[0] + e[1]).astype(np.float32))[0]
+    den = lambda v: np.sqrt(np.sum(v.astype(np.float64) ** 2))
+    lin = (s[0].astype(np.float64) * den(e[0]) + s[1].astype(np.float64) * den(e[1])) / den((e[0] + e[1]).astype(np.float32))
+    assert np.abs(both - lin).max() < 2e-3
+    bank.close()
