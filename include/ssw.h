@@ -187,6 +187,44 @@ int ssw_stage_topk_dev(ssw_ctx* ctx, const float* plane_dev, uint32_t width, uin
 int ssw_stage_inverse_rgb8_dev(ssw_ctx* ctx, float* plane_dev, const uint8_t* rgb_src_dev,
                                uint32_t width, uint32_t height, uint32_t batch, uint8_t* out_rgb_dev);
 
+/* ---- sharded single frames (BASELINE config 4; nothing in the reference corresponds -- it holds a whole
+ *      frame on one core).  Rank g owns rows [g*H/G, (g+1)*H/G) of the pixels and, after the row pass and an
+ *      all-to-all transpose, columns [col0, col0+ncols) of the coefficients, stored TRANSPOSED as a local
+ *      plane [ncols][height] so that the column pass is again a pass over contiguous lines.  These entry
+ *      points are the per-rank steps; the exchanges between them (all-to-all, max, all-gather, sum) are
+ *      issued by the host layer over NCCL.  Index lists always hold the reference's flat indices
+ *      p = r*width + c (src/algorithm.rs:204), so results are comparable with the unsharded path. */
+typedef struct ssw_shard {
+    uint32_t width, height; /* whole frame                    */
+    uint32_t col0, ncols;   /* coefficient columns of this rank */
+} ssw_shard;
+#define SSW_TOPK_CAP 8192   /* entries of one candidate list */
+
+/* 1-D DCT-II (x2, reference scaling) of n_lines contiguous lines of length n; src_type 0 RGB8 (luma is
+ * computed, src/yiq.rs:157), 1 RGB32F, 2 f32 lines.  The row pass of dct2_2d (src/dct2d.rs:129-170). */
+int ssw_lines_forward_dev(ssw_ctx* ctx, int src_type, const void* src_dev, uint32_t n, uint32_t n_lines, float* plane_dev);
+/* 1-D DCT-III (x0.5) of the lines, then x scale; dst_type 2: f32 lines, 0 / 1: RGB8 / RGB32F with the chroma
+ * of the original pixels `src_dev` (src/yiq.rs:187-197). */
+int ssw_lines_inverse_dev(ssw_ctx* ctx, float* plane_dev, uint32_t n, uint32_t n_lines, float scale, int dst_type,
+                          void* dst_dev, int src_type, const void* src_dev);
+/* dst[b][c][r] = src[b][r][c]: batched f32 transpose (packs / unpacks the all-to-all blocks) */
+int ssw_transpose_dev(ssw_ctx* ctx, const float* src_dev, uint32_t rows, uint32_t cols, int64_t src_ld, int64_t src_bstride,
+                      float* dst_dev, int64_t dst_ld, int64_t dst_bstride, uint32_t batch);
+/* distributed ordered top-k (obtain_indices_by_function, src/algorithm.rs:200-221): local bound -> [max over
+ * ranks] -> local candidates -> [all-gather] -> merge */
+int ssw_shard_topk_bin_dev(ssw_ctx* ctx, const float* plane_dev, const ssw_shard* sh, int ordering, size_t k, uint32_t* bin_dev);
+int ssw_shard_topk_collect_dev(ssw_ctx* ctx, const float* plane_dev, const ssw_shard* sh, int ordering,
+                               const uint32_t* bin_dev, uint64_t* cand_dev, uint32_t* count_dev);
+int ssw_shard_topk_merge_dev(ssw_ctx* ctx, const uint64_t* lists_dev, const uint32_t* counts_dev, uint32_t n_lists,
+                             size_t k, uint32_t* idx_dev, uint32_t* overflow_dev);
+/* embed_watermark / extract_watermark on the coefficients this rank owns (src/algorithm.rs:382-410,543-562);
+ * extract writes 0 for coefficients owned by other ranks (the per-rank vectors are summed) */
+int ssw_shard_embed_dev(ssw_ctx* ctx, float* plane_dev, const ssw_shard* sh, const uint32_t* idx_dev, size_t k,
+                        const float* marks_dev, size_t mark_stride, size_t n_marks, const uint32_t* lens_dev,
+                        const ssw_config* cfg);
+int ssw_shard_extract_dev(ssw_ctx* ctx, const float* base_plane_dev, const float* derived_plane_dev, const ssw_shard* sh,
+                          const uint32_t* idx_dev, size_t n, const ssw_config* cfg, float* out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,10 @@ class SswError(RuntimeError):
         self.status = status
 
 
+class ssw_shard(ctypes.Structure):
+    _fields_ = [('width', c_uint32), ('height', c_uint32), ('col0', c_uint32), ('ncols', c_uint32)]
+
+
 class ssw_config(ctypes.Structure):
     _fields_ = [('method', c_int32), ('alpha', c_float), ('ordering', c_int32)]
 
@@ -100,6 +104,15 @@ SIGNATURES = {
     'ssw_stage_forward_rgb8_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, _p]),
     'ssw_stage_topk_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, c_int, c_size_t, _p]),
     'ssw_stage_inverse_rgb8_dev': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _p]),
+    'ssw_lines_forward_dev': (c_int, [_p, c_int, _p, c_uint32, c_uint32, _p]),
+    'ssw_lines_inverse_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_float, c_int, _p, c_int, _p]),
+    'ssw_transpose_dev': (c_int, [_p, _p, c_uint32, c_uint32, ctypes.c_int64, ctypes.c_int64, _p, ctypes.c_int64,
+                                  ctypes.c_int64, c_uint32]),
+    'ssw_shard_topk_bin_dev': (c_int, [_p, _p, POINTER(ssw_shard), c_int, c_size_t, _p]),
+    'ssw_shard_topk_collect_dev': (c_int, [_p, _p, POINTER(ssw_shard), c_int, _p, _p, _p]),
+    'ssw_shard_topk_merge_dev': (c_int, [_p, _p, _p, c_uint32, c_size_t, _p, _p]),
+    'ssw_shard_embed_dev': (c_int, [_p, _p, POINTER(ssw_shard), _p, c_size_t, _p, c_size_t, c_size_t, _p, _cfg]),
+    'ssw_shard_extract_dev': (c_int, [_p, _p, _p, POINTER(ssw_shard), _p, c_size_t, _cfg, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

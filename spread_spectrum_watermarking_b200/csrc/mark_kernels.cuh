@@ -64,6 +64,84 @@ __global__ void extract_gather_kernel(const float* __restrict__ base, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sharded frames: each rank keeps the coefficients of its columns [col0, col0+ncols)
+// transposed, local plane [ncols][height].  The ordered index list holds the reference's flat indices
+// p = r*width + c; only the owner of column c touches coefficient p.
+// ------------------------------------------------------------------------------------------------
+struct ShardLayout {
+    unsigned width, height;   // whole frame
+    unsigned col0, ncols;     // columns owned by this rank
+};
+
+__device__ __forceinline__ bool shard_local(const ShardLayout& L, unsigned p, unsigned long long* q) {
+    const unsigned r = p / L.width, c = p - r * L.width;
+    if (c < L.col0 || c >= L.col0 + L.ncols) return false;
+    *q = (unsigned long long)(c - L.col0) * L.height + r;
+    return true;
+}
+
+__global__ void embed_scatter_shard_kernel(float* __restrict__ plane, ShardLayout L, const unsigned* __restrict__ idx,
+                                           unsigned k, const float* __restrict__ marks, long long mark_stride,
+                                           int n_marks, const unsigned* __restrict__ lens, int method, float alpha) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    unsigned long long q;
+    if (!shard_local(L, idx[i], &q)) return;
+    const float orig = plane[q];
+    if (n_marks == 1) {
+        if (!lens || i < lens[0]) plane[q] = insert_fn(method, alpha, orig, marks[i]);
+        return;
+    }
+    float c = orig;
+    for (int m = 0; m < n_marks; ++m) {
+        if (lens && i >= lens[m]) continue;
+        const float updated = insert_fn(method, alpha, orig, marks[(long long)m * mark_stride + i]);
+        c = __fadd_rn(c, __fsub_rn(updated, orig));
+    }
+    plane[q] = c;
+}
+
+// out[i] = extracted value if this rank owns coefficient idx[i], else 0 (the ranks' vectors are summed)
+__global__ void extract_gather_shard_kernel(const float* __restrict__ base, const float* __restrict__ derived,
+                                            ShardLayout L, const unsigned* __restrict__ idx, unsigned n, int method,
+                                            float alpha, float* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long q;
+    float r = 0.f;
+    if (shard_local(L, idx[i], &q)) {
+        const float b = base[q], d = derived[q];
+        if (method == 1) r = __fdiv_rn(__fsub_rn(d, b), alpha);
+        else if (method == 2) r = __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
+        else r = __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
+    }
+    out[i] = r;
+}
+
+// batched 2-D transpose of f32 tiles through shared memory (both sides coalesced):
+// dst[b][c][r] = src[b][r][c], r < rows, c < cols, leading dimensions src_ld / dst_ld
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, unsigned rows, unsigned cols, long long src_ld, long long src_bstride,
+                 float* __restrict__ dst, long long dst_ld, long long dst_bstride) {
+    __shared__ float tile[32][33];
+    const float* s = src + (long long)blockIdx.z * src_bstride;
+    float* d = dst + (long long)blockIdx.z * dst_bstride;
+    const unsigned c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const unsigned r = r0 + ty + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + i][tx] = s[(long long)r * src_ld + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        const unsigned c = c0 + ty + i, r = r0 + tx;
+        if (r < rows && c < cols) d[(long long)c * dst_ld + r] = tile[tx][ty + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tester::similarity -- src/algorithm.rs:696-714, against a bank of marks [n_marks][n].
 // One thread per stored mark walks the vectors in the reference's sequential order with separate
 // f32 multiply and add, so every score is bit-identical to the reference loop.  The bank tile is

@@ -30,9 +30,19 @@ constexpr int kTopkCap = 8192;  // candidates per image held by the single-CTA s
 
 struct OrderConsts {
     int mode;  // SSW_ORDER_*
-    int w;
+    int w;     // width of the whole frame
     float s_k0_w, s_k0_h, s_w, s_h;  // src/algorithm.rs:245-250
+    // sharded frames keep their coefficients transposed: local plane [columns col0..][t_ld = frame height];
+    // t_ld == 0: ordinary row-major plane, local position == the reference's flat index r*w + c
+    unsigned t_ld, t_col0;
 };
+
+// local linear position -> the reference's flat index r*w + c (src/algorithm.rs:204)
+__device__ __forceinline__ unsigned flat_index(unsigned q, const OrderConsts& oc) {
+    if (oc.t_ld == 0u) return q;
+    const unsigned c_local = q / oc.t_ld, r = q - c_local * oc.t_ld;
+    return r * (unsigned)oc.w + oc.t_col0 + c_local;
+}
 
 struct TopkScratch {
     unsigned* hist;        // [batch][kHistBins], zero between calls
@@ -112,16 +122,22 @@ topk_hist_kernel(const float* __restrict__ planes, long long plane_stride, unsig
         for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
             const float4 v = __ldg(p4 + i);
             const unsigned p = i << 2;
-            if (p) atomicAdd(&sh[order_key(v.x, p, oc) >> (32 - kHistBits)], 1u);
-            atomicAdd(&sh[order_key(v.y, p + 1, oc) >> (32 - kHistBits)], 1u);
-            atomicAdd(&sh[order_key(v.z, p + 2, oc) >> (32 - kHistBits)], 1u);
-            atomicAdd(&sh[order_key(v.w, p + 3, oc) >> (32 - kHistBits)], 1u);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned g = flat_index(p + u, oc);
+                if (g) atomicAdd(&sh[order_key(e[u], g, oc) >> (32 - kHistBits)], 1u);
+            }
         }
-        for (unsigned p = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-            if (p) atomicAdd(&sh[order_key(plane[p], p, oc) >> (32 - kHistBits)], 1u);
+        for (unsigned p = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+            const unsigned g = flat_index(p, oc);
+            if (g) atomicAdd(&sh[order_key(plane[p], g, oc) >> (32 - kHistBits)], 1u);
+        }
     } else {
-        for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-            if (p) atomicAdd(&sh[order_key(plane[p], p, oc) >> (32 - kHistBits)], 1u);
+        for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+            const unsigned g = flat_index(p, oc);
+            if (g) atomicAdd(&sh[order_key(plane[p], g, oc) >> (32 - kHistBits)], 1u);
+        }
     }
     __syncthreads();
     unsigned* gh = ts.hist + (size_t)img * kHistBins;
@@ -172,8 +188,9 @@ topk_block_bin_kernel(const float* __restrict__ planes, long long plane_stride, 
         for (int u = 0; u < 8; ++u) {   // 8 independent loads in flight per thread
             const unsigned e = e0 + u * blockDim.x;
             const unsigned r = e / bc, c = e - r * bc;
-            p[u] = e < total ? r * w + c : 0u;
-            v[u] = p[u] ? __ldg(plane + p[u]) : 0.f;
+            const unsigned q = r * w + c;            // local position (w = local line length)
+            p[u] = e < total ? flat_index(q, oc) : 0u;
+            v[u] = p[u] ? __ldg(plane + q) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -208,16 +225,41 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
         for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
             const float4 v = __ldg(p4 + i);
             const unsigned p = i << 2;
-            if (p) topk_push(order_key(v.x, p, oc), p, bin_sel, count, cand);
-            topk_push(order_key(v.y, p + 1, oc), p + 1, bin_sel, count, cand);
-            topk_push(order_key(v.z, p + 2, oc), p + 2, bin_sel, count, cand);
-            topk_push(order_key(v.w, p + 3, oc), p + 3, bin_sel, count, cand);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned g = flat_index(p + u, oc);
+                if (g) topk_push(order_key(e[u], g, oc), g, bin_sel, count, cand);
+            }
         }
-        for (unsigned p = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-            if (p) topk_push(order_key(plane[p], p, oc), p, bin_sel, count, cand);
+        for (unsigned p = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+            const unsigned g = flat_index(p, oc);
+            if (g) topk_push(order_key(plane[p], g, oc), g, bin_sel, count, cand);
+        }
     } else {
-        for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-            if (p) topk_push(order_key(plane[p], p, oc), p, bin_sel, count, cand);
+        for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+            const unsigned g = flat_index(p, oc);
+            if (g) topk_push(order_key(plane[p], g, oc), g, bin_sel, count, cand);
+        }
+    }
+}
+
+// ---- 2'. distributed merge: concatenate the candidate lists gathered from all ranks --------------
+__global__ void __launch_bounds__(256)
+topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned* __restrict__ counts, unsigned n_lists,
+                   unsigned list_cap, TopkScratch ts) {
+    __shared__ unsigned off[65];
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (unsigned l = 0; l < n_lists; ++l) { off[l] = run; run += min(counts[l], list_cap); }
+        off[n_lists] = run;
+        ts.cand_count[0] = run;  // > kTopkCap is reported as overflow by topk_sort
+    }
+    __syncthreads();
+    for (unsigned l = 0; l < n_lists; ++l) {
+        const unsigned c = min(counts[l], list_cap);
+        for (unsigned i = threadIdx.x; i < c; i += blockDim.x)
+            if (off[l] + i < (unsigned)kTopkCap) ts.cand[off[l] + i] = lists[(size_t)l * list_cap + i];
     }
 }
 

@@ -444,6 +444,28 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
 }
 
 // forward: pixels/plane -> coefficient plane (rows then columns)
+// row pass of the forward transform: pixels / plane rows -> DCT-II along x (x scale0/scalen) -> plane
+static int run_rows_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
+                            float rs0, float rsn) {
+    const long long npix = (long long)w * h;
+    bool done = false;
+    CKS(fast_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
+    if (done) return SSW_OK;
+    const DevPlan* pw;
+    CKS(get_plan(c, w, &pw));
+    Tiling tr;
+    CKS(pick_tiling(c, pw->dev, false, h, &tr));
+    LineArgs ar = base_args(pw->dev, w, h, tr, npix);
+    ar.src = d_src; ar.plane = d_plane; ar.scale0 = rs0; ar.scalen = rsn;
+    ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
+    const long long ntr = (long long)ar.tiles_per_image * batch;
+    switch (src_type) {
+        case PIX_RGB8: return launch_line(c, "row_fwd_rgb8", row_fwd_kernel<PIX_RGB8>, ar, tr, ntr);
+        case PIX_RGB32F: return launch_line(c, "row_fwd_rgb32f", row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr);
+        default: return launch_line(c, "row_fwd_plane", row_fwd_kernel<PIX_PLANE>, ar, tr, ntr);
+    }
+}
+
 static int run_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
                        int dct_type) {
     float rs0 = 1.f, rsn = 1.f, cs0 = 1.f, csn = 1.f;
@@ -452,23 +474,8 @@ static int run_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h
         cs0 = std::sqrt(1.0f / (4.0f * (float)h)); csn = std::sqrt(1.0f / (2.0f * (float)h));
     }
     const long long npix = (long long)w * h;
+    CKS(run_rows_forward(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn));
     bool done = false;
-    CKS(fast_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
-    if (!done) {
-        const DevPlan* pw;
-        CKS(get_plan(c, w, &pw));
-        Tiling tr;
-        CKS(pick_tiling(c, pw->dev, false, h, &tr));
-        LineArgs ar = base_args(pw->dev, w, h, tr, npix);
-        ar.src = d_src; ar.plane = d_plane; ar.scale0 = rs0; ar.scalen = rsn;
-        ar.tiles_per_image = (h + 2 * tr.P - 1) / (2 * tr.P);
-        const long long ntr = (long long)ar.tiles_per_image * batch;
-        switch (src_type) {
-            case PIX_RGB8: CKS(launch_line(c, "row_fwd_rgb8", row_fwd_kernel<PIX_RGB8>, ar, tr, ntr)); break;
-            case PIX_RGB32F: CKS(launch_line(c, "row_fwd_rgb32f", row_fwd_kernel<PIX_RGB32F>, ar, tr, ntr)); break;
-            default: CKS(launch_line(c, "row_fwd_plane", row_fwd_kernel<PIX_PLANE>, ar, tr, ntr)); break;
-        }
-    }
     CKS(fast_col(c, false, w, h, batch, d_plane, cs0, csn, &done));
     if (!done) {
         const DevPlan* ph;
@@ -484,22 +491,11 @@ static int run_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h
 }
 
 // inverse: coefficient plane (destroyed) -> pixels/plane (columns then rows)
-static int run_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
-                       int dst_type, void* d_dst) {
+// row pass of the inverse transform: plane rows -> DCT-III along x -> x out_scale -> plane | pixels
+static int run_rows_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
+                            int dst_type, void* d_dst, float out_scale) {
     const long long npix = (long long)w * h;
-    const float out_scale = 4.0f / (float)((size_t)w * (size_t)h);  // src/dct2d.rs:213-217
     bool done = false;
-    CKS(fast_col(c, true, w, h, batch, d_plane, 1.f, 1.f, &done));
-    if (!done) {
-        const DevPlan* ph;
-        CKS(get_plan(c, h, &ph));
-        Tiling tc;
-        CKS(pick_tiling(c, ph->dev, true, w, &tc));
-        LineArgs ac = base_args(ph->dev, w, h, tc, npix);
-        ac.plane = d_plane;
-        ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
-        CKS(launch_line(c, "col_inv", col_inv_kernel, ac, tc, (long long)ac.tiles_per_image * batch));
-    }
     CKS(fast_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
     if (done) return SSW_OK;
     const DevPlan* pw;
@@ -517,6 +513,25 @@ static int run_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_s
     if (dst_type == PIX_RGB32F && src_type == PIX_RGB8) return launch_line(c, "row_inv_rgb32f_src8", row_inv_kernel<PIX_RGB32F, PIX_RGB8>, ar, tr, ntr);
     if (dst_type == PIX_RGB32F && src_type == PIX_RGB32F) return launch_line(c, "row_inv_rgb32f", row_inv_kernel<PIX_RGB32F, PIX_RGB32F>, ar, tr, ntr);
     return fail(SSW_ERR_INVALID, "bad pixel type combination");
+}
+
+static int run_inverse(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
+                       int dst_type, void* d_dst) {
+    const long long npix = (long long)w * h;
+    const float out_scale = 4.0f / (float)((size_t)w * (size_t)h);  // src/dct2d.rs:213-217
+    bool done = false;
+    CKS(fast_col(c, true, w, h, batch, d_plane, 1.f, 1.f, &done));
+    if (!done) {
+        const DevPlan* ph;
+        CKS(get_plan(c, h, &ph));
+        Tiling tc;
+        CKS(pick_tiling(c, ph->dev, true, w, &tc));
+        LineArgs ac = base_args(ph->dev, w, h, tc, npix);
+        ac.plane = d_plane;
+        ac.tiles_per_image = (w + 2 * tc.P - 1) / (2 * tc.P);
+        CKS(launch_line(c, "col_inv", col_inv_kernel, ac, tc, (long long)ac.tiles_per_image * batch));
+    }
+    return run_rows_inverse(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +559,7 @@ static int ensure_topk_scratch(ssw_ctx* c, unsigned batch) {
 static OrderConsts make_order(int ordering, int w, int h) {
     OrderConsts oc;
     oc.mode = ordering; oc.w = w;
+    oc.t_ld = 0u; oc.t_col0 = 0u;
     oc.s_k0_w = std::sqrt(1.0f / (4.0f * (float)w));
     oc.s_k0_h = std::sqrt(1.0f / (4.0f * (float)h));
     oc.s_w = std::sqrt(1.0f / (2.0f * (float)w));
@@ -1376,4 +1392,166 @@ extern "C" int ssw_stage_inverse_rgb8_dev(ssw_ctx* c, float* plane, const uint8_
     CKS(check_dims(w, h));
     CKS(ctx_bind(c));
     return run_inverse(c, plane, PIX_RGB8, rgb_src, w, h, batch, PIX_RGB8, out_rgb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded frames: per-rank building blocks.  The exchange steps between them (the
+// all-to-all transposes, the max / all-gather of the distributed top-k, the sum of the extracted
+// vector) are issued by the host layer (spread_spectrum_watermarking_b200/sharded.py) through
+// torch.distributed -- NCCL over NVLink on the GPUs.
+// ------------------------------------------------------------------------------------------------
+extern "C" int ssw_lines_forward_dev(ssw_ctx* c, int src_type, const void* src, uint32_t n, uint32_t n_lines, float* plane) {
+    if (!c || !src || !plane) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (src_type < PIX_RGB8 || src_type > PIX_PLANE) return fail(SSW_ERR_INVALID, "bad pixel type");
+    CKS(check_dims(n, n_lines));
+    CKS(ctx_bind(c));
+    return run_rows_forward(c, src_type, src, (int)n, (int)n_lines, 1, plane, 1.f, 1.f);
+}
+
+extern "C" int ssw_lines_inverse_dev(ssw_ctx* c, float* plane, uint32_t n, uint32_t n_lines, float scale, int dst_type,
+                                     void* dst, int src_type, const void* src) {
+    if (!c || !plane || !dst) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (dst_type != PIX_PLANE && !src) return fail(SSW_ERR_INVALID, "pixel output needs the original pixels");
+    CKS(check_dims(n, n_lines));
+    CKS(ctx_bind(c));
+    return run_rows_inverse(c, plane, dst_type == PIX_PLANE ? PIX_PLANE : src_type, src, (int)n, (int)n_lines, 1, dst_type, dst, scale);
+}
+
+extern "C" int ssw_transpose_dev(ssw_ctx* c, const float* src, uint32_t rows, uint32_t cols, int64_t src_ld, int64_t src_bstride,
+                                 float* dst, int64_t dst_ld, int64_t dst_bstride, uint32_t batch) {
+    if (!c || !src || !dst) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (rows == 0 || cols == 0 || batch == 0) return SSW_OK;
+    if (batch > 65535 || (rows + 31) / 32 > 65535) return fail(SSW_ERR_INVALID, "transpose grid out of range");
+    CKS(ctx_bind(c));
+    {
+        KScope ks(c, "transpose");
+        transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32, batch), 256, 0, c->stream>>>(
+            src, rows, cols, src_ld, src_bstride, dst, dst_ld, dst_bstride);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+static int shard_order(const ssw_shard* sh, int ordering, OrderConsts* oc) {
+    if (!sh || sh->ncols == 0 || sh->col0 + sh->ncols > sh->width || sh->height == 0)
+        return fail(SSW_ERR_INVALID, "bad shard layout");
+    if ((uint64_t)sh->width * sh->height >= 0xFFFFFFFFull) return fail(SSW_ERR_UNSUPPORTED, "more than 2^32-1 pixels per frame");
+    if (ordering < 0 || ordering > 2) return fail(SSW_ERR_UNSUPPORTED, "only Energy/EnergyOrthogonal/Legacy orderings run on the device");
+    *oc = make_order(ordering, (int)sh->width, (int)sh->height);
+    oc->t_ld = sh->height;
+    oc->t_col0 = sh->col0;
+    return SSW_OK;
+}
+
+// lower bound (histogram bin) of the frame's k-th largest key from this rank's low-frequency block
+extern "C" int ssw_shard_topk_bin_dev(ssw_ctx* c, const float* plane, const ssw_shard* sh, int ordering, size_t k, uint32_t* bin_dev) {
+    if (!c || !plane || !bin_dev) return fail(SSW_ERR_INVALID, "NULL argument");
+    OrderConsts oc;
+    CKS(shard_order(sh, ordering, &oc));
+    if (k == 0 || k > (size_t)kTopkCap / 2) return fail(SSW_ERR_UNSUPPORTED, "sharded top-k supports mark lengths up to 4096");
+    CKS(ctx_bind(c));
+    CKS(ensure_topk_scratch(c, 1));
+    TopkScratch ts = c->ts;
+    ts.sel_bin = bin_dev;
+    {
+        KScope ks(c, "topk_block_bin");
+        // local plane [ncols][height]: "width" of the block kernel is the local line length
+        topk_block_bin_kernel<<<1, 1024, 0, c->stream>>>(plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+// every local coefficient whose key bin is >= *bin_dev -> cand_dev[0 .. *count_dev) as (key << 32 | ~flat index);
+// cand_dev holds SSW_TOPK_CAP entries, *count_dev may exceed it (overflow, reported by the merge)
+extern "C" int ssw_shard_topk_collect_dev(ssw_ctx* c, const float* plane, const ssw_shard* sh, int ordering,
+                                          const uint32_t* bin_dev, uint64_t* cand_dev, uint32_t* count_dev) {
+    if (!c || !plane || !bin_dev || !cand_dev || !count_dev) return fail(SSW_ERR_INVALID, "NULL argument");
+    OrderConsts oc;
+    CKS(shard_order(sh, ordering, &oc));
+    CKS(ctx_bind(c));
+    const size_t n = (size_t)sh->ncols * sh->height;
+    if (n >= 0xFFFFFFFFull) return fail(SSW_ERR_UNSUPPORTED, "shard too large");
+    TopkScratch ts{};
+    ts.sel_bin = const_cast<uint32_t*>(bin_dev);
+    ts.cand_count = count_dev;
+    ts.cand = (unsigned long long*)cand_dev;
+    CK(cudaMemsetAsync(count_dev, 0, sizeof(uint32_t), c->stream));
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((n / 4 + 511) / 512, (size_t)c->sm_count * 4));
+    {
+        KScope ks(c, "topk_collect");
+        topk_collect_kernel<<<dim3(blocks, 1), 512, 0, c->stream>>>(plane, 0, (unsigned)n, oc, ts);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+// merge the candidate lists gathered from all ranks ([n_lists][SSW_TOPK_CAP] + counts) into the first k
+// ordered flat indices; *overflow_dev != 0 afterwards means the lists did not fit (caller repairs)
+extern "C" int ssw_shard_topk_merge_dev(ssw_ctx* c, const uint64_t* lists_dev, const uint32_t* counts_dev, uint32_t n_lists,
+                                        size_t k, uint32_t* idx_dev, uint32_t* overflow_dev) {
+    if (!c || !lists_dev || !counts_dev || !idx_dev || !overflow_dev) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (n_lists == 0 || n_lists > 64) return fail(SSW_ERR_INVALID, "1..64 candidate lists");
+    if (k == 0 || k > (size_t)kTopkCap / 2) return fail(SSW_ERR_UNSUPPORTED, "sharded top-k supports mark lengths up to 4096");
+    CKS(ctx_bind(c));
+    CKS(ensure_topk_scratch(c, 1));
+    TopkScratch ts = c->ts;
+    ts.overflow = overflow_dev;
+    CK(cudaMemsetAsync(overflow_dev, 0, sizeof(uint32_t), c->stream));
+    {
+        KScope ks(c, "topk_concat");
+        topk_concat_kernel<<<1, 256, 0, c->stream>>>((const unsigned long long*)lists_dev, counts_dev, n_lists, (unsigned)kTopkCap, ts);
+    }
+    const void* key = (const void*)topk_sort_kernel;
+    const int smem = kTopkCap * (int)sizeof(unsigned long long);
+    if (c->smem_attr.find(key) == c->smem_attr.end()) {
+        CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->smem_attr[key] = smem;
+    }
+    { KScope ks(c, "topk_sort"); topk_sort_kernel<<<1, kSortThreads, smem, c->stream>>>(ts, (unsigned)k, idx_dev, 0); }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+static ShardLayout shard_layout(const ssw_shard* sh) {
+    ShardLayout L;
+    L.width = sh->width; L.height = sh->height; L.col0 = sh->col0; L.ncols = sh->ncols;
+    return L;
+}
+
+extern "C" int ssw_shard_embed_dev(ssw_ctx* c, float* plane, const ssw_shard* sh, const uint32_t* idx_dev, size_t k,
+                                   const float* marks_dev, size_t mark_stride, size_t n_marks, const uint32_t* lens_dev,
+                                   const ssw_config* cfg) {
+    if (!c || !plane || !idx_dev || !marks_dev) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    OrderConsts oc;
+    CKS(shard_order(sh, cfg->ordering, &oc));
+    if (k == 0 || n_marks == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    {
+        KScope ks(c, "embed_scatter");
+        embed_scatter_shard_kernel<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(
+            plane, shard_layout(sh), idx_dev, (unsigned)k, marks_dev, (long long)mark_stride, (int)n_marks, lens_dev,
+            cfg->method, cfg->alpha);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+extern "C" int ssw_shard_extract_dev(ssw_ctx* c, const float* base_plane, const float* derived_plane, const ssw_shard* sh,
+                                     const uint32_t* idx_dev, size_t n, const ssw_config* cfg, float* out_dev) {
+    if (!c || !base_plane || !derived_plane || !idx_dev || !out_dev) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    OrderConsts oc;
+    CKS(shard_order(sh, cfg->ordering, &oc));
+    if (n >= (size_t)sh->width * sh->height) return fail(SSW_ERR_INVALID, "Desired extraction length exceeds available coefficients.");
+    if (n == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    {
+        KScope ks(c, "extract_gather");
+        extract_gather_shard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+            base_plane, derived_plane, shard_layout(sh), idx_dev, (unsigned)n, cfg->method, cfg->alpha, out_dev);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
 }

@@ -1,0 +1,49 @@
+"""The CUDA steps of the sharded-frame path (libssw ssw_lines_* / ssw_transpose_dev / ssw_shard_*) driven by
+the same orchestration as the multi-rank runs, on ONE GPU (world size 1: the all-to-all degenerates to the
+local transpose), against the ordinary Writer/Reader path and the oracle.  The multi-rank exchange logic is
+covered on CPU by tests/test_sharded_gloo.py and on 2+ GPUs by tests/dist/run_sharded_nccl.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('w,h,k', [(1920, 1080, 1000), (512, 384, 300), (640, 444, 500), (2048, 1024, 1000)])
+def test_sharded_path_world1_matches_unsharded(wm, ctx, so, w, h, k):
+    import torch
+    from spread_spectrum_watermarking_b200 import sharded
+    frame = so.synth_frame(w, h, seed=31)
+    mark = np.random.default_rng(w).standard_normal(k).astype(np.float32)
+    ops = sharded.CudaOps(ctx)
+    cfg = wm._lib.ssw_config(2, 0.1, 0)
+    rows = torch.from_numpy(frame).cuda()
+    torch.cuda.synchronize()
+    wr = sharded.ShardedWriter(rows, w, h, cfg, ops, rank=0, world=1)
+    ctx.synchronize()
+    coeff_t = wr.frame.coeff.cpu().numpy()                      # [w][h] transposed
+    plain = wm.Writer.new(frame, ctx=ctx)
+    c = plain.coefficient_image()
+    assert np.abs(coeff_t.T - c).max() <= 4e-7 * np.abs(c).max()
+    wr.embed([mark])
+    idx = wr.indices.cpu().numpy().astype(np.int64)
+    assert (idx == so.obtain_indices(coeff_t.T.copy().ravel(), k=k)).all(), 'exact ordering of its own coefficients'
+    out = wr.result_rgb8().cpu().numpy()
+    ref = plain.mark_rgb8([mark])
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.02
+    rd = sharded.ShardedReader(rows, w, h, cfg, ops, rank=0, world=1)
+    ext = rd.extract(torch.from_numpy(out).cuda(), k).cpu().numpy()
+    ref_ext = wm.Reader.base(frame, ctx=ctx).extract(wm.Reader.derived(out, ctx=ctx), k)
+    assert np.abs(ext - ref_ext).max() < 5e-3
+    assert float(wm.Tester.new(ext, ctx=ctx).similarity(mark).similarity) > 6
+
+
+def test_transpose_blocks(wm, ctx):
+    import torch
+    from spread_spectrum_watermarking_b200 import sharded
+    ops = sharded.CudaOps(ctx)
+    a = torch.arange(70 * 96, dtype=torch.float32, device='cuda').reshape(70, 96)
+    t = ops.transpose_blocks(a, 70, 24, 96, 4)
+    ctx.synchronize()
+    for j in range(4):
+        assert torch.equal(t[j], a[:, j * 24:(j + 1) * 24].T)
