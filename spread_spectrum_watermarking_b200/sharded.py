@@ -53,6 +53,12 @@ class ShardPlan:
         return (c % self.wb) * self.height + r
 
 
+def _scope(ops):
+    """stream scope of the ops object (CudaOps: its torch stream; CPU stand-ins: nothing)"""
+    import contextlib
+    return ops.scope() if hasattr(ops, 'scope') else contextlib.nullcontext()
+
+
 def _all_to_all(send, group):
     """send[j] goes to rank j; returns recv with recv[g] = block sent by rank g"""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -77,11 +83,25 @@ def _all_reduce(t, op, group):
 
 
 class CudaOps:
-    """the per-rank arithmetic steps: libssw kernels on torch CUDA tensors (no CPU path)"""
+    """the per-rank arithmetic steps: libssw kernels on torch CUDA tensors (no CPU path).
 
-    def __init__(self, ctx):
-        self.ctx = ctx
-        self.device = torch.device('cuda', ctx.device)
+    libssw launches on ITS context's stream, torch (copies, NCCL collectives) on torch's current stream:
+    both must be the same stream.  `CudaOps(device)` therefore owns a torch stream, builds the libssw
+    context on it, and every step of the orchestration runs inside `scope()` (= torch.cuda.stream(...))."""
+
+    def __init__(self, device=0, ctx=None, stream=None):
+        from . import Context
+        self.device = torch.device('cuda', int(device))
+        self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
+        if ctx is not None and int(ctx.stream or 0) != int(self.stream.cuda_stream):
+            raise SswError(_lib.SSW_ERR_INVALID, 'the libssw context must be bound to the CudaOps stream')
+        self.ctx = ctx if ctx is not None else Context(int(device), stream=self.stream.cuda_stream)
+
+    def scope(self):
+        return torch.cuda.stream(self.stream)
+
+    def synchronize(self):
+        self.stream.synchronize()
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -159,21 +179,24 @@ class ShardedFrame:
             raise SswError(_lib.SSW_ERR_INVALID, 'expected this rank\'s rows as [%d][%d][3] uint8' % (p.hb, p.width))
         self.rgb_rows = rgb_rows
         self.shard = ssw_shard(p.width, p.height, p.col0, p.wb)
-        a = ops.lines_forward(rgb_rows, p.width, p.hb, PIX_RGB8)                 # rows: [hb][W]
-        send = ops.transpose_blocks(a, p.hb, p.wb, p.width, world)               # [G][wb][hb]
-        recv = _all_to_all(send, group)                                          # recv[g] = rows of rank g
-        t = ops.interleave_blocks(recv)                                          # [wb][H]
-        self.coeff = ops.lines_forward(t, p.height, p.wb, PIX_PLANE, out=t)      # cols, in place
+        with _scope(ops):
+            a = ops.lines_forward(rgb_rows, p.width, p.hb, PIX_RGB8)                 # rows: [hb][W]
+            send = ops.transpose_blocks(a, p.hb, p.wb, p.width, world)               # [G][wb][hb]
+            recv = _all_to_all(send, group)                                          # recv[g] = rows of rank g
+            t = ops.interleave_blocks(recv)                                          # [wb][H]
+            self.coeff = ops.lines_forward(t, p.height, p.wb, PIX_PLANE, out=t)      # cols, in place
 
     def ordered_indices(self, k, ordering=0):
         """first k entries of obtain_indices_by_function (src/algorithm.rs:200-210), identical on every rank"""
         p, ops = self.plan, self.ops
         k = min(int(k), p.width * p.height - 1)
-        b = _all_reduce(ops.topk_bin(self.coeff, self.shard, ordering, k), dist.ReduceOp.MAX, self.group)
-        cand, cnt = ops.topk_collect(self.coeff, self.shard, ordering, b)
-        lists, counts = _all_gather(cand, self.group), _all_gather(cnt, self.group).reshape(-1)
-        idx, overflow = ops.topk_merge(lists, counts, k)
-        if int(overflow.item()):
+        with _scope(ops):
+            b = _all_reduce(ops.topk_bin(self.coeff, self.shard, ordering, k), dist.ReduceOp.MAX, self.group)
+            cand, cnt = ops.topk_collect(self.coeff, self.shard, ordering, b)
+            lists, counts = _all_gather(cand, self.group), _all_gather(cnt, self.group).reshape(-1).contiguous()
+            idx, overflow = ops.topk_merge(lists, counts, k)
+            overflowed = int(overflow.item())
+        if overflowed:
             raise SswError(_lib.SSW_ERR_UNSUPPORTED, 'sharded top-k: candidate overflow (flat spectrum); '
                            'the low-frequency bound was too loose for this frame')
         return idx
@@ -181,12 +204,13 @@ class ShardedFrame:
     def inverse_rgb8(self):
         """DCT-III of the (possibly modified) coefficients back to this rank's RGB8 rows; consumes them"""
         p, ops = self.plan, self.ops
-        t = ops.lines_inverse(self.coeff, p.height, p.wb, 1.0)                   # cols: [wb][H]
-        send = ops.transpose_blocks(t, p.wb, p.hb, p.height, p.world)            # [G][hb][wb]
-        recv = _all_to_all(send, self.group)                                     # recv[g] = my rows, columns of rank g
-        a = ops.interleave_blocks(recv)                                          # [hb][W]
-        out = ops.empty((p.hb, p.width, 3), torch.uint8)
-        ops.lines_inverse(a, p.width, p.hb, 4.0 / float(p.width * p.height), PIX_RGB8, out, PIX_RGB8, self.rgb_rows)
+        with _scope(ops):
+            t = ops.lines_inverse(self.coeff, p.height, p.wb, 1.0)                   # cols: [wb][H]
+            send = ops.transpose_blocks(t, p.wb, p.hb, p.height, p.world)            # [G][hb][wb]
+            recv = _all_to_all(send, self.group)                                     # recv[g] = my rows, columns of rank g
+            a = ops.interleave_blocks(recv)                                          # [hb][W]
+            out = ops.empty((p.hb, p.width, 3), torch.uint8)
+            ops.lines_inverse(a, p.width, p.hb, 4.0 / float(p.width * p.height), PIX_RGB8, out, PIX_RGB8, self.rgb_rows)
         self.coeff = None
         return out
 
@@ -208,8 +232,9 @@ class ShardedWriter:
         k = min(lens.pop(), self.frame.plan.width * self.frame.plan.height - 1)
         self.indices = self.frame.ordered_indices(k, self.cfg.ordering)
         import numpy as np
-        m = self.ops.to_device(np.stack([np.asarray(x, dtype=np.float32)[:k] for x in marks]), torch.float32)
-        self.ops.embed(self.frame.coeff, self.frame.shard, self.indices, m, self.cfg)
+        with _scope(self.ops):
+            m = self.ops.to_device(np.stack([np.asarray(x, dtype=np.float32)[:k] for x in marks]), torch.float32)
+            self.ops.embed(self.frame.coeff, self.frame.shard, self.indices, m, self.cfg)
 
     def result_rgb8(self):
         return self.frame.inverse_rgb8()
@@ -234,5 +259,6 @@ class ShardedReader:
             raise SswError(_lib.SSW_ERR_INVALID, 'Desired extraction length exceeds available coefficients.')
         derived = ShardedFrame(derived_rows, *self.args)
         idx = self.base.ordered_indices(n, self.cfg.ordering)
-        part = self.ops.extract(self.base.coeff, derived.coeff, self.base.shard, idx, n, self.cfg)
-        return _all_reduce(part, dist.ReduceOp.SUM, self.group)   # every index has exactly one owner
+        with _scope(self.ops):
+            part = self.ops.extract(self.base.coeff, derived.coeff, self.base.shard, idx, n, self.cfg)
+            return _all_reduce(part, dist.ReduceOp.SUM, self.group)   # every index has exactly one owner

@@ -14,25 +14,30 @@ def test_sharded_path_world1_matches_unsharded(wm, ctx, so, w, h, k):
     from spread_spectrum_watermarking_b200 import sharded
     frame = so.synth_frame(w, h, seed=31)
     mark = np.random.default_rng(w).standard_normal(k).astype(np.float32)
-    ops = sharded.CudaOps(ctx)
+    ops = sharded.CudaOps(0)
     cfg = wm._lib.ssw_config(2, 0.1, 0)
     rows = torch.from_numpy(frame).cuda()
     torch.cuda.synchronize()
     wr = sharded.ShardedWriter(rows, w, h, cfg, ops, rank=0, world=1)
-    ctx.synchronize()
+    ops.synchronize()
     coeff_t = wr.frame.coeff.cpu().numpy()                      # [w][h] transposed
     plain = wm.Writer.new(frame, ctx=ctx)
     c = plain.coefficient_image()
     assert np.abs(coeff_t.T - c).max() <= 4e-7 * np.abs(c).max()
     wr.embed([mark])
+    ops.synchronize()
     idx = wr.indices.cpu().numpy().astype(np.int64)
     assert (idx == so.obtain_indices(coeff_t.T.copy().ravel(), k=k)).all(), 'exact ordering of its own coefficients'
-    out = wr.result_rgb8().cpu().numpy()
+    out_t = wr.result_rgb8()
+    ops.synchronize()
+    out = out_t.cpu().numpy()
     ref = plain.mark_rgb8([mark])
     d = np.abs(out.astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 0.02
     rd = sharded.ShardedReader(rows, w, h, cfg, ops, rank=0, world=1)
-    ext = rd.extract(torch.from_numpy(out).cuda(), k).cpu().numpy()
+    ext_t = rd.extract(out_t, k)
+    ops.synchronize()
+    ext = ext_t.cpu().numpy()
     ref_ext = wm.Reader.base(frame, ctx=ctx).extract(wm.Reader.derived(out, ctx=ctx), k)
     assert np.abs(ext - ref_ext).max() < 5e-3
     assert float(wm.Tester.new(ext, ctx=ctx).similarity(mark).similarity) > 6
@@ -41,9 +46,11 @@ def test_sharded_path_world1_matches_unsharded(wm, ctx, so, w, h, k):
 def test_transpose_blocks(wm, ctx):
     import torch
     from spread_spectrum_watermarking_b200 import sharded
-    ops = sharded.CudaOps(ctx)
+    ops = sharded.CudaOps(0)
     a = torch.arange(70 * 96, dtype=torch.float32, device='cuda').reshape(70, 96)
-    t = ops.transpose_blocks(a, 70, 24, 96, 4)
-    ctx.synchronize()
+    torch.cuda.synchronize()
+    with ops.scope():
+        t = ops.transpose_blocks(a, 70, 24, 96, 4)
+    ops.synchronize()
     for j in range(4):
         assert torch.equal(t[j], a[:, j * 24:(j + 1) * 24].T)
