@@ -518,6 +518,125 @@ struct ColPass {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// single-line kernels: one real line of length N = 2M per CTA through an M-point complex FFT (real-FFT
+// split).  A packed line PAIR of N complex samples needs 8N bytes of shared memory, which stops at
+// N ~ 28000; this form needs 4N bytes and carries the 32768-point lines of the gigapixel frames.
+//   forward : v = Makhoul(x);  z[m] = v[2m] + i v[2m+1];  Z = FFT_M(z);  with P = (Z_k + conj Z_{M-k})/2,
+//             Q = W_N^k (-i)(Z_k - conj Z_{M-k})/2:  V_k = P + Q,  V_{M-k} = conj(P - Q);
+//             X_k = 2 Re(t_k V_k),  X_{N-k} = -2 Im(t_k V_k)            (t_k = exp(-i pi k / 2N))
+//   inverse : V_k = conj(t_k)(X_k - i X_{N-k})/2;  A_k = (V_k + V_{k+M})/2 + i conj(W_N^k)(V_k - V_{k+M})/2;
+//             (y[2m], y[2m+1]) = conj(FFT_M(conj A))[m], un-permuted   (= 0.25 * scipy dct type 3)
+// P_ is the plan of the M-point FFT.  Verified against the oracle by tests/test_emul_fast.py.
+// ------------------------------------------------------------------------------------------------
+SSW_HD cplx cconj(cplx a) { return mk(a.x, -a.y); }
+SSW_HD cplx cscale(cplx a, float f) { return mk(a.x * f, a.y * f); }
+
+template <class P>
+SSW_HD cplx line1_w(const cplx* t4, int k) {  // W_N^k = exp(-2 pi i k / N) = t4[4k], N = 2*P::N, k <= N/4
+    return (4 * k == 2 * P::N) ? mk(0.f, -1.f) : SSW_LDG(&t4[4 * k]);
+}
+
+template <class P_, int SRC_>
+struct Line1Fwd {
+    using P = P_;
+    static constexpr int M = P_::N, N = 2 * P_::N, SRC = SRC_, THREADS = P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int SMEM = P_::PITCH * (int)sizeof(cplx);
+    static constexpr int MINB = 0;
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)w; return h; }
+
+    template <int PH>
+    static SSW_HD void phase(const FastArgs& a, cplx* s, int tile, int t, Thread& th) {
+        constexpr int T = P::T;
+        const int img = tile / a.tiles_per_image;
+        const int row = tile - img * a.tiles_per_image;
+        if constexpr (PH == 0) {
+            const void* src = image_base<SRC>(a.src, img, a.src_stride);
+#pragma unroll 2
+            for (int u = t; u < N / 4; u += T) {
+                float y[4];
+                load_luma4<SRC>(src, (long long)row * N + 4 * u, y);
+                s[P::idx(u)] = mk(y[0], y[2]);
+                s[P::idx(M - 1 - u)] = mk(y[3], y[1]);
+            }
+        } else if constexpr (PH < NPH - 1) {
+            fft_phase<P, PH>(s, a.tw, t, th.v);
+        } else {
+            float* o = a.plane + img * a.plane_stride + (long long)row * N;
+#pragma unroll 2
+            for (int k = t; k <= M / 2; k += T) {
+                const cplx zk = s[P::idx(k)], zr = cconj(s[P::idx(k ? M - k : 0)]);
+                const cplx p = cscale(cadd(zk, zr), 0.5f);
+                const cplx q = cmul(line1_w<P>(a.t4, k), cscale(mul_mi(csub(zk, zr)), 0.5f));
+                const cplx u1 = cmul(SSW_LDG(&a.t4[k]), cadd(p, q));
+                const cplx u2 = cmul(SSW_LDG(&a.t4[M - k]), cconj(csub(p, q)));
+                o[k] = 2.f * u1.x * (k ? a.scalen : a.scale0);
+                o[M - k] = 2.f * u2.x * a.scalen;
+                if (k) {
+                    o[N - k] = -2.f * u1.y * a.scalen;
+                    o[M + k] = -2.f * u2.y * a.scalen;
+                }
+            }
+        }
+    }
+};
+
+template <class P_, int DST_, int SRC_>
+struct Line1Inv {
+    using P = P_;
+    static constexpr int M = P_::N, N = 2 * P_::N, DST = DST_, SRC = SRC_, THREADS = P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int SMEM = P_::PITCH * (int)sizeof(cplx);
+    static constexpr int MINB = 0;
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)w; return h; }
+
+    template <int PH>
+    static SSW_HD void phase(const FastArgs& a, cplx* s, int tile, int t, Thread& th) {
+        constexpr int T = P::T;
+        const int img = tile / a.tiles_per_image;
+        const int row = tile - img * a.tiles_per_image;
+        if constexpr (PH == 0) {
+            const float* x = a.plane + img * a.plane_stride + (long long)row * N;
+#pragma unroll 2
+            for (int k = t; k <= M / 2; k += T) {
+                if (k == 0) {
+                    const float v0 = 0.5f * x[0], vm = 0.70710678118654752440f * x[M];
+                    s[P::idx(0)] = mk(0.5f * (v0 + vm), -0.5f * (v0 - vm));  // conj(A_0)
+                    continue;
+                }
+                const float xk = x[k], xmk = x[M - k], xpk = x[M + k], xnk = x[N - k];
+                const cplx tk = SSW_LDG(&a.t4[k]), tm = SSW_LDG(&a.t4[M - k]);
+                const cplx tkM = mul_mi(cconj(tm));   // t_{M+k} = -i conj(t_{M-k})
+                const cplx tnk = mul_mi(cconj(tk));   // t_{N-k} = -i conj(t_k)
+                const cplx w = line1_w<P>(a.t4, k);
+                // V_j = conj(t_j) (X_j - i X_{N-j}) / 2
+                const cplx vk = cscale(cmul(cconj(tk), mk(xk, -xnk)), 0.5f);
+                const cplx vkM = cscale(cmul(cconj(tkM), mk(xpk, -xmk)), 0.5f);
+                const cplx vm = cscale(cmul(cconj(tm), mk(xmk, -xpk)), 0.5f);
+                const cplx vnk = cscale(cmul(cconj(tnk), mk(xnk, -xk)), 0.5f);
+                // A_k = (V_k + V_{k+M})/2 + i conj(W)(V_k - V_{k+M})/2 ;  A_{M-k}: W^{M-k} = -conj(W)
+                const cplx ak = cadd(cscale(cadd(vk, vkM), 0.5f), mul_pi(cscale(cmul(cconj(w), csub(vk, vkM)), 0.5f)));
+                const cplx am = cadd(cscale(cadd(vm, vnk), 0.5f), mul_pi(cscale(cmul(mk(-w.x, -w.y), csub(vm, vnk)), 0.5f)));
+                s[P::idx(k)] = cconj(ak);
+                s[P::idx(M - k)] = cconj(am);
+            }
+        } else if constexpr (PH < NPH - 1) {
+            fft_phase<P, PH>(s, a.tw, t, th.v);
+        } else {
+            const void* src = (DST == PIX_PLANE) ? nullptr : image_base<SRC>(a.src, img, a.src_stride);
+            void* dst = const_cast<void*>(image_base<DST>(a.dst, img, a.dst_stride));
+#pragma unroll 2
+            for (int u = t; u < N / 4; u += T) {
+                const cplx f = s[P::idx(u)], g = s[P::idx(M - 1 - u)];
+                float y[4];
+                y[0] = f.x * a.scale0; y[2] = -f.y * a.scale0; y[3] = g.x * a.scale0; y[1] = -g.y * a.scale0;
+                store_pix4<DST, SRC>(src, dst, (long long)row * N + 4 * u, y);
+            }
+        }
+    }
+};
+
 #if defined(__CUDACC__)
 template <class K>
 constexpr int min_blocks() {
@@ -563,6 +682,10 @@ using Plan2160 = Plan<2160, 192, 15, 12, 12>;
 using Plan1920 = Plan<1920, 128, 15, 16, 8>;
 using Plan1080 = Plan<1080, 96, 15, 6, 12>;
 using Plan640 = Plan<640, 64, 5, 8, 16>;
+// plans of the M = N/2 point FFT of the single-line kernels (lines of 1024, 4096, 32768 samples)
+using PlanL512 = Plan<512, 64, 8, 8, 8>;
+using PlanL2048 = Plan<2048, 128, 16, 16, 8>;
+using PlanL16384 = Plan<16384, 1024, 16, 16, 16, 4>;
 
 }  // namespace fast
 }  // namespace ssw

@@ -24,5 +24,17 @@ inline bool with_plan(int n, F&& f) {
 
 inline bool has_plan(int n) { return with_plan(n, [](auto) {}); }
 
+// single-line kernels (one real line through an n/2-point complex FFT): line length -> plan of the FFT
+template <class F>
+inline bool with_line1_plan(int n, F&& f) {
+    switch (n) {
+        case 1024: f(PlanL512{}); return true;
+        case 4096: f(PlanL2048{}); return true;
+        case 32768: f(PlanL16384{}); return true;
+        default: return false;
+    }
+}
+inline bool has_line1_plan(int n) { return with_line1_plan(n, [](auto) {}); }
+
 }  // namespace fast
 }  // namespace ssw

@@ -61,6 +61,7 @@ struct ssw_ctx {
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
+    bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -140,6 +141,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     if (const char* s = getenv("SSW_TOPK_FULL_HIST")) c->topk_full_hist = atoi(s) != 0;
+    if (const char* s = getenv("SSW_FORCE_LINE1")) c->force_line1 = atoi(s) != 0;
     *out = c.release();
     return SSW_OK;
 }
@@ -335,9 +337,35 @@ static int fast_tables(ssw_ctx* c, const cplx** tw, const cplx** t4) {
     return SSW_OK;
 }
 
-template <class K>
+// single-line kernels: stage twiddles of the M-point plan + exp(-i*pi*k/2N) for the line length N = 2M
+template <class P>
+static int line1_tables(ssw_ctx* c, const cplx** tw, const cplx** t4) {
+    const int key = -(int)P::N;  // negative keys: line1 tables (pair plans use +N)
+    auto it = c->fast_tw.find(key);
+    if (it == c->fast_tw.end()) {
+        const int n = 2 * P::N;
+        std::vector<float> h(2 * (size_t)P::TW_TOTAL + 2 + 2 * (size_t)n);
+        fast::make_stage_twiddles<P>(h.data());
+        float* t = h.data() + 2 * (size_t)P::TW_TOTAL + 2;
+        for (int j = 0; j < n; ++j) {
+            const double b = -M_PI * (double)j / (2.0 * (double)n);
+            t[2 * j] = (float)std::cos(b);
+            t[2 * j + 1] = (float)std::sin(b);
+        }
+        void* d = nullptr;
+        CK(cudaMalloc(&d, h.size() * sizeof(float)));
+        CK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        it = c->fast_tw.emplace(key, d).first;
+    }
+    *tw = (const cplx*)it->second;
+    *t4 = (const cplx*)((const float*)it->second + 2 * (size_t)P::TW_TOTAL + 2);
+    return SSW_OK;
+}
+
+template <class K, bool LINE1 = false>
 static int launch_fast(ssw_ctx* c, const char* name, fast::FastArgs a, int w, int h, int batch) {
-    CKS(fast_tables<typename K::P>(c, &a.tw, &a.t4));
+    if (LINE1) CKS(line1_tables<typename K::P>(c, &a.tw, &a.t4));
+    else CKS(fast_tables<typename K::P>(c, &a.tw, &a.t4));
     a.tiles_per_image = K::tiles_per_image(w, h);
     const long long tiles = (long long)a.tiles_per_image * batch;
     if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
@@ -444,13 +472,57 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
 }
 
 // forward: pixels/plane -> coefficient plane (rows then columns)
+// single-line kernels (lines too long for a packed pair, e.g. 32768; SSW_FORCE_LINE1=1 prefers them wherever
+// a plan exists so that the GPU tests can compare them with the pair kernels)
+static int line1_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
+                         float scale0, float scalen, bool* done) {
+    *done = false;
+    if (src_type != PIX_RGB8 && src_type != PIX_PLANE) return SSW_OK;
+    if (!aligned(d_plane, 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
+    int rc = SSW_OK;
+    *done = fast::with_line1_plan(w, [&](auto p) {
+        using P = decltype(p);
+        fast::FastArgs a = fast_args(w, h);
+        a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
+        if (src_type == PIX_RGB8) rc = launch_fast<fast::Line1Fwd<P, PIX_RGB8>, true>(c, "fwd_line1", a, w, h, batch);
+        else rc = launch_fast<fast::Line1Fwd<P, PIX_PLANE>, true>(c, "fwd_line1_plane", a, w, h, batch);
+    });
+    return rc;
+}
+
+static int line1_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_src, int w, int h, int batch,
+                         int dst_type, void* d_dst, float scale, bool* done) {
+    *done = false;
+    if (!aligned(d_plane, 16)) return SSW_OK;
+    const bool rgb8 = dst_type == PIX_RGB8 && src_type == PIX_RGB8 && aligned(d_src, 4) && aligned(d_dst, 4);
+    const bool plane = dst_type == PIX_PLANE && aligned(d_dst, 16);
+    if (!rgb8 && !plane) return SSW_OK;
+    int rc = SSW_OK;
+    *done = fast::with_line1_plan(w, [&](auto p) {
+        using P = decltype(p);
+        fast::FastArgs a = fast_args(w, h);
+        a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
+        if (rgb8) rc = launch_fast<fast::Line1Inv<P, PIX_RGB8, PIX_RGB8>, true>(c, "inv_line1", a, w, h, batch);
+        else rc = launch_fast<fast::Line1Inv<P, PIX_PLANE, PIX_PLANE>, true>(c, "inv_line1_plane", a, w, h, batch);
+    });
+    return rc;
+}
+
 // row pass of the forward transform: pixels / plane rows -> DCT-II along x (x scale0/scalen) -> plane
 static int run_rows_forward(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
                             float rs0, float rsn) {
     const long long npix = (long long)w * h;
     bool done = false;
+    if (c->force_line1) {
+        CKS(line1_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
+        if (done) return SSW_OK;
+    }
     CKS(fast_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
     if (done) return SSW_OK;
+    if (w > 16384) {
+        CKS(line1_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
+        if (done) return SSW_OK;
+    }
     const DevPlan* pw;
     CKS(get_plan(c, w, &pw));
     Tiling tr;
@@ -496,8 +568,16 @@ static int run_rows_inverse(ssw_ctx* c, float* d_plane, int src_type, const void
                             int dst_type, void* d_dst, float out_scale) {
     const long long npix = (long long)w * h;
     bool done = false;
+    if (c->force_line1) {
+        CKS(line1_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
+        if (done) return SSW_OK;
+    }
     CKS(fast_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
     if (done) return SSW_OK;
+    if (w > 16384) {
+        CKS(line1_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
+        if (done) return SSW_OK;
+    }
     const DevPlan* pw;
     CKS(get_plan(c, w, &pw));
     Tiling tr;

@@ -121,6 +121,43 @@ int emul_fast_row_inv(int dst_type, int src_type, float* plane, const void* src,
     }) ? 0 : -2;
 }
 
+// single-line kernels: n_lines lines of length n (plan of n/2 points); src_type / dst_type as above
+int emul_line1_fwd(int src_type, const void* src, int n, int n_lines, float* plane, float scale0, float scalen) {
+    return with_line1_plan(n, [&](auto p) {
+        using P = decltype(p);
+        Tables<P> tb;   // stage twiddles of the M-point plan; t4 below must have N = 2M entries
+        std::vector<float> t4(2 * (size_t)n);
+        for (int j = 0; j < n; ++j) {
+            const double b = -M_PI * (double)j / (2.0 * (double)n);
+            t4[2 * j] = (float)std::cos(b); t4[2 * j + 1] = (float)std::sin(b);
+        }
+        FastArgs a = base_args(n, n_lines);
+        a.src = src; a.plane = plane; a.scale0 = scale0; a.scalen = scalen;
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)t4.data();
+        a.tiles_per_image = n_lines;
+        if (src_type == PIX_RGB8) emulate<Line1Fwd<P, PIX_RGB8>>(a, n_lines);
+        else emulate<Line1Fwd<P, PIX_PLANE>>(a, n_lines);
+    }) ? 0 : -2;
+}
+
+int emul_line1_inv(int dst_type, float* plane, const void* src, int n, int n_lines, void* dst, float scale) {
+    return with_line1_plan(n, [&](auto p) {
+        using P = decltype(p);
+        Tables<P> tb;
+        std::vector<float> t4(2 * (size_t)n);
+        for (int j = 0; j < n; ++j) {
+            const double b = -M_PI * (double)j / (2.0 * (double)n);
+            t4[2 * j] = (float)std::cos(b); t4[2 * j + 1] = (float)std::sin(b);
+        }
+        FastArgs a = base_args(n, n_lines);
+        a.src = src; a.plane = plane; a.dst = dst; a.scale0 = scale;
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)t4.data();
+        a.tiles_per_image = n_lines;
+        if (dst_type == PIX_RGB8) emulate<Line1Inv<P, PIX_RGB8, PIX_RGB8>>(a, n_lines);
+        else emulate<Line1Inv<P, PIX_PLANE, PIX_PLANE>>(a, n_lines);
+    }) ? 0 : -2;
+}
+
 // exactness of the division-free u8 -> [0,1] conversion: returns the number of mismatching inputs
 int emul_fast_u8_unit_mismatches(void) {
     int bad = 0;

@@ -123,3 +123,32 @@ def test_rgb32f_rows_match_rgb8_rows(emul, so):
     assert emul.emul_fast_row_inv(1, 1, ptr(p8.copy()), ptr(rgbf), w, h, 1, ptr(o32b), s) == 0
     assert (so.rgb32f_to_rgb8(o32) == o8).all() and (o8b == o8).all() and (o32b == o32).all()
     assert o32.min() >= 0.0 and o32.max() <= 1.0 and (o8 != rgb).any()
+
+
+@pytest.mark.parametrize('n', [1024, 4096, 32768])
+def test_single_line_kernels(emul, so, n):
+    """one real line through an n/2-point complex FFT (the form that carries 32768-point lines)"""
+    lines = 3 if n < 32768 else 2
+    rng = np.random.default_rng(n)
+    a = rng.random((lines, n)).astype(np.float32)
+    out = np.zeros_like(a)
+    assert emul.emul_line1_fwd(2, ptr(a), n, lines, ptr(out), f32(1.0), f32(1.0)) == 0
+    ref = dct1d_rows(so, a, 'fwd')
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    back = np.zeros_like(a)
+    c = ref.astype(np.float32)
+    assert emul.emul_line1_inv(2, ptr(c), None, n, lines, ptr(back), f32(2.0 / n)) == 0
+    assert np.abs(back - a).max() <= 4e-6
+
+
+def test_single_line_rgb8(emul, so):
+    n, lines = 1024, 4
+    rgb = so.synth_frame(n, lines, seed=8)
+    plane = np.zeros((lines, n), np.float32)
+    assert emul.emul_line1_fwd(0, ptr(rgb), n, lines, ptr(plane), f32(1.0), f32(1.0)) == 0
+    y, _, _ = so.rgb32f_to_yiq(so.rgb8_to_rgb32f(rgb))
+    ref = dct1d_rows(so, y, 'fwd')
+    assert np.abs(plane - ref).max() <= 2e-6 * np.abs(ref).max()
+    out = np.zeros_like(rgb)
+    assert emul.emul_line1_inv(0, ptr(plane.copy()), ptr(rgb), n, lines, ptr(out), f32(2.0 / n)) == 0
+    assert np.abs(out.astype(int) - rgb.astype(int)).max() <= 1 and (out != rgb).mean() < 0.01

@@ -54,3 +54,68 @@ def test_transpose_blocks(wm, ctx):
     ops.synchronize()
     for j in range(4):
         assert torch.equal(t[j], a[:, j * 24:(j + 1) * 24].T)
+
+
+@pytest.mark.parametrize('w,h', [(1024, 96), (4096, 40)])
+def test_single_line_kernels_match_pair_kernels(wm, so, w, h, monkeypatch):
+    """SSW_FORCE_LINE1 routes the row passes through the single-line kernels (one real line per n/2-point
+    FFT); the coefficients and the watermarked pixels must agree with the line-pair kernels"""
+    rgb = so.synth_frame(w, h, seed=13)
+    monkeypatch.setenv('SSW_FORCE_LINE1', '1')
+    c1 = wm.Context(0)
+    monkeypatch.delenv('SSW_FORCE_LINE1')
+    c2 = wm.Context(0)
+    try:
+        w1, w2 = wm.Writer.new(rgb, ctx=c1), wm.Writer.new(rgb, ctx=c2)
+        a, b = w1.coefficient_image(), w2.coefficient_image()
+        ref, _, _ = so.forward(rgb)
+        assert np.abs(a - b).max() <= 4e-7 * np.abs(b).max()
+        assert np.abs(a - ref).max() <= 4e-7 * np.abs(ref).max()
+        mark = np.random.default_rng(w).standard_normal(300).astype(np.float32)
+        o1, o2 = w1.mark_rgb8([mark]), w2.mark_rgb8([mark])
+        d = np.abs(o1.astype(int) - o2.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.02
+    finally:
+        w1 = w2 = None
+        import gc
+        gc.collect()
+        c1.close(); c2.close()
+
+
+def test_32768_point_lines(wm, ctx, so):
+    """the line length of the gigapixel config: only the single-line kernels can hold it"""
+    w, h = 32768, 8
+    rng = np.random.default_rng(1)
+    a = rng.random((h, w)).astype(np.float32)
+    f = a.copy().ravel()
+    wm.dct2d.dct2_2d(0, w, h, f, ctx)
+    ref = so.dct2_2d(a, so.DCT2)
+    assert np.abs(f.reshape(h, w) - ref).max() <= 4e-7 * np.abs(ref).max()
+    b = ref.astype(np.float32).ravel().copy()
+    wm.dct2d.dct2_2d(2, w, h, b, ctx)
+    assert np.abs(b.reshape(h, w) - a).max() < 4e-6
+
+
+def test_sharded_world1_32768_wide(wm, ctx, so):
+    import torch
+    from spread_spectrum_watermarking_b200 import sharded
+    w, h, k = 32768, 64, 300
+    frame = so.synth_frame(w, h, seed=41)
+    mark = np.random.default_rng(2).standard_normal(k).astype(np.float32)
+    ops = sharded.CudaOps(0)
+    cfg = wm._lib.ssw_config(2, 0.1, 0)
+    rows = torch.from_numpy(frame).cuda()
+    torch.cuda.synchronize()
+    wr = sharded.ShardedWriter(rows, w, h, cfg, ops, rank=0, world=1)
+    out_t = wr.mark_rgb8([mark])
+    ops.synchronize()
+    ref_img, ref_idx, _ = so.embed(frame, [mark])
+    out = out_t.cpu().numpy()
+    d = np.abs(out.astype(int) - ref_img.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-2
+    idx = wr.indices.cpu().numpy().astype(np.int64)
+    assert set(idx.tolist()) == set(ref_idx.tolist())
+    rd = sharded.ShardedReader(rows, w, h, cfg, ops, rank=0, world=1)
+    ext_t = rd.extract(out_t, k)
+    ops.synchronize()
+    assert float(so.similarity(ext_t.cpu().numpy(), mark)) > 6
