@@ -48,6 +48,8 @@ WORKLOADS = {
                name='single synthetic 3840x2160 RGB frame, mark length 1000, embed+extract'),
     'c3': dict(w=1920, h=1080, batch=64, ring=2, seed=3,
                name='batches of synthetic 1920x1080 RGB frames, mark length 1000, embed+extract'),
+    'c4': dict(w=32768, h=32768, batch=1, ring=1, seed=4,
+               name='gigapixel 32768x32768 single frame, row-sharded DCT with all-to-all transpose and distributed top-k'),
     'c5': dict(w=3840, h=2160, batch=1, ring=8, seed=5,
                name='extraction on 3840x2160 frames + similarity against a bank of 100k stored marks (length 1000)'),
 }
@@ -498,6 +500,176 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# configs[3]: one gigapixel frame sharded by rows over the ranks (strong scaling)
+# ------------------------------------------------------------------------------------------------
+C4_BYTES_PER_PX = {'fwd_line1': 7.0, 'fwd_line1_plane': 8.0, 'inv_line1_plane': 8.0, 'inv_line1': 10.0, 'transpose': 8.0,
+                   'topk_collect': 4.0, 'fwd_rows': 7.0, 'fwd_rows_plane': 8.0, 'inv_rows_plane': 8.0, 'inv_rows': 10.0,
+                   'row_fwd_rgb8': 7.0, 'row_fwd_plane': 8.0, 'row_inv_plane': 8.0, 'row_inv_rgb8': 10.0}
+C4_PASSES = {'fwd_line1': 3, 'fwd_line1_plane': 3, 'inv_line1_plane': 1, 'inv_line1': 1, 'transpose': 4, 'topk_collect': 2,
+             'fwd_rows': 3, 'fwd_rows_plane': 3, 'inv_rows_plane': 1, 'inv_rows': 1,
+             'row_fwd_rgb8': 3, 'row_fwd_plane': 3, 'row_inv_plane': 1, 'row_inv_rgb8': 1}
+
+
+def run_c4(args, wl):
+    import torch
+    import torch.distributed as dist
+    import spread_spectrum_watermarking_b200 as wm
+    from spread_spectrum_watermarking_b200 import sharded
+    from spread_spectrum_watermarking_b200._lib import check, lib, ssw_config
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)' % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    w = h = int(os.environ.get('SSW_C4_SIZE', wl['w']))
+    ops = sharded.CudaOps(local)
+    ctx = ops.ctx
+    plan = sharded.ShardPlan(w, h, world, rank)
+    cfg = ssw_config(2, ALPHA, 0)
+    rows = torch.empty((plan.hb, w, 3), dtype=torch.uint8, device='cuda')
+    with ops.scope():
+        check(lib.ssw_synth_rows_rgb8_dev(ctx.handle, w, wl['seed'], 0, plan.row0, plan.hb, rows.data_ptr()))
+    mark = np.random.default_rng(1000).standard_normal(MARK_LEN).astype(np.float32)
+    state = {}
+
+    def step(_s):
+        wr = sharded.ShardedWriter(rows, w, h, cfg, ops)
+        out = wr.mark_rgb8([mark])
+        rd = sharded.ShardedReader(rows, w, h, cfg, ops)
+        state['ext'] = rd.extract(out, MARK_LEN)
+        state['out'] = out
+
+    def barrier():
+        ops.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ops.stream)
+        for s in range(steps):
+            fn(warmup + s)
+        e1.record(ops.stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    K, W = max(1, min(args.steps, 10)), max(3, min(args.warmup, 3))
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count
+    ms_total = timed(step, K, W)
+    launches = (ctx.launch_count - l0) * K // (K + W)
+    clk = clocks.stop() if rank == 0 else None
+    with ops.scope():
+        ext = state['ext'].cpu().numpy()
+    sim = float(wm.Tester.new(ext, ctx=ctx).similarity(mark).similarity)
+    if not sim > 6.0:
+        raise SystemExit('bench c4: the embedded mark was not detected (similarity %.2f)' % sim)
+    px = w * h
+    value = px * K / (ms_total * 1e-3) / 1e6
+
+    barrier()
+    ctx.profile_begin()
+    for s in range(K):
+        step(s)
+    ops.synchronize()
+    prof = ctx.profile_end()
+    peak, peak_src = load_peaks()
+    kernels = []
+    for name, r in prof.items():
+        avg_us = r['ms'] / r['launches'] * 1e3
+        ent = {'name': name, 'launches_per_step': r['launches'] / K, 'avg_us': round(avg_us, 2), 'share': 0.0,
+               'algo_bytes': None, 'gbs': None, 'frac': None}
+        bpp = C4_BYTES_PER_PX.get(name)
+        if bpp:
+            ab = bpp * (px / world) * C4_PASSES.get(name, 1) * K / r['launches']
+            ent.update(algo_bytes=ab, gbs=round(ab / (avg_us * 1e-6) / 1e9, 1), frac=round(ab / (avg_us * 1e-6) / 1e9 / peak, 4))
+        kernels.append(ent)
+    tot = sum(r['ms'] for r in prof.values()) or 1.0
+    for ent in kernels:
+        ent['share'] = round(prof[ent['name']]['ms'] / tot, 4)
+    kernels.sort(key=lambda e: -e['share'])
+    dom = next((e for e in kernels if e['frac'] is not None), None)
+    roofline = None
+    if dom:
+        roofline = {'bound': 'hbm', 'kernel': dom['name'], 'achieved': dom['gbs'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': dom['frac'], 'traffic': load_traffic().get(dom['name']), 'peak_source': peak_src,
+                    'algo_bytes_per_launch': dom['algo_bytes'], 'avg_launch_us': dom['avg_us'], 'share_of_step': dom['share']}
+    kernel_ms = tot / K
+
+    # end to end: this rank's rows from pinned host memory, the watermarked rows and the extracted vector back
+    hrows = torch.empty((plan.hb, w, 3), dtype=torch.uint8).pin_memory()
+    hout = torch.empty((plan.hb, w, 3), dtype=torch.uint8).pin_memory()
+    with ops.scope():
+        hrows.copy_(rows)
+    ops.synchronize()
+
+    def e2e_step(_s):
+        with ops.scope():
+            d = hrows.to('cuda', non_blocking=True)
+        wr = sharded.ShardedWriter(d, w, h, cfg, ops)
+        out = wr.mark_rgb8([mark])
+        with ops.scope():
+            hout.copy_(out, non_blocking=True)
+            d2 = hrows.to('cuda', non_blocking=True)      # Reader::base uploads the original again
+            d3 = hout.to('cuda', non_blocking=True)       # Reader::derived uploads the watermarked image
+        rd = sharded.ShardedReader(d2, w, h, cfg, ops)
+        e = rd.extract(d3, MARK_LEN)
+        with ops.scope():
+            state['e2e_ext'] = e.cpu()
+
+    Ke = 2
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        e2e_step(s)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    fb = plan.hb * w * 3
+    e2e = {'value': px * Ke / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 3 * fb + MARK_LEN * 4,
+           'd2h_bytes_per_step': fb + MARK_LEN * 4, 'steps': Ke, 'ms_per_step': e2e_ms / Ke,
+           'api': 'sharded.ShardedWriter.mark_rgb8 + ShardedReader.extract (per-rank rows in pinned host memory)'}
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
+            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'frame': [w, h], 'frames_per_step': 1, 'mark_len': MARK_LEN, 'alpha': ALPHA,
+                       'insertion': 'Option2', 'ordering': 'Energy',
+                       'l2': 'inputs larger than L2: %.1f GB of RGB8 rows per rank' % (fb / 1e9),
+                       'parallelism': 'rows sharded over %d rank(s); all-to-all transpose between the DCT passes '
+                                      '(2 per embed, 1 per image per extract), distributed top-k' % world},
+            'roofline': roofline, 'kernels': kernels, 'kernel_ms_per_step': kernel_ms,
+            'cpu_baseline': None, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'similarity': sim,
+        }), flush=True)
+    state.clear()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -515,6 +687,8 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29533')] + sys.argv
         raise SystemExit(subprocess.call(cmd))
+    if args.workload == 'c4':
+        return run_c4(args, wl)
     run_ours(args, wl)
 
 

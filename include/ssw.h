@@ -178,6 +178,10 @@ int ssw_ctx_last_topk_fallbacks(ssw_ctx* ctx);
 int ssw_synth_frame_rgb8_dev(ssw_ctx* ctx, uint32_t width, uint32_t height, uint64_t seed,
                              uint32_t first_image, uint32_t n_images, uint8_t* out_dev);
 
+/* rows [row0, row0+n_rows) of synthetic frame `image` (one rank's shard of a sharded frame) */
+int ssw_synth_rows_rgb8_dev(ssw_ctx* ctx, uint32_t width, uint64_t seed, uint32_t image, uint32_t row0, uint32_t n_rows,
+                            uint8_t* out_dev);
+
 /* ---- per-stage timing hooks for bench.py / profiling: run one stage of the pipeline on
  *      device-resident data (used to attribute time to kernels with CUDA events). */
 int ssw_stage_forward_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width, uint32_t height,

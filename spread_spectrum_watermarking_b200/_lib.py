@@ -101,6 +101,7 @@ SIGNATURES = {
     'ssw_extract_batch_rgb8': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _cfg, c_size_t, _p, _p, _p]),
     'ssw_ctx_last_topk_fallbacks': (c_int, [_p]),
     'ssw_synth_frame_rgb8_dev': (c_int, [_p, c_uint32, c_uint32, c_uint64, c_uint32, c_uint32, _p]),
+    'ssw_synth_rows_rgb8_dev': (c_int, [_p, c_uint32, c_uint64, c_uint32, c_uint32, c_uint32, _p]),
     'ssw_stage_forward_rgb8_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, _p]),
     'ssw_stage_topk_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, c_int, c_size_t, _p]),
     'ssw_stage_inverse_rgb8_dev': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _p]),

@@ -319,13 +319,14 @@ __device__ __forceinline__ unsigned long long sm64(unsigned long long x) {
 }
 
 __global__ void synth_frame_kernel(unsigned char* __restrict__ out, unsigned w, unsigned h,
-                                   unsigned long long seed, unsigned first_image) {
+                                   unsigned long long seed, unsigned first_image, unsigned row0) {
     const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned y = blockIdx.y;
+    const unsigned yl = blockIdx.y;          // row inside the generated block of h rows
+    const unsigned y = row0 + yl;            // row of the frame
     const unsigned img = blockIdx.z;
     if (x >= w) return;
     const unsigned long long base = seed ^ ((unsigned long long)(first_image + img) * 0x9E3779B97F4A7C15ull);
-    unsigned char* o = out + ((size_t)img * h * w + (size_t)y * w + x) * 3;
+    unsigned char* o = out + ((size_t)img * h * w + (size_t)yl * w + x) * 3;
     for (unsigned c = 0; c < 3; ++c) {
         unsigned long long acc = 0;
         for (unsigned oct = 2; oct <= 8; ++oct) {

@@ -1444,7 +1444,21 @@ extern "C" int ssw_synth_frame_rgb8_dev(ssw_ctx* c, uint32_t w, uint32_t h, uint
     CKS(ctx_bind(c));
     for (uint32_t i0 = 0; i0 < n_images; i0 += 65535) {
         const uint32_t nb = std::min<uint32_t>(65535, n_images - i0);
-        { KScope ks(c, "synth_frame"); synth_frame_kernel<<<dim3((w + 127) / 128, h, nb), 128, 0, c->stream>>>(out + (size_t)i0 * w * h * 3, w, h, seed, first_image + i0); }
+        { KScope ks(c, "synth_frame"); synth_frame_kernel<<<dim3((w + 127) / 128, h, nb), 128, 0, c->stream>>>(out + (size_t)i0 * w * h * 3, w, h, seed, first_image + i0, 0u); }
+        CK(cudaGetLastError());
+    }
+    return SSW_OK;
+}
+
+// rows [row0, row0 + n_rows) of synthetic frame `image` (the shard of one rank of a sharded frame)
+extern "C" int ssw_synth_rows_rgb8_dev(ssw_ctx* c, uint32_t w, uint64_t seed, uint32_t image, uint32_t row0, uint32_t n_rows,
+                                       uint8_t* out) {
+    if (!c || !out) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(w, n_rows));
+    CKS(ctx_bind(c));
+    for (uint32_t r = 0; r < n_rows; r += 32768) {
+        const uint32_t nr = std::min<uint32_t>(32768, n_rows - r);
+        { KScope ks(c, "synth_frame"); synth_frame_kernel<<<dim3((w + 127) / 128, nr, 1), 128, 0, c->stream>>>(out + (size_t)r * w * 3, w, nr, seed, image, row0 + r); }
         CK(cudaGetLastError());
     }
     return SSW_OK;
