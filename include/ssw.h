@@ -207,6 +207,10 @@ typedef struct ssw_shard {
 /* 1-D DCT-II (x2, reference scaling) of n_lines contiguous lines of length n; src_type 0 RGB8 (luma is
  * computed, src/yiq.rs:157), 1 RGB32F, 2 f32 lines.  The row pass of dct2_2d (src/dct2d.rs:129-170). */
 int ssw_lines_forward_dev(ssw_ctx* ctx, int src_type, const void* src_dev, uint32_t n, uint32_t n_lines, float* plane_dev);
+/* the same over lines assembled from all-to-all blocks, read in place (no interleaving copy): src layout
+ * [chunks][ranks][n_lines][seg_len]; SSW_ERR_UNSUPPORTED unless seg_len, chunks are powers of two and n is planned */
+int ssw_lines_forward_seg_dev(ssw_ctx* ctx, const float* src_dev, uint32_t n, uint32_t n_lines, uint32_t seg_len,
+                              uint32_t chunks, uint32_t ranks, float* plane_dev);
 /* 1-D DCT-III (x0.5) of the lines, then x scale; dst_type 2: f32 lines, 0 / 1: RGB8 / RGB32F with the chroma
  * of the original pixels `src_dev` (src/yiq.rs:187-197). */
 int ssw_lines_inverse_dev(ssw_ctx* ctx, float* plane_dev, uint32_t n, uint32_t n_lines, float scale, int dst_type,

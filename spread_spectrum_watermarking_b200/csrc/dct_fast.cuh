@@ -38,7 +38,19 @@ struct FastArgs {
     float scale0, scalen;  // forward: factors for k == 0 / k > 0; inverse: scale0 = output scale
     const cplx* tw;        // stage twiddles of the plan, layout per stage [r-1][k]
     const cplx* t4;        // exp(-i*pi*k/(2N)), k < N
+    // segmented f32 source lines (sharded frames: a line is the concatenation of the blocks received from
+    // the all-to-all, buffer layout [chunks][ranks][lines][seg_len]); seg_shift < 0: contiguous lines.
+    // sample m of line l lives at (((c*ranks + g)*lines + l) << seg_shift) + (m & (seg_len-1)) with
+    // s = m >> seg_shift, g = s >> chunk_shift, c = s & (chunks-1)      (seg_len and chunks: powers of two)
+    int seg_shift, chunk_shift, seg_ranks, seg_lines;
 };
+
+// position of 4 consecutive samples [m, m+4) of line `line` inside a segmented source
+SSW_HD long long seg_index(const FastArgs& a, int line, int m) {
+    const int s = m >> a.seg_shift, off = m & ((1 << a.seg_shift) - 1);
+    const int g = s >> a.chunk_shift, c = s & ((1 << a.chunk_shift) - 1);
+    return (((long long)(c * a.seg_ranks + g) * a.seg_lines + line) << a.seg_shift) + off;
+}
 
 // ------------------------------------------------------------------------------------------------
 // plan: N = R0*R1*R2*R3 (unused trailing radices = 1), T threads cooperate on one line pair
@@ -336,8 +348,13 @@ struct RowFwd {
                 const int u = t + it * T;
                 if (u < N / 4) {
                     float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (ha) load_luma4<SRC>(src, rowa + 4 * u, ya);
-                    if (hb) load_luma4<SRC>(src, rowa + N + 4 * u, yb);
+                    if (SRC == PIX_PLANE && a.seg_shift >= 0) {
+                        if (ha) load_luma4<SRC>(src, seg_index(a, ra, 4 * u), ya);
+                        if (hb) load_luma4<SRC>(src, seg_index(a, rb, 4 * u), yb);
+                    } else {
+                        if (ha) load_luma4<SRC>(src, rowa + 4 * u, ya);
+                        if (hb) load_luma4<SRC>(src, rowa + N + 4 * u, yb);
+                    }
                     put4<P>(s, u, ya, yb);
                 }
             }
@@ -556,7 +573,7 @@ struct Line1Fwd {
 #pragma unroll 2
             for (int u = t; u < N / 4; u += T) {
                 float y[4];
-                load_luma4<SRC>(src, (long long)row * N + 4 * u, y);
+                load_luma4<SRC>(src, (SRC == PIX_PLANE && a.seg_shift >= 0) ? seg_index(a, row, 4 * u) : (long long)row * N + 4 * u, y);
                 s[P::idx(u)] = mk(y[0], y[2]);
                 s[P::idx(M - 1 - u)] = mk(y[3], y[1]);
             }

@@ -62,6 +62,7 @@ struct ssw_ctx {
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
+    struct { bool active = false; int seg_shift = -1, chunk_shift = 0, ranks = 1, lines = 0; } seg;  // ssw_lines_forward_seg_dev
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -389,7 +390,14 @@ static fast::FastArgs fast_args(int w, int h) {
     a.w = w; a.h = h;
     a.scale0 = 1.f; a.scalen = 1.f;
     a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
+    a.seg_shift = -1;
     return a;
+}
+
+static void apply_seg(const ssw_ctx* c, fast::FastArgs* a) {
+    if (!c->seg.active) return;
+    a->seg_shift = c->seg.seg_shift; a->chunk_shift = c->seg.chunk_shift;
+    a->seg_ranks = c->seg.ranks; a->seg_lines = c->seg.lines;
 }
 
 static bool aligned(const void* p, size_t n) { return (((size_t)p) & (n - 1)) == 0; }
@@ -406,6 +414,7 @@ static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int 
         constexpr int G = fast::RowG<P>::value;
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
+        apply_seg(c, &a);
         if (src_type == PIX_RGB8) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
         else if (src_type == PIX_RGB32F) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB32F>>(c, "fwd_rows_rgb32f", a, w, h, batch);
         else rc = launch_fast<fast::RowFwd<P, G, PIX_PLANE>>(c, "fwd_rows_plane", a, w, h, batch);
@@ -484,6 +493,7 @@ static int line1_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int
         using P = decltype(p);
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
+        apply_seg(c, &a);
         if (src_type == PIX_RGB8) rc = launch_fast<fast::Line1Fwd<P, PIX_RGB8>, true>(c, "fwd_line1", a, w, h, batch);
         else rc = launch_fast<fast::Line1Fwd<P, PIX_PLANE>, true>(c, "fwd_line1_plane", a, w, h, batch);
     });
@@ -519,10 +529,11 @@ static int run_rows_forward(ssw_ctx* c, int src_type, const void* d_src, int w, 
     }
     CKS(fast_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
     if (done) return SSW_OK;
-    if (w > 16384) {
+    if (w > 16384 || c->seg.active) {
         CKS(line1_row_fwd(c, src_type, d_src, w, h, batch, d_plane, rs0, rsn, &done));
         if (done) return SSW_OK;
     }
+    if (c->seg.active) return fail(SSW_ERR_UNSUPPORTED, "segmented source lines need a planned line length");
     const DevPlan* pw;
     CKS(get_plan(c, w, &pw));
     Tiling tr;
@@ -1500,6 +1511,30 @@ extern "C" int ssw_lines_forward_dev(ssw_ctx* c, int src_type, const void* src, 
     CKS(check_dims(n, n_lines));
     CKS(ctx_bind(c));
     return run_rows_forward(c, src_type, src, (int)n, (int)n_lines, 1, plane, 1.f, 1.f);
+}
+
+// the same over lines assembled from all-to-all blocks, read in place: src layout [chunks][ranks][n_lines][seg_len],
+// sample m of a line in segment s = m / seg_len, which came from rank s / chunks, chunk s % chunks.
+// SSW_ERR_UNSUPPORTED (caller falls back to an interleaving copy) unless seg_len and chunks are powers of two,
+// seg_len % 4 == 0 and the line length has a compile-time plan.
+extern "C" int ssw_lines_forward_seg_dev(ssw_ctx* c, const float* src, uint32_t n, uint32_t n_lines, uint32_t seg_len,
+                                         uint32_t chunks, uint32_t ranks, float* plane) {
+    if (!c || !src || !plane) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_dims(n, n_lines));
+    if (seg_len == 0 || chunks == 0 || ranks == 0 || (uint64_t)seg_len * chunks * ranks != n)
+        return fail(SSW_ERR_INVALID, "segments do not tile the line");
+    int ss = 0, cs = 0;
+    while ((1u << ss) < seg_len) ++ss;
+    while ((1u << cs) < chunks) ++cs;
+    if ((1u << ss) != seg_len || (1u << cs) != chunks || (seg_len & 3u) || src == plane)
+        return fail(SSW_ERR_UNSUPPORTED, "segmented source lines: seg_len and chunks must be powers of two (seg_len >= 4), out of place");
+    if (!fast::has_plan((int)n) && !fast::has_line1_plan((int)n))
+        return fail(SSW_ERR_UNSUPPORTED, "segmented source lines need a planned line length");
+    CKS(ctx_bind(c));
+    c->seg.active = true; c->seg.seg_shift = ss; c->seg.chunk_shift = cs; c->seg.ranks = (int)ranks; c->seg.lines = (int)n_lines;
+    const int rc = run_rows_forward(c, PIX_PLANE, src, (int)n, (int)n_lines, 1, plane, 1.f, 1.f);
+    c->seg.active = false;
+    return rc;
 }
 
 extern "C" int ssw_lines_inverse_dev(ssw_ctx* c, float* plane, uint32_t n, uint32_t n_lines, float scale, int dst_type,

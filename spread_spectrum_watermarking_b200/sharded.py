@@ -53,6 +53,18 @@ class ShardPlan:
         return (c % self.wb) * self.height + r
 
 
+def _pick_chunks(n_lines, world):
+    """slices of the local pass whose all-to-all overlaps the next slice's kernels (1 when nothing is exchanged)"""
+    import os
+    if world == 1:
+        return 1
+    floor = int(os.environ.get('SSW_SHARD_MIN_CHUNK_LINES', '64'))
+    for c in (4, 2):
+        if n_lines % (2 * c) == 0 and n_lines // c >= floor:
+            return c
+    return 1
+
+
 def _scope(ops):
     """stream scope of the ops object (CudaOps: its torch stream; CPU stand-ins: nothing)"""
     import contextlib
@@ -66,6 +78,13 @@ def _all_to_all(send, group):
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
     return recv
+
+
+def _all_to_all_async(recv, send, group):
+    """start the exchange of one chunk; returns a handle whose wait() orders the current stream after it
+    (None when there is nothing to exchange).  NCCL runs it on its own stream, so the kernels launched next
+    on the ops stream overlap with the transfer."""
+    return dist.all_to_all_single(recv, send, group=group, async_op=True)
 
 
 def _all_gather(t, group):
@@ -124,13 +143,27 @@ class CudaOps:
         return dst
 
     def interleave_blocks(self, recv):
-        """recv [G][lines][seg] -> [lines][G*seg] (line l = concatenation of the G segments)"""
-        g, lines, seg = recv.shape
-        if g == 1:
+        """recv [C][G][lines][seg] -> [lines][G*C*seg]: line l = concatenation over ranks g, chunks c of its segments"""
+        c, g, lines, seg = recv.shape
+        if g == 1 and c == 1:
             return recv.view(lines, seg)
-        out = self.empty((lines, g, seg), torch.float32)
-        out.copy_(recv.permute(1, 0, 2))   # plain strided copy (data movement only)
-        return out.view(lines, g * seg)
+        out = self.empty((lines, g, c, seg), torch.float32)
+        out.copy_(recv.permute(2, 1, 0, 3))   # plain strided copy (data movement only)
+        return out.view(lines, g * c * seg)
+
+    def lines_forward_segmented(self, recv, n):
+        """DCT-II of the lines held as all-to-all blocks [C][G][lines][seg], read in place when the kernels
+        support it (power-of-two segments, planned length); otherwise interleave first"""
+        c, g, lines, seg = recv.shape
+        if c * g > 1:
+            plane = self.empty((lines, n), torch.float32)
+            rc = lib.ssw_lines_forward_seg_dev(self.ctx.handle, recv.data_ptr(), n, lines, seg, c, g, plane.data_ptr())
+            if rc == _lib.SSW_OK:
+                return plane
+            if rc != _lib.SSW_ERR_UNSUPPORTED:
+                check(rc)
+        t = self.interleave_blocks(recv)
+        return self.lines_forward(t, n, lines, PIX_PLANE, out=t)
 
     def topk_bin(self, plane, shard, ordering, k):
         b = self.empty((1,), torch.int32)
@@ -179,12 +212,24 @@ class ShardedFrame:
             raise SswError(_lib.SSW_ERR_INVALID, 'expected this rank\'s rows as [%d][%d][3] uint8' % (p.hb, p.width))
         self.rgb_rows = rgb_rows
         self.shard = ssw_shard(p.width, p.height, p.col0, p.wb)
+        # the row pass runs in `chunks` slices; the exchange of slice i overlaps the kernels of slice i+1
+        chunks = _pick_chunks(p.hb, world)
+        hc = p.hb // chunks
         with _scope(ops):
-            a = ops.lines_forward(rgb_rows, p.width, p.hb, PIX_RGB8)                 # rows: [hb][W]
-            send = ops.transpose_blocks(a, p.hb, p.wb, p.width, world)               # [G][wb][hb]
-            recv = _all_to_all(send, group)                                          # recv[g] = rows of rank g
-            t = ops.interleave_blocks(recv)                                          # [wb][H]
-            self.coeff = ops.lines_forward(t, p.height, p.wb, PIX_PLANE, out=t)      # cols, in place
+            recv = ops.empty((chunks, world, p.wb, hc), torch.float32) if world > 1 else None
+            pending = []
+            for ci in range(chunks):
+                a = ops.lines_forward(rgb_rows[ci * hc:(ci + 1) * hc], p.width, hc, PIX_RGB8)   # rows: [hc][W]
+                send = ops.transpose_blocks(a, hc, p.wb, p.width, world)                       # [G][wb][hc]
+                if world == 1:
+                    recv = send.view(1, 1, p.wb, hc)          # nothing to exchange: the transpose is the result
+                else:
+                    pending.append((_all_to_all_async(recv[ci], send, group), send))
+            for work, _keep in pending:
+                if work is not None:
+                    work.wait()
+            # line l of my columns = segments [rank g][chunk c] of recv[c][g][l]
+            self.coeff = ops.lines_forward_segmented(recv, p.height)                  # cols: [wb][H]
 
     def ordered_indices(self, k, ordering=0):
         """first k entries of obtain_indices_by_function (src/algorithm.rs:200-210), identical on every rank"""
@@ -204,10 +249,21 @@ class ShardedFrame:
     def inverse_rgb8(self):
         """DCT-III of the (possibly modified) coefficients back to this rank's RGB8 rows; consumes them"""
         p, ops = self.plan, self.ops
+        chunks = _pick_chunks(p.wb, p.world)
+        wc = p.wb // chunks
         with _scope(ops):
-            t = ops.lines_inverse(self.coeff, p.height, p.wb, 1.0)                   # cols: [wb][H]
-            send = ops.transpose_blocks(t, p.wb, p.hb, p.height, p.world)            # [G][hb][wb]
-            recv = _all_to_all(send, self.group)                                     # recv[g] = my rows, columns of rank g
+            recv = ops.empty((chunks, p.world, p.hb, wc), torch.float32) if p.world > 1 else None
+            pending = []
+            for ci in range(chunks):
+                t = ops.lines_inverse(self.coeff[ci * wc:(ci + 1) * wc], p.height, wc, 1.0)     # cols: [wc][H]
+                send = ops.transpose_blocks(t, wc, p.hb, p.height, p.world)                    # [G][hb][wc]
+                if p.world == 1:
+                    recv = send.view(1, 1, p.hb, wc)
+                else:
+                    pending.append((_all_to_all_async(recv[ci], send, self.group), send))
+            for work, _keep in pending:
+                if work is not None:
+                    work.wait()
             a = ops.interleave_blocks(recv)                                          # [hb][W]
             out = ops.empty((p.hb, p.width, 3), torch.uint8)
             ops.lines_inverse(a, p.width, p.hb, 4.0 / float(p.width * p.height), PIX_RGB8, out, PIX_RGB8, self.rgb_rows)

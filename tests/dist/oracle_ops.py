@@ -46,8 +46,12 @@ class OracleOps:
         return torch.from_numpy(np.stack([a[:, j * cols:(j + 1) * cols].T.copy() for j in range(nblocks)]))
 
     def interleave_blocks(self, recv):
-        g, lines, seg = recv.shape
-        return recv.permute(1, 0, 2).contiguous().view(lines, g * seg)
+        c, g, lines, seg = recv.shape
+        return recv.permute(2, 1, 0, 3).contiguous().view(lines, g * c * seg)
+
+    def lines_forward_segmented(self, recv, n):
+        t = self.interleave_blocks(recv)
+        return self.lines_forward(t, n, t.shape[0], 2, out=t)
 
     @staticmethod
     def _keys(plane, shard, ordering):

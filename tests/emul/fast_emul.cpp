@@ -45,6 +45,7 @@ FastArgs base_args(int w, int h) {
     a.w = w; a.h = h;
     a.scale0 = 1.f; a.scalen = 1.f;
     a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
+    a.seg_shift = -1;
     return a;
 }
 
@@ -155,6 +156,45 @@ int emul_line1_inv(int dst_type, float* plane, const void* src, int n, int n_lin
         a.tiles_per_image = n_lines;
         if (dst_type == PIX_RGB8) emulate<Line1Inv<P, PIX_RGB8, PIX_RGB8>>(a, n_lines);
         else emulate<Line1Inv<P, PIX_PLANE, PIX_PLANE>>(a, n_lines);
+    }) ? 0 : -2;
+}
+
+// forward pass over SEGMENTED f32 lines (layout [chunks][ranks][n_lines][seg_len]); line1 != 0: single-line kernels
+int emul_fwd_segmented(int line1, const float* src, int n, int n_lines, int seg_len, int chunks, int ranks, float* plane) {
+    int seg_shift = 0, chunk_shift = 0;
+    while ((1 << seg_shift) < seg_len) ++seg_shift;
+    while ((1 << chunk_shift) < chunks) ++chunk_shift;
+    if ((1 << seg_shift) != seg_len || (1 << chunk_shift) != chunks || seg_len * chunks * ranks != n) return -3;
+    auto fill = [&](FastArgs& a) {
+        a.src = src; a.plane = plane;
+        a.seg_shift = seg_shift; a.chunk_shift = chunk_shift; a.seg_ranks = ranks; a.seg_lines = n_lines;
+    };
+    if (line1) {
+        return with_line1_plan(n, [&](auto p) {
+            using P = decltype(p);
+            Tables<P> tb;
+            std::vector<float> t4(2 * (size_t)n);
+            for (int j = 0; j < n; ++j) {
+                const double b = -M_PI * (double)j / (2.0 * (double)n);
+                t4[2 * j] = (float)std::cos(b); t4[2 * j + 1] = (float)std::sin(b);
+            }
+            FastArgs a = base_args(n, n_lines);
+            fill(a);
+            a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)t4.data();
+            a.tiles_per_image = n_lines;
+            emulate<Line1Fwd<P, PIX_PLANE>>(a, n_lines);
+        }) ? 0 : -2;
+    }
+    return with_plan(n, [&](auto p) {
+        using P = decltype(p);
+        constexpr int G = RowG<P>::value;
+        Tables<P> tb;
+        FastArgs a = base_args(n, n_lines);
+        fill(a);
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+        using K = RowFwd<P, G, PIX_PLANE>;
+        a.tiles_per_image = K::tiles_per_image(n, n_lines);
+        emulate<K>(a, a.tiles_per_image);
     }) ? 0 : -2;
 }
 

@@ -152,3 +152,21 @@ def test_single_line_rgb8(emul, so):
     out = np.zeros_like(rgb)
     assert emul.emul_line1_inv(0, ptr(plane.copy()), ptr(rgb), n, lines, ptr(out), f32(2.0 / n)) == 0
     assert np.abs(out.astype(int) - rgb.astype(int)).max() <= 1 and (out != rgb).mean() < 0.01
+
+
+@pytest.mark.parametrize('line1,n,seg,chunks,ranks', [(1, 1024, 128, 2, 4), (1, 4096, 512, 4, 2), (1, 1024, 1024, 1, 1), (0, 1920, 128, 1, 15),
+                                                     (0, 640, 32, 4, 5)])
+def test_segmented_source_lines(emul, so, line1, n, seg, chunks, ranks):
+    """lines assembled from all-to-all blocks ([chunks][ranks][lines][seg]) are read in place"""
+    lines = 5
+    rng = np.random.default_rng(n + seg)
+    a = rng.random((lines, n)).astype(np.float32)
+    # sample m of line l: s = m // seg, g = s // chunks, c = s % chunks
+    blocks = np.zeros((chunks, ranks, lines, seg), np.float32)
+    for s_ in range(n // seg):
+        g, c = divmod(s_, chunks)
+        blocks[c, g] = a[:, s_ * seg:(s_ + 1) * seg]
+    out = np.zeros_like(a)
+    assert emul.emul_fwd_segmented(line1, ptr(blocks), n, lines, seg, chunks, ranks, ptr(out)) == 0
+    ref = dct1d_rows(so, a, 'fwd')
+    assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()

@@ -12,10 +12,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, 'tests', 'dist', 'run_sharded_gloo.py')
 
 
-def _run(world, args, port):
+def _run(world, args, port, min_chunk_lines=None):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
            '--master-addr', '127.0.0.1', '--master-port', str(port), WORKER] + [str(a) for a in args]
     env = dict(os.environ, OMP_NUM_THREADS='1')
+    if min_chunk_lines:
+        env['SSW_SHARD_MIN_CHUNK_LINES'] = str(min_chunk_lines)   # force the chunked (overlapped) exchange
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and 'SHARDED_GLOO_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
@@ -36,3 +38,8 @@ def test_shard_plan_partition():
                                                         (2, 64, 48, 100, 1, 29623)])
 def test_sharded_frame_over_gloo(world, w, h, k, ordering, port):
     _run(world, [w, h, k, ordering], port)
+
+
+def test_sharded_frame_chunked_exchange_over_gloo():
+    """4 slices per pass, each with its own asynchronous all-to-all"""
+    _run(2, [128, 64, 200, 0], 29624, min_chunk_lines=4)
