@@ -38,6 +38,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...") and debug output on stderr
+os.environ.setdefault('NCCL_DEBUG', 'WARN')
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 MARK_LEN = 1000
 ALPHA = 0.1
