@@ -171,34 +171,54 @@ topk_hist_kernel(const float* __restrict__ planes, long long plane_stride, unsig
 // candidate overflow, which is detected by topk_sort and repaired with the full histogram.
 constexpr int kBlockRows = 128, kBlockCols = 256;
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 topk_block_bin_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned k,
                       OrderConsts oc, TopkScratch ts) {
+    // grid (x = slices of the block, y = image): per-CTA shared histogram -> global histogram -> the last CTA of
+    // the image finds the bin (same ticket scheme as topk_hist_kernel; scratch is left zeroed)
     __shared__ unsigned sh[kHistBins];
-    const unsigned img = blockIdx.x;
+    __shared__ unsigned s_last;
+    const unsigned img = blockIdx.y;
     const float* plane = planes + (long long)img * plane_stride;
     for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const unsigned br = min(h, (unsigned)kBlockRows), bc = min(w, (unsigned)kBlockCols);
     const unsigned total = br * bc;
-    for (unsigned e0 = threadIdx.x; e0 < total; e0 += 8 * blockDim.x) {
-        float v[8];
-        unsigned p[8];
+    for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * gridDim.x * blockDim.x) {
+        float v[4];
+        unsigned p[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {   // 8 independent loads in flight per thread
-            const unsigned e = e0 + u * blockDim.x;
+        for (int u = 0; u < 4; ++u) {   // independent loads in flight
+            const unsigned e = e0 + u * gridDim.x * blockDim.x;
             const unsigned r = e / bc, c = e - r * bc;
             const unsigned q = r * w + c;            // local position (w = local line length)
             p[u] = e < total ? flat_index(q, oc) : 0u;
             v[u] = p[u] ? __ldg(plane + q) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 4; ++u)
             if (p[u]) atomicAdd(&sh[order_key(v[u], p[u], oc) >> (32 - kHistBits)], 1u);
     }
     __syncthreads();
+    unsigned* gh = ts.hist + (size_t)img * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&gh[i], sh[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ts.ticket[img], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) {
+        sh[i] = __ldcg(&gh[i]);
+        gh[i] = 0;
+    }
+    __syncthreads();
     const unsigned b = find_kth_bin(sh, k);
-    if (threadIdx.x == 0) ts.sel_bin[img] = b;
+    if (threadIdx.x == 0) {
+        ts.sel_bin[img] = b;
+        ts.ticket[img] = 0;
+    }
 }
 
 // ---- 2. collect candidates -----------------------------------------------------------------------
@@ -277,41 +297,45 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 
 template <int E>
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long (&v)[E], unsigned long long* sc) {
+    // The size / stride loops stay ROLLED on purpose: one CTA runs this once, so a fully unrolled network
+    // (hundreds of KB of straight-line code) would execute at instruction-fetch speed.
     const unsigned tid = threadIdx.x;
-#pragma unroll
+#pragma unroll 1
     for (unsigned size = 2; size <= (unsigned)(kSortThreads * E); size <<= 1) {
+#pragma unroll 1
+        for (unsigned stride = size >> 1; stride >= (unsigned)E; stride >>= 1) {
+            const unsigned tmask = stride / E;  // partner thread = tid ^ tmask, same slot
+            unsigned long long o[E];
+            if (tmask < 32u) {
 #pragma unroll
-        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride < (unsigned)E) {
+                for (int i = 0; i < E; ++i) o[i] = shfl_xor_u64(v[i], (int)tmask);
+            } else {
+#pragma unroll
+                for (int i = 0; i < E; ++i) sc[i * kSortThreads + tid] = v[i];
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < E; ++i) o[i] = sc[i * kSortThreads + (tid ^ tmask)];
+                __syncthreads();
+            }
+            // all E slots of a thread share the direction bits (stride, size >= E)
+            const bool keep_max = (((tid * E) & stride) == 0) == (((tid * E) & size) == 0);
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const bool gt = v[i] > o[i];
+                v[i] = (gt == keep_max) ? v[i] : o[i];
+            }
+        }
+        // strides < E: compare-exchanges inside the thread (at most log2(E) steps, unrolled per stride)
+#pragma unroll
+        for (unsigned stride = E >> 1; stride > 0; stride >>= 1) {
+            if (stride < size) {
 #pragma unroll
                 for (int i = 0; i < E; ++i) {
                     if ((i & stride) == 0) {
-                        const unsigned idx = tid * E + i;
-                        const bool desc = (idx & size) == 0;
+                        const bool desc = ((tid * E + i) & size) == 0;
                         const unsigned long long a = v[i], b = v[i + stride];
                         if ((a < b) == desc) { v[i] = b; v[i + stride] = a; }
                     }
-                }
-            } else {
-                const unsigned tmask = stride / E;  // partner thread = tid ^ tmask, same slot
-                unsigned long long o[E];
-                if (tmask < 32u) {
-#pragma unroll
-                    for (int i = 0; i < E; ++i) o[i] = shfl_xor_u64(v[i], (int)tmask);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < E; ++i) sc[i * kSortThreads + tid] = v[i];
-                    __syncthreads();
-#pragma unroll
-                    for (int i = 0; i < E; ++i) o[i] = sc[i * kSortThreads + (tid ^ tmask)];
-                    __syncthreads();
-                }
-#pragma unroll
-                for (int i = 0; i < E; ++i) {
-                    const unsigned idx = tid * E + i;
-                    const bool lower = (idx & stride) == 0, desc = (idx & size) == 0;
-                    const unsigned long long mx = v[i] > o[i] ? v[i] : o[i], mn = v[i] > o[i] ? o[i] : v[i];
-                    v[i] = (lower == desc) ? mx : mn;
                 }
             }
         }

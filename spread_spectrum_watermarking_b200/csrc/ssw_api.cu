@@ -679,7 +679,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
             topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
         } else {
             KScope ks(c, "topk_block_bin");
-            topk_block_bin_kernel<<<nb, 1024, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
+            topk_block_bin_kernel<<<dim3(16, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
         { KScope ks(c, "topk_collect"); topk_collect_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, oc, ts); }
         CK(cudaGetLastError());
@@ -1585,7 +1585,7 @@ extern "C" int ssw_shard_topk_bin_dev(ssw_ctx* c, const float* plane, const ssw_
     {
         KScope ks(c, "topk_block_bin");
         // local plane [ncols][height]: "width" of the block kernel is the local line length
-        topk_block_bin_kernel<<<1, 1024, 0, c->stream>>>(plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
+        topk_block_bin_kernel<<<dim3(16, 1), 512, 0, c->stream>>>(plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
     }
     CK(cudaGetLastError());
     return SSW_OK;
