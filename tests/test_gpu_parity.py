@@ -148,6 +148,36 @@ def test_attack_crop(wm, ctx, golden):
     assert s > 8.0 and abs(s - 8.07) < 0.06, s
 
 
+def test_attack_resize(wm, ctx, golden):
+    """tests/attack_resize.rs:17-36,65-66: down to 1/8 and back up with a Catmull-Rom filter (PIL BICUBIC, a = -0.5,
+    stands in for image::imageops::resize); similarity "approx 9.85", asserted > 9.5 there"""
+    from PIL import Image
+    cat, m = golden['cat'], golden['marks']['seed_2']
+    marked = wm.Writer.new(cat, ctx=ctx).mark_rgb8([m])
+    h, w = marked.shape[:2]
+    small = Image.fromarray(marked).resize((w // 8, h // 8), Image.BICUBIC)
+    back = np.asarray(small.resize((w, h), Image.BICUBIC))
+    e = wm.Reader.base(cat, ctx=ctx).extract(wm.Reader.derived(back, ctx=ctx), 1000)
+    s = float(wm.Tester.new(e, ctx=ctx).similarity(m).similarity)
+    assert s > 9.5 and abs(s - 9.87) < 0.3, s
+
+
+def test_bank_from_storage_file(wm, ctx, so, tmp_path):
+    """marks written in the reference CLI's JSON form are scored from a device-resident bank"""
+    from spread_spectrum_watermarking_b200 import storage
+    rng = np.random.default_rng(1)
+    marks = rng.standard_normal((5, 300)).astype(np.float32)
+    path = str(tmp_path / 'marks.json')
+    storage.save(path, {'method': 2, 'alpha': 0.1, 'ordering': 0}, marks)
+    bank, cfg, _ = storage.bank_from_file(path, ctx=ctx)
+    frame = so.synth_frame(320, 200, 3)
+    out = wm.Writer.new(frame, ctx=ctx).mark_rgb8([marks[3]])
+    e = wm.Reader.base(frame, ctx=ctx).extract(wm.Reader.derived(out, ctx=ctx), 300)
+    s = bank.similarity(e)[0]
+    assert int(s.argmax()) == 3 and s[3] > 6 and float(s[3]) == float(so.similarity(e, marks[3]))
+    bank.close()
+
+
 # ---------------------------------------------------------------------------- algorithm.rs unit tests through the API
 @pytest.mark.parametrize('method', [1, 2, 3])
 @pytest.mark.parametrize('ordering', [0, 1, 2])
