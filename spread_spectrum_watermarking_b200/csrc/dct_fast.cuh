@@ -109,6 +109,18 @@ SSW_HD bool stage_map(int t, int it, int& j, int& k) {
     }
 }
 
+// padded position of (base + off): when the constant offset is a multiple of 16 (or the layout is not padded)
+// the padding of the sum splits into idx(base) + a compile-time constant, so butterfly operands stay
+// addressed as base + immediate; otherwise (first power-of-two stage: off = r < 16 on a base that is a
+// multiple of 16) the low bits cannot carry either.
+template <class P, int OFF, bool BASE16>
+SSW_HD int idx_off(int base_idx, int base) {
+    if constexpr (!P::PAD) return base_idx + OFF;
+    else if constexpr (OFF % 16 == 0) return base_idx + OFF + OFF / 16;
+    else if constexpr (BASE16 && OFF < 16) return base_idx + OFF;
+    else return P::idx(base + OFF);
+}
+
 template <class P, int S>
 SSW_HD void stage_load(const cplx* s, int t, cplx* v) {
     using I = StageInfo<P, S>;
@@ -116,8 +128,11 @@ SSW_HD void stage_load(const cplx* s, int t, cplx* v) {
     for (int it = 0; it < I::ITER; ++it) {
         int j, k;
         if (stage_map<P, S>(t, it, j, k)) {
-#pragma unroll
-            for (int r = 0; r < I::R; ++r) v[it * I::R + r] = s[P::idx(j + r * I::NB)];
+            const int bj = P::idx(j);
+            static_for<I::R>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                v[it * I::R + r] = s[idx_off<P, r * I::NB, false>(bj, j)];
+            });
         }
     }
 }
@@ -137,8 +152,12 @@ SSW_HD void stage_store(cplx* s, const cplx* tw, int t, cplx* v) {
             }
             Dft<I::R>::run(x);
             const int j0 = (j - k) * I::R + k;
-#pragma unroll
-            for (int r = 0; r < I::R; ++r) s[P::idx(j0 + r * I::NS)] = x[r];
+            const int b0 = P::idx(j0);
+            // first stage (NS == 1): j0 = j*R; with R == 16 it is a multiple of 16 and r < 16 cannot carry
+            static_for<I::R>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                s[idx_off<P, r * I::NS, (I::NS == 1 && I::R == 16)>(b0, j0)] = x[r];
+            });
         }
     }
 }
@@ -468,7 +487,7 @@ struct ColPass {
             fft_phase<P, SUB>(smem + (RD * TEAMS + g) * P::PITCH, a.tw, t, th.v);
         } else if constexpr ((PH == 0) != INVERSE_) {
             // sample-domain side: forward load (PH == 0) or inverse store (PH == NPH-1)
-#pragma unroll
+#pragma unroll 6
             for (int it = 0; it < (N * H + THREADS - 1) / THREADS; ++it) {
                 const int e = tid + it * THREADS;
                 const int r = e / H, q = e - r * H;
@@ -499,7 +518,7 @@ struct ColPass {
             }
         } else {
             // coefficient-domain side: forward store (post pass) or inverse load (pre pass)
-#pragma unroll 4
+#pragma unroll(P::PAD ? 2 : 4)
             for (int e = tid; e < (N / 2 + 1) * H; e += THREADS) {
                 const int k = e / H, q = e - k * H;
                 const int c = c0 + 4 * q;
@@ -699,6 +718,12 @@ using Plan2160 = Plan<2160, 192, 15, 12, 12>;
 using Plan1920 = Plan<1920, 128, 15, 16, 8>;
 using Plan1080 = Plan<1080, 96, 15, 6, 12>;
 using Plan640 = Plan<640, 64, 5, 8, 16>;
+// powers of two (first radix even -> padded layout)
+using Plan1024 = Plan<1024, 64, 16, 16, 4>;
+using Plan2048 = Plan<2048, 128, 16, 16, 8>;
+using Plan4096 = Plan<4096, 256, 16, 16, 16>;
+using Plan8192 = Plan<8192, 512, 16, 16, 16, 2>;
+using Plan16384 = Plan<16384, 1024, 16, 16, 16, 4>;
 // plans of the M = N/2 point FFT of the single-line kernels (lines of 1024, 4096, 32768 samples)
 using PlanL512 = Plan<512, 64, 8, 8, 8>;
 using PlanL2048 = Plan<2048, 128, 16, 16, 8>;

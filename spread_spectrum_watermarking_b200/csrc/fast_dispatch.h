@@ -9,6 +9,12 @@ namespace fast {
 template <class P> struct RowG { static constexpr int value = (P::T >= 192) ? 1 : 2; };
 constexpr int kColG = 4;      // column pairs per CTA (8 adjacent columns = one 32-byte sector per row)
 constexpr int kColTeams = 2;  // teams transforming them (G / TEAMS rounds)
+constexpr int kMaxSmem = 227 * 1024;
+// column tiles of the long power-of-two lines: fewer pairs so that the tile still fits shared memory
+template <class P> struct ColG {
+    static constexpr int value = (4 * P::PITCH * 8 <= kMaxSmem) ? 4 : ((2 * P::PITCH * 8 <= kMaxSmem) ? 2 : 0);
+};
+template <class P> struct ColTeams { static constexpr int value = (P::T >= 512) ? 1 : 2; };
 
 template <class F>
 inline bool with_plan(int n, F&& f) {
@@ -18,6 +24,11 @@ inline bool with_plan(int n, F&& f) {
         case 1920: f(Plan1920{}); return true;
         case 1080: f(Plan1080{}); return true;
         case 640: f(Plan640{}); return true;
+        case 1024: f(Plan1024{}); return true;
+        case 2048: f(Plan2048{}); return true;
+        case 4096: f(Plan4096{}); return true;
+        case 8192: f(Plan8192{}); return true;
+        case 16384: f(Plan16384{}); return true;
         default: return false;
     }
 }

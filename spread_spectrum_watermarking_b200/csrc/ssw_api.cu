@@ -437,7 +437,13 @@ static int launch_col_variant(ssw_ctx* c, const fast::FastArgs& a, int w, int h,
         default: break;
     }
 #endif
-    return launch_fast<fast::ColPass<P, fast::kColG, fast::kColTeams, INV>>(c, name, a, w, h, batch);
+    constexpr int G = fast::ColG<P>::value, TEAMS = fast::ColTeams<P>::value;
+    if constexpr (G == 0) {
+        (void)a; (void)w; (void)h; (void)batch; (void)name;
+        return SSW_ERR_UNSUPPORTED;   // tile does not fit shared memory: generic column kernel
+    } else {
+        return launch_fast<fast::ColPass<P, G, TEAMS, INV, (P::PAD ? 2 : 0)>>(c, name, a, w, h, batch);
+    }
 }
 
 static int fast_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen,
@@ -452,6 +458,7 @@ static int fast_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_
         if (inverse) rc = launch_col_variant<P, true>(c, a, w, h, batch);
         else rc = launch_col_variant<P, false>(c, a, w, h, batch);
     });
+    if (rc == SSW_ERR_UNSUPPORTED) { *done = false; rc = SSW_OK; }
     return rc;
 }
 

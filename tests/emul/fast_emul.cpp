@@ -54,6 +54,7 @@ FastArgs base_args(int w, int h) {
 extern "C" {
 
 int emul_fast_has_plan(int n) { return has_plan(n) ? 1 : 0; }
+int emul_fast_col_pairs(int n) { int g = -1; with_plan(n, [&](auto p) { g = ColG<decltype(p)>::value; }); return g; }
 
 // src_type: 0 = RGB8, 1 = RGB32F, 2 = plane (PIX_*).  plane: [batch][h][w].  scale0/scalen: DCT2Orthogonal factors.
 int emul_fast_row_fwd(int src_type, const void* src, int w, int h, int batch, float* plane, float scale0, float scalen) {
@@ -88,14 +89,17 @@ int emul_fast_col(int inverse, int w, int h, int batch, float* plane, float scal
         FastArgs a = base_args(w, h);
         a.plane = plane; a.scale0 = scale0; a.scalen = scalen;
         a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
-        if (inverse) {
-            using K = ColPass<P, kColG, kColTeams, true>;
-            a.tiles_per_image = K::tiles_per_image(w, h);
-            emulate<K>(a, a.tiles_per_image * batch);
-        } else {
-            using K = ColPass<P, kColG, kColTeams, false>;
-            a.tiles_per_image = K::tiles_per_image(w, h);
-            emulate<K>(a, a.tiles_per_image * batch);
+        constexpr int G = ColG<P>::value, TEAMS = ColTeams<P>::value;
+        if constexpr (G > 0) {
+            if (inverse) {
+                using K = ColPass<P, G, TEAMS, true>;
+                a.tiles_per_image = K::tiles_per_image(w, h);
+                emulate<K>(a, a.tiles_per_image * batch);
+            } else {
+                using K = ColPass<P, G, TEAMS, false>;
+                a.tiles_per_image = K::tiles_per_image(w, h);
+                emulate<K>(a, a.tiles_per_image * batch);
+            }
         }
     }) ? 0 : -2;
 }
