@@ -442,7 +442,7 @@ static int launch_col_variant(ssw_ctx* c, const fast::FastArgs& a, int w, int h,
         (void)a; (void)w; (void)h; (void)batch; (void)name;
         return SSW_ERR_UNSUPPORTED;   // tile does not fit shared memory: generic column kernel
     } else {
-        return launch_fast<fast::ColPass<P, G, TEAMS, INV, (P::PAD ? 2 : 0)>>(c, name, a, w, h, batch);
+        return launch_fast<fast::ColPass<P, G, TEAMS, INV, ((P::PAD && TEAMS * P::T <= 256) ? 2 : 0)>>(c, name, a, w, h, batch);
     }
 }
 
