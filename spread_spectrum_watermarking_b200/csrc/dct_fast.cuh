@@ -43,6 +43,7 @@ struct FastArgs {
     // sample m of line l lives at (((c*ranks + g)*lines + l) << seg_shift) + (m & (seg_len-1)) with
     // s = m >> seg_shift, g = s >> chunk_shift, c = s & (chunks-1)      (seg_len and chunks: powers of two)
     int seg_shift, chunk_shift, seg_ranks, seg_lines;
+    int dbg_skip;   // tuning builds only (-DSSW_TUNE): 1 = no global loads, 2 = no global stores, 4 = no FFT stages
 };
 
 // position of 4 consecutive samples [m, m+4) of line `line` inside a segmented source
@@ -66,6 +67,7 @@ struct Plan {
     static constexpr int ns(int s) { int p = 1; for (int i = 0; i < s; ++i) p *= radix(i); return p; }
     static constexpr int tw_off(int s) { int o = 0; for (int i = 1; i < s; ++i) o += (radix(i) - 1) * ns(i); return o; }
     static constexpr int TW_TOTAL = tw_off(NST);
+    static constexpr int KEY = ((N_ * 31 + R0_) * 31 + R1_) * 31 + R2_;  // twiddle-cache key (plans of one N may differ in radices)
     static constexpr bool PAD = (R0_ % 2) == 0;
     static SSW_HD int idx(int a) { return PAD ? a + (a >> 4) : a; }
     static constexpr int LINE = PAD ? N_ + (N_ >> 4) : N_;
@@ -367,6 +369,9 @@ struct RowFwd {
                 const int u = t + it * T;
                 if (u < N / 4) {
                     float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
+#ifdef SSW_TUNE
+                    if (a.dbg_skip & 1) { ya[0] = (float)u; yb[1] = 1.f; } else
+#endif
                     if (SRC == PIX_PLANE && a.seg_shift >= 0) {
                         if (ha) load_luma4<SRC>(src, seg_index(a, ra, 4 * u), ya);
                         if (hb) load_luma4<SRC>(src, seg_index(a, rb, 4 * u), yb);
@@ -378,9 +383,15 @@ struct RowFwd {
                 }
             }
         } else if constexpr (PH < NPH - 1) {
+#ifdef SSW_TUNE
+            if (a.dbg_skip & 4) return;
+#endif
             fft_phase<P, PH>(s, a.tw, t, th.v);
         } else {
             if (ra >= a.h) return;
+#ifdef SSW_TUNE
+            if (a.dbg_skip & 2) { if (s[P::idx(t)].x == 123.456f) a.plane[t] = 1.f; return; }
+#endif
             const bool hb = rb < a.h;
             float* oa = a.plane + img * a.plane_stride + (long long)ra * N;
             float* ob = oa + N;
@@ -686,6 +697,8 @@ constexpr int min_blocks() {
 
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel(const __grid_constant__ FastArgs a) {
+    // one CTA per tile.  (A persistent one-wave grid striding over the tiles was measured: no faster, and the
+    // loop state cost registers in the widest kernels.)
     extern __shared__ __align__(16) unsigned char fast_smem[];
     typename K::Thread th;
     static_for<K::NPH>([&](auto ph) {
@@ -718,6 +731,10 @@ using Plan2160 = Plan<2160, 192, 15, 12, 12>;
 using Plan1920 = Plan<1920, 128, 15, 16, 8>;
 using Plan1080 = Plan<1080, 96, 15, 6, 12>;
 using Plan640 = Plan<640, 64, 5, 8, 16>;
+#ifdef SSW_TUNE
+using Plan3840b = Plan<3840, 480, 5, 8, 8, 12>;   // small radices, more threads per line pair
+using Plan3840c = Plan<3840, 384, 15, 8, 8, 4>;
+#endif
 // powers of two (first radix even -> padded layout)
 using Plan1024 = Plan<1024, 64, 16, 16, 4>;
 using Plan2048 = Plan<2048, 128, 16, 16, 8>;

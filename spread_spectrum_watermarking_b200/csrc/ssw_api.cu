@@ -60,6 +60,7 @@ struct ssw_ctx {
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
+    int row_variant = 0;                   // SSW_ROW_VARIANT (tuning builds)
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
     struct { bool active = false; int seg_shift = -1, chunk_shift = 0, ranks = 1, lines = 0; } seg;  // ssw_lines_forward_seg_dev
@@ -141,6 +142,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
+    if (const char* s = getenv("SSW_ROW_VARIANT")) c->row_variant = atoi(s);
     if (const char* s = getenv("SSW_TOPK_FULL_HIST")) c->topk_full_hist = atoi(s) != 0;
     if (const char* s = getenv("SSW_FORCE_LINE1")) c->force_line1 = atoi(s) != 0;
     *out = c.release();
@@ -325,14 +327,14 @@ static int fast_tables(ssw_ctx* c, const cplx** tw, const cplx** t4) {
     const DevPlan* gp;
     CKS(get_plan(c, P::N, &gp));  // the generic plan owns the exp(-i*pi*k/2N) table
     *t4 = gp->dev.t4;
-    auto it = c->fast_tw.find(P::N);
+    auto it = c->fast_tw.find(P::KEY);
     if (it == c->fast_tw.end()) {
         std::vector<float> h(2 * (size_t)P::TW_TOTAL + 2);
         fast::make_stage_twiddles<P>(h.data());
         void* d = nullptr;
         CK(cudaMalloc(&d, h.size() * sizeof(float)));
         CK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
-        it = c->fast_tw.emplace(P::N, d).first;
+        it = c->fast_tw.emplace(P::KEY, d).first;
     }
     *tw = (const cplx*)it->second;
     return SSW_OK;
@@ -391,6 +393,7 @@ static fast::FastArgs fast_args(int w, int h) {
     a.scale0 = 1.f; a.scalen = 1.f;
     a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
     a.seg_shift = -1;
+    a.dbg_skip = 0;
     return a;
 }
 
@@ -402,6 +405,10 @@ static void apply_seg(const ssw_ctx* c, fast::FastArgs* a) {
 
 static bool aligned(const void* p, size_t n) { return (((size_t)p) & (n - 1)) == 0; }
 
+#ifdef SSW_TUNE
+template <class K, int M> struct WithMinB : K { static constexpr int MINB = M; };
+#endif
+
 // returns SSW_OK and sets *done when a fast kernel ran; *done = false -> caller uses the generic kernel
 static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
                         float scale0, float scalen, bool* done) {
@@ -409,6 +416,27 @@ static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int 
     if (!c->use_fast) return SSW_OK;
     if (!aligned(d_plane, 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
     int rc = SSW_OK;
+#ifdef SSW_TUNE
+    if (w == 3840 && src_type == PIX_RGB8 && c->row_variant) {
+        fast::FastArgs a = fast_args(w, h);
+        a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
+        *done = true;
+        if (c->row_variant >= 10) {   // 10 + mask: default kernel with parts switched off (upper bounds for pipelining)
+            a.dbg_skip = c->row_variant - 10;
+            return launch_fast<fast::RowFwd<fast::Plan3840, 1, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+        }
+        switch (c->row_variant) {
+            case 1: return launch_fast<fast::RowFwd<fast::Plan3840b, 1, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+            case 2: return launch_fast<fast::RowFwd<fast::Plan3840, 2, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+            case 3: return launch_fast<fast::RowFwd<fast::Plan3840c, 1, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+            case 4: return launch_fast<fast::RowFwd<fast::Plan3840b, 2, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+            case 5: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840b, 1, PIX_RGB8>, 3>>(c, "fwd_rows", a, w, h, batch);
+            case 6: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840, 1, PIX_RGB8>, 5>>(c, "fwd_rows", a, w, h, batch);
+            case 7: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840c, 1, PIX_RGB8>, 3>>(c, "fwd_rows", a, w, h, batch);
+            default: *done = false; break;
+        }
+    }
+#endif
     *done = fast::with_plan(w, [&](auto p) {
         using P = decltype(p);
         constexpr int G = fast::RowG<P>::value;

@@ -46,6 +46,7 @@ FastArgs base_args(int w, int h) {
     a.scale0 = 1.f; a.scalen = 1.f;
     a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
     a.seg_shift = -1;
+    a.dbg_skip = 0;
     return a;
 }
 
@@ -56,7 +57,8 @@ extern "C" {
 int emul_fast_has_plan(int n) { return has_plan(n) ? 1 : 0; }
 int emul_fast_col_pairs(int n) { int g = -1; with_plan(n, [&](auto p) { g = ColG<decltype(p)>::value; }); return g; }
 
-// src_type: 0 = RGB8, 1 = RGB32F, 2 = plane (PIX_*).  plane: [batch][h][w].  scale0/scalen: DCT2Orthogonal factors.
+// src_type: 0 = RGB8, 1 = RGB32F, 2 = plane (PIX_*).
+// plane: [batch][h][w].  scale0/scalen: DCT2Orthogonal factors.
 int emul_fast_row_fwd(int src_type, const void* src, int w, int h, int batch, float* plane, float scale0, float scalen) {
     return with_plan(w, [&](auto p) {
         using P = decltype(p);
@@ -65,19 +67,14 @@ int emul_fast_row_fwd(int src_type, const void* src, int w, int h, int batch, fl
         FastArgs a = base_args(w, h);
         a.src = src; a.plane = plane; a.scale0 = scale0; a.scalen = scalen;
         a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
-        if (src_type == PIX_RGB8) {
-            using K = RowFwd<P, G, PIX_RGB8>;
+        auto run = [&](auto k) {
+            using K = decltype(k);
             a.tiles_per_image = K::tiles_per_image(w, h);
             emulate<K>(a, a.tiles_per_image * batch);
-        } else if (src_type == PIX_RGB32F) {
-            using K = RowFwd<P, G, PIX_RGB32F>;
-            a.tiles_per_image = K::tiles_per_image(w, h);
-            emulate<K>(a, a.tiles_per_image * batch);
-        } else {
-            using K = RowFwd<P, G, PIX_PLANE>;
-            a.tiles_per_image = K::tiles_per_image(w, h);
-            emulate<K>(a, a.tiles_per_image * batch);
-        }
+        };
+        if (src_type == PIX_RGB8) run(RowFwd<P, G, PIX_RGB8>{});
+        else if (src_type == PIX_RGB32F) run(RowFwd<P, G, PIX_RGB32F>{});
+        else run(RowFwd<P, G, PIX_PLANE>{});
     }) ? 0 : -2;
 }
 

@@ -172,3 +172,4 @@ def test_segmented_source_lines(emul, so, line1, n, seg, chunks, ranks):
     assert emul.emul_fwd_segmented(line1, ptr(blocks), n, lines, seg, chunks, ranks, ptr(out)) == 0
     ref = dct1d_rows(so, a, 'fwd')
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
