@@ -35,6 +35,7 @@ struct FastArgs {
     void* dst;           // row_inv destination
     long long src_stride, plane_stride, dst_stride;  // per-image strides in pixels
     int tiles_per_image;
+    int total_tiles, tiles_per_cta;   // prefetching kernels: a CTA works through tiles_per_cta consecutive tiles
     float scale0, scalen;  // forward: factors for k == 0 / k > 0; inverse: scale0 = output scale
     const cplx* tw;        // stage twiddles of the plan, layout per stage [r-1][k]
     const cplx* t4;        // exp(-i*pi*k/(2N)), k < N
@@ -684,6 +685,88 @@ struct Line1Inv {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// forward row pass with asynchronous prefetch (RGB8 rows): a CTA works through `tiles_per_cta` consecutive
+// tiles; while the FFT of tile i runs, the raw bytes of tile i+1 stream into a staging buffer with
+// cp.async (LDGSTS, no registers, no scoreboard stall), so only the first tile of a CTA waits for HBM.
+// Shared memory: G line-pair buffers + G * 2 rows * 3N bytes of staging.
+// ------------------------------------------------------------------------------------------------
+SSW_HD void async_copy16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+    __builtin_memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+SSW_HD void async_commit_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+template <class P_, int G_>
+struct RowFwdPF {
+    using P = P_;
+    static_assert((3 * P_::N) % 16 == 0, "rows must be whole 16-byte chunks");
+    static constexpr int G = G_, SRC = PIX_RGB8, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
+    static constexpr int ROW_BYTES = 3 * P_::N;
+    static constexpr int FFT_BYTES = G_ * P_::PITCH * (int)sizeof(cplx);
+    static constexpr int SMEM = FFT_BYTES + G_ * 2 * ROW_BYTES;
+    static constexpr int MINB = 0;
+    static constexpr bool PREFETCH = true;
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)w; return ((h + 1) / 2 + G - 1) / G; }
+
+    // issue the copies of tile `tile` into the staging buffer (all threads of the CTA)
+    static SSW_HD void prefetch(const FastArgs& a, cplx* smem, int tile, int tid) {
+        constexpr int N = P::N, CH = ROW_BYTES / 16;
+        const int img = tile / a.tiles_per_image;
+        const int row0 = 2 * ((tile - img * a.tiles_per_image) * G);   // first of the 2G rows of the tile
+        const unsigned char* src = (const unsigned char*)a.src + 3 * (img * a.src_stride + (long long)row0 * N);
+        unsigned char* stage = (unsigned char*)smem + FFT_BYTES;
+        for (int e = tid; e < 2 * G * CH; e += THREADS) {
+            const int r = e / CH, c = e - r * CH;
+            if (row0 + r < a.h) async_copy16(stage + r * ROW_BYTES + 16 * c, src + (long long)r * ROW_BYTES + 16 * c);
+        }
+    }
+
+    template <int PH>
+    static SSW_HD void phase(const FastArgs& a, cplx* smem, int tile, int tid, Thread& th) {
+        constexpr int N = P::N, T = P::T;
+        const int g = tid / T, t = tid - g * T;
+        cplx* s = smem + g * P::PITCH;
+        const int img = tile / a.tiles_per_image;
+        const int ra = 2 * ((tile - img * a.tiles_per_image) * G + g), rb = ra + 1;
+        if constexpr (PH == 0) {
+            const bool ha = ra < a.h, hb = rb < a.h;
+            const unsigned* sa = (const unsigned*)((const unsigned char*)smem + FFT_BYTES + (2 * g) * ROW_BYTES);
+            const unsigned* sb = (const unsigned*)((const unsigned char*)sa + ROW_BYTES);
+#pragma unroll
+            for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
+                const int u = t + it * T;
+                if (u < N / 4) {
+                    float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
+                    unsigned b[12];
+                    if (ha) {
+                        unpack4(sa[3 * u], sa[3 * u + 1], sa[3 * u + 2], b);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ya[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+                    }
+                    if (hb) {
+                        unpack4(sb[3 * u], sb[3 * u + 1], sb[3 * u + 2], b);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) yb[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+                    }
+                    put4<P>(s, u, ya, yb);
+                }
+            }
+        } else {
+            RowFwd<P_, G_, PIX_RGB8>::template phase<PH>(a, smem, tile, tid, th);   // FFT stages + post pass are shared
+        }
+    }
+};
+
 #if defined(__CUDACC__)
 template <class K>
 constexpr int min_blocks() {
@@ -706,6 +789,28 @@ __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel(const
         K::template phase<p>(a, (cplx*)fast_smem, blockIdx.x, threadIdx.x, th);
         if constexpr (p + 1 < K::NPH) __syncthreads();
     });
+}
+
+// prefetching kernels: CTA b works through tiles [b*per, (b+1)*per)
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel_pf(const __grid_constant__ FastArgs a) {
+    extern __shared__ __align__(16) unsigned char fast_smem[];
+    typename K::Thread th;
+    int tile = blockIdx.x * a.tiles_per_cta;
+    const int end = min(tile + a.tiles_per_cta, a.total_tiles);
+    if (tile < end) K::prefetch(a, (cplx*)fast_smem, tile, threadIdx.x);
+    for (; tile < end; ++tile) {
+        async_commit_wait_all();
+        __syncthreads();                                   // staging of `tile` has landed for everybody
+        K::template phase<0>(a, (cplx*)fast_smem, tile, threadIdx.x, th);
+        __syncthreads();                                   // staging consumed
+        if (tile + 1 < end) K::prefetch(a, (cplx*)fast_smem, tile + 1, threadIdx.x);
+        static_for<K::NPH - 1>([&](auto ph) {
+            constexpr int p = decltype(ph)::value + 1;
+            K::template phase<p>(a, (cplx*)fast_smem, tile, threadIdx.x, th);
+            __syncthreads();
+        });
+    }
 }
 #endif
 

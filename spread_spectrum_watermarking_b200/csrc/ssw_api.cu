@@ -61,6 +61,8 @@ struct ssw_ctx {
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     int row_variant = 0;                   // SSW_ROW_VARIANT (tuning builds)
+    bool prefetch = false;                 // SSW_PREFETCH=1: cp.async-staged forward row pass (RowFwdPF)
+    int pf_tiles = 0;                      // SSW_PF_TILES: tiles per CTA of the prefetching kernels (0 = automatic)
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
     struct { bool active = false; int seg_shift = -1, chunk_shift = 0, ranks = 1, lines = 0; } seg;  // ssw_lines_forward_seg_dev
@@ -143,6 +145,8 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     if (const char* s = getenv("SSW_ROW_VARIANT")) c->row_variant = atoi(s);
+    if (const char* s = getenv("SSW_PREFETCH")) c->prefetch = atoi(s) != 0;
+    if (const char* s = getenv("SSW_PF_TILES")) c->pf_tiles = atoi(s);
     if (const char* s = getenv("SSW_TOPK_FULL_HIST")) c->topk_full_hist = atoi(s) != 0;
     if (const char* s = getenv("SSW_FORCE_LINE1")) c->force_line1 = atoi(s) != 0;
     *out = c.release();
@@ -386,6 +390,36 @@ static int launch_fast(ssw_ctx* c, const char* name, fast::FastArgs a, int w, in
     return SSW_OK;
 }
 
+// prefetching kernels (fast_kernel_pf): a CTA works through `per` consecutive tiles
+template <class K>
+static int launch_fast_pf(ssw_ctx* c, const char* name, fast::FastArgs a, int w, int h, int batch) {
+    CKS(fast_tables<typename K::P>(c, &a.tw, &a.t4));
+    a.tiles_per_image = K::tiles_per_image(w, h);
+    const long long tiles = (long long)a.tiles_per_image * batch;
+    if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
+    auto kernel = fast::fast_kernel_pf<K>;
+    const void* key = (const void*)kernel;
+    auto it = c->smem_attr.find(key);
+    if (it == c->smem_attr.end()) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K::THREADS, K::SMEM));
+        it = c->smem_attr.emplace(key, std::max(1, occ)).first;   // value: resident CTAs per SM
+    }
+    // enough tiles per CTA that the grid is about one resident wave, at most 8
+    const long long slots = (long long)it->second * c->sm_count;
+    long long per = c->pf_tiles > 0 ? c->pf_tiles : std::min<long long>(8, (tiles + slots - 1) / slots);
+    per = std::max<long long>(1, per);
+    a.total_tiles = (int)tiles;
+    a.tiles_per_cta = (int)per;
+    {
+        KScope ks(c, name);
+        kernel<<<(unsigned)((tiles + per - 1) / per), K::THREADS, K::SMEM, c->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
 static fast::FastArgs fast_args(int w, int h) {
     fast::FastArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -443,9 +477,19 @@ static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int 
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.scale0 = scale0; a.scalen = scalen;
         apply_seg(c, &a);
-        if (src_type == PIX_RGB8) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
-        else if (src_type == PIX_RGB32F) rc = launch_fast<fast::RowFwd<P, G, PIX_RGB32F>>(c, "fwd_rows_rgb32f", a, w, h, batch);
-        else rc = launch_fast<fast::RowFwd<P, G, PIX_PLANE>>(c, "fwd_rows_plane", a, w, h, batch);
+        if (src_type == PIX_RGB8) {
+            if constexpr ((3 * P::N) % 16 == 0) {
+                if (c->prefetch && aligned(d_src, 16)) {   // cp.async-staged rows, several tiles per CTA
+                    rc = launch_fast_pf<fast::RowFwdPF<P, G>>(c, "fwd_rows", a, w, h, batch);
+                    return;
+                }
+            }
+            rc = launch_fast<fast::RowFwd<P, G, PIX_RGB8>>(c, "fwd_rows", a, w, h, batch);
+        } else if (src_type == PIX_RGB32F) {
+            rc = launch_fast<fast::RowFwd<P, G, PIX_RGB32F>>(c, "fwd_rows_rgb32f", a, w, h, batch);
+        } else {
+            rc = launch_fast<fast::RowFwd<P, G, PIX_PLANE>>(c, "fwd_rows_plane", a, w, h, batch);
+        }
     });
     return rc;
 }

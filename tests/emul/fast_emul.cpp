@@ -4,6 +4,7 @@
 // __global__ wrapper runs phase p for all threads, __syncthreads(), phase p+1, ...  Here the same
 // phase functions are called for tid = 0..THREADS-1 in turn, with the per-thread states kept in an
 // array, which is an exact model of that execution.  Never linked into libssw.so; not a fallback.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -23,6 +24,28 @@ void emulate(const FastArgs& a, int ntiles) {
             constexpr int p = decltype(ph)::value;
             for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<p>(a, smem.data(), tile, tid, th[tid]);
         });
+    }
+}
+
+// prefetching kernels: same schedule as fast_kernel_pf (prefetch == immediate copy on the CPU)
+template <class K>
+void emulate_pf(FastArgs a, int ntiles, int per) {
+    std::vector<cplx> smem(K::SMEM / sizeof(cplx) + 8);
+    std::vector<typename K::Thread> th(K::THREADS);
+    a.total_tiles = ntiles; a.tiles_per_cta = per;
+    for (int cta = 0; cta * per < ntiles; ++cta) {
+        int tile = cta * per;
+        const int end = std::min(tile + per, ntiles);
+        for (int tid = 0; tid < K::THREADS; ++tid) K::prefetch(a, smem.data(), tile, tid);
+        for (; tile < end; ++tile) {
+            for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<0>(a, smem.data(), tile, tid, th[tid]);
+            if (tile + 1 < end)
+                for (int tid = 0; tid < K::THREADS; ++tid) K::prefetch(a, smem.data(), tile + 1, tid);
+            static_for<K::NPH - 1>([&](auto ph) {
+                constexpr int p = decltype(ph)::value + 1;
+                for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<p>(a, smem.data(), tile, tid, th[tid]);
+            });
+        }
     }
 }
 
@@ -196,6 +219,23 @@ int emul_fwd_segmented(int line1, const float* src, int n, int n_lines, int seg_
         using K = RowFwd<P, G, PIX_PLANE>;
         a.tiles_per_image = K::tiles_per_image(n, n_lines);
         emulate<K>(a, a.tiles_per_image);
+    }) ? 0 : -2;
+}
+
+// forward RGB8 row pass through the prefetching kernel, `per` tiles per CTA
+int emul_fast_row_fwd_pf(const void* src, int w, int h, int batch, float* plane, int per) {
+    return with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        if constexpr ((3 * P::N) % 16 == 0) {
+            constexpr int G = RowG<P>::value;
+            Tables<P> tb;
+            FastArgs a = base_args(w, h);
+            a.src = src; a.plane = plane;
+            a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+            using K = RowFwdPF<P, G>;
+            a.tiles_per_image = K::tiles_per_image(w, h);
+            emulate_pf<K>(a, a.tiles_per_image * batch, per);
+        }
     }) ? 0 : -2;
 }
 

@@ -173,3 +173,14 @@ def test_segmented_source_lines(emul, so, line1, n, seg, chunks, ranks):
     ref = dct1d_rows(so, a, 'fwd')
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
 
+
+
+@pytest.mark.parametrize('n,h,per', [(3840, 7, 2), (1920, 10, 3), (640, 9, 8), (2160, 4, 1)])
+def test_prefetching_row_kernel_is_bit_identical(emul, so, n, h, per):
+    """cp.async-staged rows (several tiles per CTA) give exactly the coefficients of the direct loader"""
+    rgb = so.synth_frame(n, h, seed=n + per, img=1)
+    rgb2 = np.concatenate([rgb, so.synth_frame(n, h, seed=n, img=2)])   # batch of 2 images
+    a, b = np.zeros((2 * h, n), np.float32), np.zeros((2 * h, n), np.float32)
+    assert emul.emul_fast_row_fwd(0, ptr(rgb2), n, h, 2, ptr(a), f32(1.0), f32(1.0)) == 0
+    assert emul.emul_fast_row_fwd_pf(ptr(rgb2), n, h, 2, ptr(b), per) == 0
+    assert (a == b).all()
