@@ -153,25 +153,45 @@ constexpr int kSimChunk = 32;   // elements staged per step
 
 // sum of squares of each extracted vector in the reference's sequential f32 order (the denominator of
 // every score of that vector; src/algorithm.rs:709 accumulates it inside the same loop)
+// Sequential f32 sum  acc = (((0 + v_0) + v_1) + ...)  of per-element products, by one warp: the products
+// (round-to-nearest multiplies, order independent) are formed lane-parallel -- all global loads of a 2048-
+// element block in flight at once -- and parked in shared memory; only the adds run in the reference's order,
+// one broadcast LDS (off the dependent path) + one FADD per element.  kind 0: x*m, kind 1: x*x.
+constexpr int kSeqBlock = 2048;
+
+__device__ __forceinline__ float seq_sum_products(const float* __restrict__ x, const float* __restrict__ m, unsigned n,
+                                                  int lane, int kind, float* __restrict__ prod /* [kSeqBlock] of this warp */) {
+    float acc = 0.f;
+    for (unsigned b0 = 0; b0 < n; b0 += kSeqBlock) {
+        const unsigned len = min((unsigned)kSeqBlock, n - b0);
+#pragma unroll 8
+        for (unsigned j = lane; j < len; j += 32) {
+            const float xv = __ldg(x + b0 + j);
+            prod[j] = kind == 0 ? __fmul_rn(xv, __ldg(m + b0 + j)) : __fmul_rn(xv, xv);
+        }
+        __syncwarp();
+        unsigned j = 0;
+        for (; j + 16 <= len; j += 16) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = prod[j + i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc = __fadd_rn(acc, v[i]);
+        }
+        for (; j < len; ++j) acc = __fadd_rn(acc, prod[j]);
+        __syncwarp();
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(128)
 similarity_den_kernel(const float* __restrict__ extracted, unsigned n, long long ext_stride,
                       unsigned n_ext, float* __restrict__ den) {
-    __shared__ float se[4][512];   // one warp per vector: coalesced staging, lane 0 walks it in order
+    __shared__ float prod[4][kSeqBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned e = blockIdx.x * 4 + warp;
     if (e >= n_ext) return;
-    const float* x = extracted + (long long)e * ext_stride;
-    float d = 0.f;
-    for (unsigned j0 = 0; j0 < n; j0 += 512) {
-        const unsigned len = min(512u, n - j0);
-        for (unsigned j = lane; j < len; j += 32) se[warp][j] = __ldg(x + j0 + j);
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll 8
-            for (unsigned j = 0; j < len; ++j) { const float v = se[warp][j]; d = __fadd_rn(d, __fmul_rn(v, v)); }
-        }
-        __syncwarp();
-    }
+    const float d = seq_sum_products(extracted + (long long)e * ext_stride, nullptr, n, lane, 1, prod[warp]);
     if (lane == 0) den[e] = d;
 }
 
@@ -220,36 +240,24 @@ similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned 
     if (m < n_marks) out[(long long)e * out_stride + m] = __fdiv_rn(nom, __fsqrt_rn(__ldg(den + e)));
 }
 
-// 1:1 form: extracted vector i against mark i (the fused extract pipeline).  One warp per pair stages
-// both vectors through shared memory with coalesced loads; lane 0 then walks them in the reference's
-// sequential order (bit-identical), the loads no longer sit on the dependent FADD chain.
-constexpr int kPairWarps = 4, kPairChunk = 512;
+// 1:1 form: extracted vector i against mark i (the fused extract pipeline).
+constexpr int kPairsPerCta = 2;   // two warps per pair: one walks the numerator chain, one the denominator chain
 
-__global__ void __launch_bounds__(kPairWarps * 32)
+__global__ void __launch_bounds__(kPairsPerCta * 64)
 similarity_pairs_kernel(const float* __restrict__ marks, const float* __restrict__ extracted, unsigned n,
                         long long stride, unsigned n_pairs, float* __restrict__ out) {
-    __shared__ float sm[kPairWarps][kPairChunk], se[kPairWarps][kPairChunk];
+    __shared__ float part[kPairsPerCta][2];
+    __shared__ float prod[kPairsPerCta * 2][kSeqBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned pair = blockIdx.x * kPairWarps + warp;
-    if (pair >= n_pairs) return;
-    const float* mk = marks + (long long)pair * stride;
-    const float* ex = extracted + (long long)pair * stride;
-    float nom = 0.f, den = 0.f;
-    for (unsigned j0 = 0; j0 < n; j0 += kPairChunk) {
-        const unsigned len = min((unsigned)kPairChunk, n - j0);
-        for (unsigned j = lane; j < len; j += 32) { sm[warp][j] = __ldg(mk + j0 + j); se[warp][j] = __ldg(ex + j0 + j); }
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll 8
-            for (unsigned j = 0; j < len; ++j) {
-                const float x = se[warp][j];
-                nom = __fadd_rn(nom, __fmul_rn(x, sm[warp][j]));
-                den = __fadd_rn(den, __fmul_rn(x, x));
-            }
-        }
-        __syncwarp();
+    const int slot = warp >> 1, kind = warp & 1;
+    const unsigned pair = blockIdx.x * kPairsPerCta + slot;
+    if (pair < n_pairs) {
+        const float v = seq_sum_products(extracted + (long long)pair * stride, marks + (long long)pair * stride, n, lane, kind,
+                                         prod[warp]);
+        if (lane == 0) part[slot][kind] = v;
     }
-    if (lane == 0) out[pair] = __fdiv_rn(nom, __fsqrt_rn(den));
+    __syncthreads();
+    if (pair < n_pairs && kind == 0 && lane == 0) out[pair] = __fdiv_rn(part[slot][0], __fsqrt_rn(part[slot][1]));
 }
 
 // ------------------------------------------------------------------------------------------------

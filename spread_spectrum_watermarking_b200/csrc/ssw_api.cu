@@ -55,6 +55,11 @@ struct ssw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // side stream: the (latency-bound) top-k of the base frame runs beside the forward transform of the
+    // derived frame in the fused extract pipeline
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_topk = true;              // SSW_OVERLAP_TOPK=0 keeps everything on one stream
     std::map<int, std::unique_ptr<DevPlan>> plans;
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
@@ -139,6 +144,10 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     uint64_t thr = UINT64_MAX;
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     CK(cudaHostAlloc((void**)&c->h_flag, 64, cudaHostAllocDefault));
+    CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if (const char* s = getenv("SSW_OVERLAP_TOPK")) c->overlap_topk = atoi(s) != 0;
     if (const char* s = getenv("SSW_ROW_PAIRS")) c->row_pairs = atoi(s);
     if (const char* s = getenv("SSW_COL_PAIRS")) c->col_pairs = atoi(s);
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
@@ -172,6 +181,9 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     topk_scratch_free(c);
     c->general.release();
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1213,7 +1225,7 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
         if (n_marks > 0x7FFFFFFFull || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
         {
             KScope ks(c, "similarity_pairs");
-            similarity_pairs_kernel<<<(unsigned)((n_marks + kPairWarps - 1) / kPairWarps), kPairWarps * 32, 0, c->stream>>>(
+            similarity_pairs_kernel<<<(unsigned)((n_marks + kPairsPerCta - 1) / kPairsPerCta), kPairsPerCta * 64, 0, c->stream>>>(
                 d_bank, d_ext, (unsigned)n, (long long)n, (unsigned)n_marks, d_out);
         }
         CK(cudaGetLastError());
@@ -1414,8 +1426,21 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         float* pb = d_planes;
         float* pd = d_planes + (size_t)cb * np;
         rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
-        if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
-        if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
+        if (rc == SSW_OK && c->overlap_topk) {
+            // fork: ordering of the base coefficients on the side stream, derived forward transform on the main one
+            cudaStream_t main_stream = c->stream;
+            CK(cudaEventRecord(c->ev_fork, main_stream));
+            CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+            c->stream = c->aux;
+            rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
+            c->stream = main_stream;
+            CK(cudaEventRecord(c->ev_join, c->aux));
+            if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
+            CK(cudaStreamWaitEvent(main_stream, c->ev_join, 0));   // join (also on error paths: keeps the streams ordered)
+        } else {
+            if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
+            if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
+        }
         if (rc == SSW_OK) {
             {
                 KScope ks(c, "extract_gather");
