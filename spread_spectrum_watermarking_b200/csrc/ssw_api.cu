@@ -59,6 +59,9 @@ struct ssw_ctx {
     // derived frame in the fused extract pipeline
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // copy streams + events of the pipelined host-buffer batch entry points
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> pipe_events;
     bool overlap_topk = true;              // SSW_OVERLAP_TOPK=0 keeps everything on one stream
     std::map<int, std::unique_ptr<DevPlan>> plans;
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
@@ -145,6 +148,8 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     CK(cudaHostAlloc((void**)&c->h_flag, 64, cudaHostAllocDefault));
     CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* s = getenv("SSW_OVERLAP_TOPK")) c->overlap_topk = atoi(s) != 0;
@@ -182,6 +187,9 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     c->general.release();
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+    if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
+    if (c->copy_out) { cudaStreamSynchronize(c->copy_out); cudaStreamDestroy(c->copy_out); }
+    for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1457,31 +1465,71 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
     return rc;
 }
 
+// host-buffer entry points: the batch is cut into chunks of >= ~32 MB; chunk i+1 is uploaded (copy-in stream) while
+// chunk i is transformed (context stream) and chunk i-1 is downloaded (copy-out stream) -- PCIe is full duplex, so a
+// batch approaches the one-directional line rate instead of the sum of both directions.
+static int pipe_event(ssw_ctx* c, size_t i, cudaEvent_t* ev) {
+    while (c->pipe_events.size() <= i) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipe_events.push_back(e);
+    }
+    *ev = c->pipe_events[i];
+    return SSW_OK;
+}
+
+static uint32_t pipe_chunk_frames(size_t frame_bytes, uint32_t batch) {
+    if (batch <= 1) return std::max(1u, batch);
+    const size_t target = 32u << 20;
+    uint32_t cb = (uint32_t)std::max<size_t>(1, target / std::max<size_t>(1, frame_bytes));
+    cb = std::min(cb, (batch + 1) / 2);   // at least two chunks so that the directions overlap
+    return std::max(1u, cb);
+}
+
 extern "C" int ssw_embed_batch_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t batch,
                                     const ssw_config* cfg, const float* marks, size_t n, uint8_t* out_rgb) {
     if (!c || !rgb || !out_rgb || (n && !marks)) return fail(SSW_ERR_INVALID, "NULL argument");
     CKS(check_dims(w, h));
     if (batch == 0) return SSW_OK;
     CKS(ctx_bind(c));
-    const size_t bytes = (size_t)w * h * 3 * batch;
+    const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch;
     uint8_t *d_in = nullptr, *d_out = nullptr;
     float* d_marks = nullptr;
     CK(cudaMallocAsync(&d_in, bytes, c->stream));
     CK(cudaMallocAsync(&d_out, bytes, c->stream));
     CK(cudaMallocAsync(&d_marks, std::max<size_t>(n * batch, 1) * sizeof(float), c->stream));
-    CK(cudaMemcpyAsync(d_in, rgb, bytes, cudaMemcpyHostToDevice, c->stream));
     if (n) CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const uint32_t cb = pipe_chunk_frames(fbytes, batch);
+    const uint32_t nchunks = (batch + cb - 1) / cb;
     // first attempt: threshold bin from the low-frequency block; a candidate overflow (noise-like
     // spectrum) is repaired by one more run with the full-plane histogram
     int rc = SSW_OK;
     unsigned ov = 0;
     const bool saved = c->topk_full_hist;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        rc = ssw_embed_batch_rgb8_dev(c, d_in, w, h, batch, cfg, d_marks, n, d_out);
-        if (rc == SSW_OK) {
-            cudaError_t e = cudaMemcpyAsync(out_rgb, d_out, bytes, cudaMemcpyDeviceToHost, c->stream);
-            if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
+        cudaEvent_t e0;
+        CKS(pipe_event(c, 0, &e0));
+        CK(cudaEventRecord(e0, c->stream));                 // allocations (and a previous attempt) are ordered before the copies
+        CK(cudaStreamWaitEvent(c->copy_in, e0, 0));
+        CK(cudaStreamWaitEvent(c->copy_out, e0, 0));
+        for (uint32_t ci = 0; ci < nchunks && rc == SSW_OK; ++ci) {
+            const uint32_t f0 = ci * cb, nf = std::min(cb, batch - f0);
+            cudaEvent_t e_in, e_cmp;
+            CKS(pipe_event(c, 1 + 2 * (size_t)ci, &e_in));
+            CKS(pipe_event(c, 2 + 2 * (size_t)ci, &e_cmp));
+            CK(cudaMemcpyAsync(d_in + f0 * fbytes, rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+            CK(cudaEventRecord(e_in, c->copy_in));
+            CK(cudaStreamWaitEvent(c->stream, e_in, 0));
+            rc = ssw_embed_batch_rgb8_dev(c, d_in + f0 * fbytes, w, h, nf, cfg, d_marks + (size_t)f0 * n, n, d_out + f0 * fbytes);
+            if (rc != SSW_OK) break;
+            CK(cudaEventRecord(e_cmp, c->stream));
+            CK(cudaStreamWaitEvent(c->copy_out, e_cmp, 0));
+            CK(cudaMemcpyAsync(out_rgb + f0 * fbytes, d_out + f0 * fbytes, nf * fbytes, cudaMemcpyDeviceToHost, c->copy_out));
         }
+        CK(cudaEventRecord(e0, c->copy_out));               // join the copy streams back into the context stream
+        CK(cudaStreamWaitEvent(c->stream, e0, 0));
+        CK(cudaEventRecord(e0, c->copy_in));
+        CK(cudaStreamWaitEvent(c->stream, e0, 0));
         int rs = take_overflow(c, &ov);  // synchronises
         if (rc == SSW_OK) rc = rs;
         if (rc != SSW_OK || !ov || c->topk_full_hist) break;
@@ -1501,29 +1549,45 @@ extern "C" int ssw_extract_batch_rgb8(ssw_ctx* c, const uint8_t* base_rgb, const
     CKS(check_dims(w, h));
     if (batch == 0 || n == 0) return SSW_OK;
     CKS(ctx_bind(c));
-    const size_t bytes = (size_t)w * h * 3 * batch;
+    const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch;
     uint8_t *d_b = nullptr, *d_d = nullptr;
     float *d_ext = nullptr, *d_marks = nullptr, *d_sim = nullptr;
     CK(cudaMallocAsync(&d_b, bytes, c->stream));
     CK(cudaMallocAsync(&d_d, bytes, c->stream));
     CK(cudaMallocAsync(&d_ext, n * batch * sizeof(float), c->stream));
-    CK(cudaMemcpyAsync(d_b, base_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_d, derived_rgb, bytes, cudaMemcpyHostToDevice, c->stream));
     if (sim && marks) {
         CK(cudaMallocAsync(&d_marks, n * batch * sizeof(float), c->stream));
         CK(cudaMallocAsync(&d_sim, batch * sizeof(float), c->stream));
         CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
+    const uint32_t cb = pipe_chunk_frames(2 * fbytes, batch);
+    const uint32_t nchunks = (batch + cb - 1) / cb;
     int rc = SSW_OK;
     unsigned ov = 0;
     const bool saved = c->topk_full_hist;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        rc = ssw_extract_batch_rgb8_dev(c, d_b, d_d, w, h, batch, cfg, n, d_ext, d_marks, d_sim);
+        cudaEvent_t e0;
+        CKS(pipe_event(c, 0, &e0));
+        CK(cudaEventRecord(e0, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_in, e0, 0));
+        for (uint32_t ci = 0; ci < nchunks && rc == SSW_OK; ++ci) {
+            const uint32_t f0 = ci * cb, nf = std::min(cb, batch - f0);
+            cudaEvent_t e_in;
+            CKS(pipe_event(c, 1 + (size_t)ci, &e_in));
+            CK(cudaMemcpyAsync(d_b + f0 * fbytes, base_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+            CK(cudaMemcpyAsync(d_d + f0 * fbytes, derived_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+            CK(cudaEventRecord(e_in, c->copy_in));
+            CK(cudaStreamWaitEvent(c->stream, e_in, 0));
+            rc = ssw_extract_batch_rgb8_dev(c, d_b + f0 * fbytes, d_d + f0 * fbytes, w, h, nf, cfg, n, d_ext + (size_t)f0 * n,
+                                            d_marks ? d_marks + (size_t)f0 * n : nullptr, d_sim ? d_sim + f0 : nullptr);
+        }
         if (rc == SSW_OK) {
             cudaError_t e = cudaMemcpyAsync(extracted, d_ext, n * batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
             if (e == cudaSuccess && d_sim) e = cudaMemcpyAsync(sim, d_sim, batch * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
             if (e != cudaSuccess) rc = fail(SSW_ERR_CUDA, cudaGetErrorString(e));
         }
+        CK(cudaEventRecord(e0, c->copy_in));
+        CK(cudaStreamWaitEvent(c->stream, e0, 0));
         int rs = take_overflow(c, &ov);  // synchronises
         if (rc == SSW_OK) rc = rs;
         if (rc != SSW_OK || !ov || c->topk_full_hist) break;

@@ -162,6 +162,49 @@ def test_attack_resize(wm, ctx, golden):
     assert s > 9.5 and abs(s - 9.87) < 0.3, s
 
 
+def test_attack_jpeg_recompression(wm, ctx, golden):
+    """robustness regression beyond the reference's two attack tests: the mark survives a
+    quality-75 JPEG round trip of the watermarked image and an unrelated mark stays below the 6-sigma threshold"""
+    import io
+    from PIL import Image
+    cat, m = golden['cat'], golden['marks']['seed_2']
+    marked = wm.Writer.new(cat, ctx=ctx).mark_rgb8([m])
+    buf = io.BytesIO()
+    Image.fromarray(marked).save(buf, format='JPEG', quality=75)
+    attacked = np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert('RGB'))
+    e = wm.Reader.base(cat, ctx=ctx).extract(wm.Reader.derived(attacked, ctx=ctx), 1000)
+    t = wm.Tester.new(e, ctx=ctx)
+    assert t.similarity(m).exceeds_sigma(6.0)
+    assert not t.similarity(golden['marks']['seed_baaaaaad']).exceeds_sigma(6.0)
+
+
+def test_host_batch_pipeline_matches_device_path(wm, ctx, so):
+    """the chunked, three-stream host-buffer entry points (upload / transform / download overlapped) give the bytes
+    of the device-resident pipeline for a batch that spans several chunks"""
+    import torch
+    w, h, B, n = 1920, 1080, 12, 500
+    frames = _synth_dev(wm, ctx, w, h, 3, 40, B)
+    rng = np.random.default_rng(12)
+    mk_h = rng.standard_normal((B, n)).astype(np.float32)
+    mk = torch.from_numpy(mk_h).cuda()
+    out = torch.empty_like(frames)
+    cfg = wm._lib.ssw_config(2, 0.1, 0)
+    torch.cuda.synchronize()
+    wm._lib.check(wm.lib.ssw_embed_batch_rgb8_dev(ctx.handle, frames.data_ptr(), w, h, B, ctypes.byref(cfg), mk.data_ptr(), n, out.data_ptr()))
+    ctx.synchronize()
+    fh = frames.cpu().numpy()
+    oh = np.zeros_like(fh)
+    wm._lib.check(wm.lib.ssw_embed_batch_rgb8(ctx.handle, fh.ctypes.data, w, h, B, ctypes.byref(cfg), mk_h.ctypes.data, n, oh.ctypes.data))
+    assert (oh == out.cpu().numpy()).all()
+    eh = np.zeros((B, n), np.float32)
+    sh = np.zeros(B, np.float32)
+    wm._lib.check(wm.lib.ssw_extract_batch_rgb8(ctx.handle, fh.ctypes.data, oh.ctypes.data, w, h, B, ctypes.byref(cfg), n,
+                                                eh.ctypes.data, mk_h.ctypes.data, sh.ctypes.data))
+    assert (sh > 12).all() and np.abs(eh - mk_h).mean() < 0.3
+    for i in (0, B - 1):
+        assert float(sh[i]) == float(so.similarity(eh[i], mk_h[i]))
+
+
 def test_bank_from_storage_file(wm, ctx, so, tmp_path):
     """marks written in the reference CLI's JSON form are scored from a device-resident bank"""
     from spread_spectrum_watermarking_b200 import storage
