@@ -840,6 +840,13 @@ using Plan640 = Plan<640, 64, 5, 8, 16>;
 using Plan3840b = Plan<3840, 480, 5, 8, 8, 12>;   // small radices, more threads per line pair
 using Plan3840c = Plan<3840, 384, 15, 8, 8, 4>;
 #endif
+// other common video formats: 720p, 1440p, 8K in both orientations
+using Plan1280 = Plan<1280, 96, 5, 16, 16>;
+using Plan720 = Plan<720, 96, 5, 9, 16>;
+using Plan2560 = Plan<2560, 320, 5, 8, 8, 8>;
+using Plan1440 = Plan<1440, 160, 9, 10, 16>;
+using Plan7680 = Plan<7680, 512, 15, 16, 16, 2>;
+using Plan4320 = Plan<4320, 384, 15, 12, 12, 2>;
 // powers of two (first radix even -> padded layout)
 using Plan1024 = Plan<1024, 64, 16, 16, 4>;
 using Plan2048 = Plan<2048, 128, 16, 16, 8>;

@@ -24,6 +24,12 @@ inline bool with_plan(int n, F&& f) {
         case 1920: f(Plan1920{}); return true;
         case 1080: f(Plan1080{}); return true;
         case 640: f(Plan640{}); return true;
+        case 1280: f(Plan1280{}); return true;
+        case 720: f(Plan720{}); return true;
+        case 2560: f(Plan2560{}); return true;
+        case 1440: f(Plan1440{}); return true;
+        case 7680: f(Plan7680{}); return true;
+        case 4320: f(Plan4320{}); return true;
         case 1024: f(Plan1024{}); return true;
         case 2048: f(Plan2048{}); return true;
         case 4096: f(Plan4096{}); return true;

@@ -8,7 +8,7 @@ import pytest
 
 from conftest import ptr
 
-FAST = [3840, 2160, 1920, 1080, 640, 1024, 2048, 4096, 8192, 16384]
+FAST = [3840, 2160, 1920, 1080, 640, 1280, 720, 2560, 1440, 7680, 4320, 1024, 2048, 4096, 8192, 16384]
 f32 = ctypes.c_float
 
 

@@ -419,7 +419,8 @@ def test_embed_is_idempotent_on_zero_mark_and_deterministic(wm, ctx, so):
 
 # ---------------------------------------------------------------------------- fast path vs generic kernels
 @pytest.mark.parametrize('w,h', [(1920, 1080), (3840, 2160), (640, 1080), (1080, 640), (2160, 3840), (1920, 37), (1000, 1080),
-                                 (1024, 2048), (4096, 64), (64, 4096), (8192, 32), (32, 8192), (16384, 8), (2048, 1024)])
+                                 (1024, 2048), (4096, 64), (64, 4096), (8192, 32), (32, 8192), (16384, 8), (2048, 1024),
+                                 (1280, 720), (720, 1280), (2560, 1440), (1440, 2560), (7680, 96), (96, 7680), (4320, 64), (64, 4320)])
 def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
     """the compile-time planned kernels (dct_fast.cuh) against the generic line kernels on the same
     frame: coefficients agree to FP32 rounding, and both reproduce the pixels within 1 LSB"""
