@@ -218,6 +218,10 @@ int ssw_lines_inverse_dev(ssw_ctx* ctx, float* plane_dev, uint32_t n, uint32_t n
 /* dst[b][c][r] = src[b][r][c]: batched f32 transpose (packs / unpacks the all-to-all blocks) */
 int ssw_transpose_dev(ssw_ctx* ctx, const float* src_dev, uint32_t rows, uint32_t cols, int64_t src_ld, int64_t src_bstride,
                       float* dst_dev, int64_t dst_ld, int64_t dst_bstride, uint32_t batch);
+/* the same with the coefficient lines held as all-to-all blocks [chunks][ranks][n_lines][seg_len], read in place */
+int ssw_lines_inverse_seg_dev(ssw_ctx* ctx, const float* src_dev, uint32_t n, uint32_t n_lines, uint32_t seg_len,
+                              uint32_t chunks, uint32_t ranks, float scale, int dst_type, void* dst_dev, int pix_type,
+                              const void* pixels_dev);
 /* distributed ordered top-k (obtain_indices_by_function, src/algorithm.rs:200-221): local bound -> [max over
  * ranks] -> local candidates -> [all-gather] -> merge */
 int ssw_shard_topk_bin_dev(ssw_ctx* ctx, const float* plane_dev, const ssw_shard* sh, int ordering, size_t k, uint32_t* bin_dev);

@@ -107,6 +107,7 @@ SIGNATURES = {
     'ssw_stage_inverse_rgb8_dev': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _p]),
     'ssw_lines_forward_dev': (c_int, [_p, c_int, _p, c_uint32, c_uint32, _p]),
     'ssw_lines_forward_seg_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, _p]),
+    'ssw_lines_inverse_seg_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, c_uint32, c_uint32, c_float, c_int, _p, c_int, _p]),
     'ssw_lines_inverse_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_float, c_int, _p, c_int, _p]),
     'ssw_transpose_dev': (c_int, [_p, _p, c_uint32, c_uint32, ctypes.c_int64, ctypes.c_int64, _p, ctypes.c_int64,
                                   ctypes.c_int64, c_uint32]),

@@ -436,11 +436,18 @@ struct RowInv {
         if constexpr (PH == 0) {
             const float* ia = a.plane + img * a.plane_stride + (long long)ra * N;
             const float* ib = ia + N;
+            const bool seg = a.seg_shift >= 0;   // coefficient lines held as all-to-all blocks (sharded frames)
 #pragma unroll 4
             for (int k = t; k <= N / 2; k += T) {
                 const int kr = k ? N - k : 0;
-                const float pa = ha ? ia[k] : 0.f, pb = hb ? ib[k] : 0.f;
-                const float qa = (k && ha) ? ia[kr] : 0.f, qb = (k && hb) ? ib[kr] : 0.f;
+                float pa = 0.f, pb = 0.f, qa = 0.f, qb = 0.f;
+                if (!seg) {
+                    pa = ha ? ia[k] : 0.f; pb = hb ? ib[k] : 0.f;
+                    qa = (k && ha) ? ia[kr] : 0.f; qb = (k && hb) ? ib[kr] : 0.f;
+                } else {
+                    if (ha) { pa = a.plane[seg_index(a, ra, k)]; if (k) qa = a.plane[seg_index(a, ra, kr)]; }
+                    if (hb) { pb = a.plane[seg_index(a, rb, k)]; if (k) qb = a.plane[seg_index(a, rb, kr)]; }
+                }
                 cplx zk, zr;
                 dct3_pre(pa, pb, qa, qb, SSW_LDG(&a.t4[k]), zk, zr);
                 s[P::idx(k)] = zk;
@@ -646,14 +653,16 @@ struct Line1Inv {
         const int row = tile - img * a.tiles_per_image;
         if constexpr (PH == 0) {
             const float* x = a.plane + img * a.plane_stride + (long long)row * N;
+            const bool seg = a.seg_shift >= 0;   // coefficient line held as all-to-all blocks (sharded frames)
+            auto X = [&](int j) -> float { return seg ? a.plane[seg_index(a, row, j)] : x[j]; };
 #pragma unroll 2
             for (int k = t; k <= M / 2; k += T) {
                 if (k == 0) {
-                    const float v0 = 0.5f * x[0], vm = 0.70710678118654752440f * x[M];
+                    const float v0 = 0.5f * X(0), vm = 0.70710678118654752440f * X(M);
                     s[P::idx(0)] = mk(0.5f * (v0 + vm), -0.5f * (v0 - vm));  // conj(A_0)
                     continue;
                 }
-                const float xk = x[k], xmk = x[M - k], xpk = x[M + k], xnk = x[N - k];
+                const float xk = X(k), xmk = X(M - k), xpk = X(M + k), xnk = X(N - k);
                 const cplx tk = SSW_LDG(&a.t4[k]), tm = SSW_LDG(&a.t4[M - k]);
                 const cplx tkM = mul_mi(cconj(tm));   // t_{M+k} = -i conj(t_{M-k})
                 const cplx tnk = mul_mi(cconj(tk));   // t_{N-k} = -i conj(t_k)

@@ -570,6 +570,7 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
         constexpr int G = fast::RowG<P>::value;
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
+        apply_seg(c, &a);
         if (dst_type == PIX_PLANE) rc = launch_fast<fast::RowInv<P, G, PIX_PLANE, PIX_PLANE>>(c, "inv_rows_plane", a, w, h, batch);
         else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
         else if (dst_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB32F>>(c, "inv_rows_src32f", a, w, h, batch);
@@ -611,6 +612,7 @@ static int line1_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d
         using P = decltype(p);
         fast::FastArgs a = fast_args(w, h);
         a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
+        apply_seg(c, &a);
         if (rgb8) rc = launch_fast<fast::Line1Inv<P, PIX_RGB8, PIX_RGB8>, true>(c, "inv_line1", a, w, h, batch);
         else rc = launch_fast<fast::Line1Inv<P, PIX_PLANE, PIX_PLANE>, true>(c, "inv_line1_plane", a, w, h, batch);
     });
@@ -684,10 +686,11 @@ static int run_rows_inverse(ssw_ctx* c, float* d_plane, int src_type, const void
     }
     CKS(fast_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
     if (done) return SSW_OK;
-    if (w > 16384) {
+    if (w > 16384 || c->seg.active) {
         CKS(line1_row_inv(c, d_plane, src_type, d_src, w, h, batch, dst_type, d_dst, out_scale, &done));
         if (done) return SSW_OK;
     }
+    if (c->seg.active) return fail(SSW_ERR_UNSUPPORTED, "segmented source lines need a planned line length");
     const DevPlan* pw;
     CKS(get_plan(c, w, &pw));
     Tiling tr;
@@ -1701,6 +1704,30 @@ extern "C" int ssw_lines_forward_seg_dev(ssw_ctx* c, const float* src, uint32_t 
     CKS(ctx_bind(c));
     c->seg.active = true; c->seg.seg_shift = ss; c->seg.chunk_shift = cs; c->seg.ranks = (int)ranks; c->seg.lines = (int)n_lines;
     const int rc = run_rows_forward(c, PIX_PLANE, src, (int)n, (int)n_lines, 1, plane, 1.f, 1.f);
+    c->seg.active = false;
+    return rc;
+}
+
+// inverse counterpart: the coefficient lines are all-to-all blocks [chunks][ranks][n_lines][seg_len], read in place
+extern "C" int ssw_lines_inverse_seg_dev(ssw_ctx* c, const float* src, uint32_t n, uint32_t n_lines, uint32_t seg_len,
+                                         uint32_t chunks, uint32_t ranks, float scale, int dst_type, void* dst, int pix_type,
+                                         const void* pixels) {
+    if (!c || !src || !dst) return fail(SSW_ERR_INVALID, "NULL argument");
+    if (dst_type != PIX_PLANE && !pixels) return fail(SSW_ERR_INVALID, "pixel output needs the original pixels");
+    CKS(check_dims(n, n_lines));
+    if (seg_len == 0 || chunks == 0 || ranks == 0 || (uint64_t)seg_len * chunks * ranks != n)
+        return fail(SSW_ERR_INVALID, "segments do not tile the line");
+    int ss = 0, cs = 0;
+    while ((1u << ss) < seg_len) ++ss;
+    while ((1u << cs) < chunks) ++cs;
+    if ((1u << ss) != seg_len || (1u << cs) != chunks || (const void*)src == dst)
+        return fail(SSW_ERR_UNSUPPORTED, "segmented source lines: seg_len and chunks must be powers of two, out of place");
+    if (!fast::has_plan((int)n) && !fast::has_line1_plan((int)n))
+        return fail(SSW_ERR_UNSUPPORTED, "segmented source lines need a planned line length");
+    CKS(ctx_bind(c));
+    c->seg.active = true; c->seg.seg_shift = ss; c->seg.chunk_shift = cs; c->seg.ranks = (int)ranks; c->seg.lines = (int)n_lines;
+    const int rc = run_rows_inverse(c, const_cast<float*>(src), dst_type == PIX_PLANE ? PIX_PLANE : pix_type, pixels, (int)n,
+                                    (int)n_lines, 1, dst_type, dst, scale);
     c->seg.active = false;
     return rc;
 }

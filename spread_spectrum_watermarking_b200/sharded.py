@@ -165,6 +165,19 @@ class CudaOps:
         t = self.interleave_blocks(recv)
         return self.lines_forward(t, n, lines, PIX_PLANE, out=t)
 
+    def lines_inverse_segmented(self, recv, n, scale, dst, pixels):
+        """DCT-III + colour of the lines held as all-to-all blocks [C][G][lines][seg] -> RGB8 rows `dst`"""
+        c, g, lines, seg = recv.shape
+        if c * g > 1:
+            rc = lib.ssw_lines_inverse_seg_dev(self.ctx.handle, recv.data_ptr(), n, lines, seg, c, g, ctypes.c_float(scale),
+                                               PIX_RGB8, dst.data_ptr(), PIX_RGB8, pixels.data_ptr())
+            if rc == _lib.SSW_OK:
+                return dst
+            if rc != _lib.SSW_ERR_UNSUPPORTED:
+                check(rc)
+        a = self.interleave_blocks(recv)
+        return self.lines_inverse(a, n, lines, scale, PIX_RGB8, dst, PIX_RGB8, pixels)
+
     def topk_bin(self, plane, shard, ordering, k):
         b = self.empty((1,), torch.int32)
         check(lib.ssw_shard_topk_bin_dev(self.ctx.handle, plane.data_ptr(), ctypes.byref(shard), ordering, k, b.data_ptr()))
@@ -240,11 +253,15 @@ class ShardedFrame:
             cand, cnt = ops.topk_collect(self.coeff, self.shard, ordering, b)
             lists, counts = _all_gather(cand, self.group), _all_gather(cnt, self.group).reshape(-1).contiguous()
             idx, overflow = ops.topk_merge(lists, counts, k)
-            overflowed = int(overflow.item())
-        if overflowed:
+        self._overflow = overflow     # checked once per step (check_overflow): no host round trip on the critical path
+        return idx
+
+    def check_overflow(self):
+        ov = getattr(self, '_overflow', None)
+        self._overflow = None
+        if ov is not None and int(ov.item()):
             raise SswError(_lib.SSW_ERR_UNSUPPORTED, 'sharded top-k: candidate overflow (flat spectrum); '
                            'the low-frequency bound was too loose for this frame')
-        return idx
 
     def inverse_rgb8(self):
         """DCT-III of the (possibly modified) coefficients back to this rank's RGB8 rows; consumes them"""
@@ -264,9 +281,8 @@ class ShardedFrame:
             for work, _keep in pending:
                 if work is not None:
                     work.wait()
-            a = ops.interleave_blocks(recv)                                          # [hb][W]
-            out = ops.empty((p.hb, p.width, 3), torch.uint8)
-            ops.lines_inverse(a, p.width, p.hb, 4.0 / float(p.width * p.height), PIX_RGB8, out, PIX_RGB8, self.rgb_rows)
+            out = ops.empty((p.hb, p.width, 3), torch.uint8)                         # rows: read the blocks in place
+            ops.lines_inverse_segmented(recv, p.width, 4.0 / float(p.width * p.height), out, self.rgb_rows)
         self.coeff = None
         return out
 
@@ -293,7 +309,9 @@ class ShardedWriter:
             self.ops.embed(self.frame.coeff, self.frame.shard, self.indices, m, self.cfg)
 
     def result_rgb8(self):
-        return self.frame.inverse_rgb8()
+        out = self.frame.inverse_rgb8()
+        self.frame.check_overflow()
+        return out
 
     def mark_rgb8(self, marks):
         self.embed(marks)
@@ -317,4 +335,6 @@ class ShardedReader:
         idx = self.base.ordered_indices(n, self.cfg.ordering)
         with _scope(self.ops):
             part = self.ops.extract(self.base.coeff, derived.coeff, self.base.shard, idx, n, self.cfg)
-            return _all_reduce(part, dist.ReduceOp.SUM, self.group)   # every index has exactly one owner
+            out = _all_reduce(part, dist.ReduceOp.SUM, self.group)   # every index has exactly one owner
+        self.base.check_overflow()
+        return out

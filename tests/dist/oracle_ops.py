@@ -53,6 +53,10 @@ class OracleOps:
         t = self.interleave_blocks(recv)
         return self.lines_forward(t, n, t.shape[0], 2, out=t)
 
+    def lines_inverse_segmented(self, recv, n, scale, dst, pixels):
+        a = self.interleave_blocks(recv)
+        return self.lines_inverse(a, n, a.shape[0], scale, 0, dst, 0, pixels)
+
     @staticmethod
     def _keys(plane, shard, ordering):
         ncols, h = plane.shape

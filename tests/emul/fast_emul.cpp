@@ -239,6 +239,45 @@ int emul_fast_row_fwd_pf(const void* src, int w, int h, int batch, float* plane,
     }) ? 0 : -2;
 }
 
+// inverse pass over SEGMENTED coefficient lines -> contiguous f32 lines `out` (scale applied)
+int emul_inv_segmented(int line1, const float* src, int n, int n_lines, int seg_len, int chunks, int ranks, float* out, float scale) {
+    int seg_shift = 0, chunk_shift = 0;
+    while ((1 << seg_shift) < seg_len) ++seg_shift;
+    while ((1 << chunk_shift) < chunks) ++chunk_shift;
+    if ((1 << seg_shift) != seg_len || (1 << chunk_shift) != chunks || seg_len * chunks * ranks != n) return -3;
+    auto fill = [&](FastArgs& a) {
+        a.plane = const_cast<float*>(src); a.dst = out; a.scale0 = scale;
+        a.seg_shift = seg_shift; a.chunk_shift = chunk_shift; a.seg_ranks = ranks; a.seg_lines = n_lines;
+    };
+    if (line1) {
+        return with_line1_plan(n, [&](auto p) {
+            using P = decltype(p);
+            Tables<P> tb;
+            std::vector<float> t4(2 * (size_t)n);
+            for (int j = 0; j < n; ++j) {
+                const double b = -M_PI * (double)j / (2.0 * (double)n);
+                t4[2 * j] = (float)std::cos(b); t4[2 * j + 1] = (float)std::sin(b);
+            }
+            FastArgs a = base_args(n, n_lines);
+            fill(a);
+            a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)t4.data();
+            a.tiles_per_image = n_lines;
+            emulate<Line1Inv<P, PIX_PLANE, PIX_PLANE>>(a, n_lines);
+        }) ? 0 : -2;
+    }
+    return with_plan(n, [&](auto p) {
+        using P = decltype(p);
+        constexpr int G = RowG<P>::value;
+        Tables<P> tb;
+        FastArgs a = base_args(n, n_lines);
+        fill(a);
+        a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+        using K = RowInv<P, G, PIX_PLANE, PIX_PLANE>;
+        a.tiles_per_image = K::tiles_per_image(n, n_lines);
+        emulate<K>(a, a.tiles_per_image);
+    }) ? 0 : -2;
+}
+
 // exactness of the division-free u8 -> [0,1] conversion: returns the number of mismatching inputs
 int emul_fast_u8_unit_mismatches(void) {
     int bad = 0;

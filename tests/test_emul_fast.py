@@ -172,6 +172,11 @@ def test_segmented_source_lines(emul, so, line1, n, seg, chunks, ranks):
     assert emul.emul_fwd_segmented(line1, ptr(blocks), n, lines, seg, chunks, ranks, ptr(out)) == 0
     ref = dct1d_rows(so, a, 'fwd')
     assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+    # inverse: the same block layout holds coefficient lines; result = 0.25*dct3 * scale
+    back = np.zeros_like(a)
+    assert emul.emul_inv_segmented(line1, ptr(blocks), n, lines, seg, chunks, ranks, ptr(back), f32(2.0 / n)) == 0
+    refi = dct1d_rows(so, a, 'inv') * np.float32(2.0 / n)
+    assert np.abs(back - refi).max() <= 3e-6 * max(np.abs(refi).max(), 1e-30)
 
 
 
