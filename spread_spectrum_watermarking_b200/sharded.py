@@ -259,7 +259,11 @@ class ShardedFrame:
     def check_overflow(self):
         ov = getattr(self, '_overflow', None)
         self._overflow = None
-        if ov is not None and int(ov.item()):
+        if ov is None:
+            return
+        with _scope(self.ops):          # read on the stream that wrote it
+            overflowed = int(ov.item())
+        if overflowed:
             raise SswError(_lib.SSW_ERR_UNSUPPORTED, 'sharded top-k: candidate overflow (flat spectrum); '
                            'the low-frequency bound was too loose for this frame')
 
