@@ -55,8 +55,8 @@ struct ssw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // side stream: the (latency-bound) top-k of the base frame runs beside the forward transform of the
-    // derived frame in the fused extract pipeline
+    // side stream: in the fused extract pipeline the derived frame's forward transform runs beside the base
+    // frame's forward transform and ordering
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // copy streams + events of the pipelined host-buffer batch entry points
@@ -1436,19 +1436,21 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         const unsigned nb = std::min(cb, batch - b0);
         float* pb = d_planes;
         float* pd = d_planes + (size_t)cb * np;
-        rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
-        if (rc == SSW_OK && c->overlap_topk) {
-            // fork: ordering of the base coefficients on the side stream, derived forward transform on the main one
+        if (c->overlap_topk) {
+            // fork: the derived frame's forward transform runs on the side stream beside the base frame's forward
+            // transform and its (latency-bound) ordering; CTAs of the two transforms fill each other's partial waves
             cudaStream_t main_stream = c->stream;
             CK(cudaEventRecord(c->ev_fork, main_stream));
             CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
             c->stream = c->aux;
-            rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
+            rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
             c->stream = main_stream;
             CK(cudaEventRecord(c->ev_join, c->aux));
-            if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
+            if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
+            if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
             CK(cudaStreamWaitEvent(main_stream, c->ev_join, 0));   // join (also on error paths: keeps the streams ordered)
         } else {
+            rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
             if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
             if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
         }
