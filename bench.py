@@ -489,7 +489,9 @@ def run_ours(args, wl):
                        'insertion': 'Option2', 'ordering': 'Energy',
                        'l2': 'inputs larger than L2: ring of %d distinct frames (%.0f MB in + %.0f MB out per rank)'
                              % (nfr, nfr * fb / 1e6, nfr * fb / 1e6),
-                       'parallelism': 'independent frames per GPU, no collective'},
+                       'parallelism': 'independent frames per GPU, no collective',
+                       'streams': 'extract: base and derived forward transforms run concurrently on two streams in the timed '
+                                  'region; the per-kernel table / roofline times every kernel alone on one stream'},
             'embed_mpix_s': world * px_step * K / (ms_embed * 1e-3) / 1e6,
             'extract_mpix_s': world * px_step * K / (ms_extract * 1e-3) / 1e6,
             'roofline': roofline, 'kernels': kernels, 'whole_step': dict(step_algo, **whole),

@@ -1436,7 +1436,7 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         const unsigned nb = std::min(cb, batch - b0);
         float* pb = d_planes;
         float* pd = d_planes + (size_t)cb * np;
-        if (c->overlap_topk) {
+        if (c->overlap_topk && !c->profiling) {   // per-kernel profiling times every kernel alone, on one stream
             // fork: the derived frame's forward transform runs on the side stream beside the base frame's forward
             // transform and its (latency-bound) ordering; CTAs of the two transforms fill each other's partial waves
             cudaStream_t main_stream = c->stream;
