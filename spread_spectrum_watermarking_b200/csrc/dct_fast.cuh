@@ -17,12 +17,39 @@
 // thread after the other, so the index arithmetic is verified without a GPU.
 #pragma once
 #include "dct_kernels.cuh"
+#if defined(__CUDACC__)
+#include "pdl.cuh"
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define SSW_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define SSW_FADD_RZ(a, b) __fadd_rz((a), (b))
+#define SSW_PRMT(a, b, sel) __byte_perm((a), (b), (sel))
+#define SSW_F2U(f) __float_as_uint(f)
+#define SSW_U2F(u) __uint_as_float(u)
 #else
 #include <cmath>
+#include <cstring>
 #define SSW_FMA(a, b, c) std::fmaf((a), (b), (c))
+// host stand-ins (tests/emul): a + b is exact in double for the operands used here; truncate to f32
+inline float ssw_host_fadd_rz(float a, float b) {
+    const double d = (double)a + (double)b;
+    float f = (float)d;
+    if (std::fabs((double)f) > std::fabs(d)) f = std::nextafterf(f, 0.0f);
+    return f;
+}
+inline unsigned ssw_host_prmt(unsigned a, unsigned b, unsigned sel) {   // PRMT, default mode, selectors 0..7
+    const unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 255u) << (8 * i);
+    return r;
+}
+inline unsigned ssw_host_f2u(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float ssw_host_u2f(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+#define SSW_FADD_RZ(a, b) ssw_host_fadd_rz((a), (b))
+#define SSW_PRMT(a, b, sel) ssw_host_prmt((a), (b), (sel))
+#define SSW_F2U(f) ssw_host_f2u(f)
+#define SSW_U2F(u) ssw_host_u2f(u)
 #endif
 
 namespace ssw {
@@ -177,18 +204,37 @@ SSW_HD void fft_phase(cplx* s, const cplx* tw, int t, cplx* v) {
 // colour helpers (bit-identical to color.cuh; the division by 255 is replaced by an exact
 // two-term constant and one fma -- verified for all 256 inputs by the CPU test-suite)
 // ------------------------------------------------------------------------------------------------
-SSW_HD float u8_unit(unsigned v) {
+#ifndef SSW_U8_MAGIC
+#define SSW_U8_MAGIC 1
+#endif
+// x (an integer 0..255 held exactly in a float) -> x/255, correctly rounded
+SSW_HD float unit_of(float x) {
     // 1/255 = c_hi + c_lo to ~2^-50: fma(x, c_hi, fl(x*c_lo)) is the correctly rounded x/255 for x = 0..255
-    const float x = (float)v;
     const float c_hi = 0.0039215688593685626983642578125f;  // fl32(1/255)
     const float c_lo = -2.31917579870781060424633324146270751953125e-10f;  // fl32(1/255 - c_hi)
     return SSW_FMA(x, c_hi, SSW_FMUL(x, c_lo));
 }
+SSW_HD float u8_unit(unsigned v) { return unit_of((float)v); }
 
-SSW_HD void unpack4(unsigned w0, unsigned w1, unsigned w2, unsigned* b) {
-    b[0] = w0 & 255u; b[1] = (w0 >> 8) & 255u; b[2] = (w0 >> 16) & 255u; b[3] = w0 >> 24;
-    b[4] = w1 & 255u; b[5] = (w1 >> 8) & 255u; b[6] = (w1 >> 16) & 255u; b[7] = w1 >> 24;
-    b[8] = w2 & 255u; b[9] = (w2 >> 8) & 255u; b[10] = (w2 >> 16) & 255u; b[11] = w2 >> 24;
+// byte j of w -> float, exactly.  Device: one PRMT builds the bits of 2^23 + b (0x4B0000bb) and one FADD removes
+// the 2^23 -- both on the full-rate ALU / FMA pipes, instead of an I2F.U8 on the conversion unit.
+template <int J>
+SSW_HD float byte_to_float(unsigned w) {
+#if SSW_U8_MAGIC
+    return SSW_FADD(SSW_U2F(SSW_PRMT(w, 0x4B000000u, 0x7540u + J)), -8388608.0f);
+#else
+    return (float)((w >> (8 * J)) & 255u);
+#endif
+}
+
+// 12 bytes (4 RGB8 pixels) -> the 12 channel values as u8/255
+SSW_HD void unpack4_unit(unsigned w0, unsigned w1, unsigned w2, float* c) {
+    c[0] = unit_of(byte_to_float<0>(w0)); c[1] = unit_of(byte_to_float<1>(w0));
+    c[2] = unit_of(byte_to_float<2>(w0)); c[3] = unit_of(byte_to_float<3>(w0));
+    c[4] = unit_of(byte_to_float<0>(w1)); c[5] = unit_of(byte_to_float<1>(w1));
+    c[6] = unit_of(byte_to_float<2>(w1)); c[7] = unit_of(byte_to_float<3>(w1));
+    c[8] = unit_of(byte_to_float<0>(w2)); c[9] = unit_of(byte_to_float<1>(w2));
+    c[10] = unit_of(byte_to_float<2>(w2)); c[11] = unit_of(byte_to_float<3>(w2));
 }
 
 struct f4 { float a, b, c, d; };  // 16-byte vector for host + device
@@ -236,6 +282,27 @@ SSW_HD unsigned unit_to_u8_fast(float v) {
 #endif
 }
 
+// four unit values -> four RGB8 bytes packed into one word (byte i = unit_to_u8_fast(o[i])).
+// Device: floor(t) of t = RZ(s + 0.5) in [0, 256) is read off the low mantissa byte of RZ(t + 2^23), and three
+// PRMTs gather the four bytes -- no F2I on the conversion unit, no shift/or chain.
+SSW_HD unsigned pack_u8x4(const float* o) {
+#if SSW_U8_MAGIC
+    unsigned m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#if defined(__CUDA_ARCH__)
+        const float c = fminf(fmaxf(o[i], 0.0f), 1.0f);   // NaN -> 0
+#else
+        const float c = !(o[i] == o[i]) ? 0.0f : (o[i] < 0.0f ? 0.0f : (o[i] > 1.0f ? 1.0f : o[i]));
+#endif
+        m[i] = SSW_F2U(SSW_FADD_RZ(SSW_FADD_RZ(SSW_FMUL(c, 255.0f), 0.5f), 8388608.0f));
+    }
+    return SSW_PRMT(SSW_PRMT(m[0], m[1], 0x0040u), SSW_PRMT(m[2], m[3], 0x0040u), 0x5410u);
+#else
+    return unit_to_u8_fast(o[0]) | (unit_to_u8_fast(o[1]) << 8) | (unit_to_u8_fast(o[2]) << 16) | (unit_to_u8_fast(o[3]) << 24);
+#endif
+}
+
 // base pointer of image `img` inside a batch of pixel type TYPE (stride in pixels)
 template <int TYPE>
 SSW_HD const void* image_base(const void* p, long long img, long long stride) {
@@ -249,10 +316,10 @@ template <int SRC>
 SSW_HD void load_luma4(const void* src, long long pix4 /* index of the first of 4 pixels */, float* y) {
     if constexpr (SRC == PIX_RGB8) {
         const unsigned* p = (const unsigned*)((const unsigned char*)src + 3 * pix4);
-        unsigned b[12];
-        unpack4(ldw(p), ldw(p + 1), ldw(p + 2), b);
+        float c[12];
+        unpack4_unit(ldw(p), ldw(p + 1), ldw(p + 2), c);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+        for (int i = 0; i < 4; ++i) y[i] = rgb_to_y(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
     } else if constexpr (SRC == PIX_RGB32F) {
         const float* p = (const float*)src + 3 * pix4;
         const f4 v0 = ld4(p), v1 = ld4(p + 4), v2 = ld4(p + 8);
@@ -273,10 +340,7 @@ SSW_HD void store_pix4(const void* src, void* dst, long long pix4, const float* 
         float c[12];
         if constexpr (SRC == PIX_RGB8) {
             const unsigned* p = (const unsigned*)((const unsigned char*)src + 3 * pix4);
-            unsigned b[12];
-            unpack4(ldw(p), ldw(p + 1), ldw(p + 2), b);
-#pragma unroll
-            for (int i = 0; i < 12; ++i) c[i] = u8_unit(b[i]);
+            unpack4_unit(ldw(p), ldw(p + 1), ldw(p + 2), c);
         } else {
             const float* p = (const float*)src + 3 * pix4;
             const f4 v0 = ld4(p), v1 = ld4(p + 4), v2 = ld4(p + 8);
@@ -294,13 +358,10 @@ SSW_HD void store_pix4(const void* src, void* dst, long long pix4, const float* 
             o[3 * i + 2] = SSW_FADD(SSW_FADD(y[i], SSW_FMUL(-1.105450f, ci)), SSW_FMUL(1.729860f, cq));
         }
         if constexpr (DST == PIX_RGB8) {
-            unsigned q[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) q[i] = unit_to_u8_fast(o[i]);
             unsigned* d = (unsigned*)((unsigned char*)dst + 3 * pix4);
-            d[0] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
-            d[1] = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
-            d[2] = q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24);
+            d[0] = pack_u8x4(o);
+            d[1] = pack_u8x4(o + 4);
+            d[2] = pack_u8x4(o + 8);
         } else {
             float* d = (float*)dst + 3 * pix4;
 #pragma unroll
@@ -756,16 +817,16 @@ struct RowFwdPF {
                 const int u = t + it * T;
                 if (u < N / 4) {
                     float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
-                    unsigned b[12];
+                    float c[12];
                     if (ha) {
-                        unpack4(sa[3 * u], sa[3 * u + 1], sa[3 * u + 2], b);
+                        unpack4_unit(sa[3 * u], sa[3 * u + 1], sa[3 * u + 2], c);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) ya[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+                        for (int i = 0; i < 4; ++i) ya[i] = rgb_to_y(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
                     }
                     if (hb) {
-                        unpack4(sb[3 * u], sb[3 * u + 1], sb[3 * u + 2], b);
+                        unpack4_unit(sb[3 * u], sb[3 * u + 1], sb[3 * u + 2], c);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) yb[i] = rgb_to_y(u8_unit(b[3 * i]), u8_unit(b[3 * i + 1]), u8_unit(b[3 * i + 2]));
+                        for (int i = 0; i < 4; ++i) yb[i] = rgb_to_y(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
                     }
                     put4<P>(s, u, ya, yb);
                 }
@@ -793,6 +854,7 @@ __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel(const
     // loop state cost registers in the widest kernels.)
     extern __shared__ __align__(16) unsigned char fast_smem[];
     typename K::Thread th;
+    pdl_enter();
     static_for<K::NPH>([&](auto ph) {
         constexpr int p = decltype(ph)::value;
         K::template phase<p>(a, (cplx*)fast_smem, blockIdx.x, threadIdx.x, th);
@@ -805,6 +867,7 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel_pf(const __grid_constant__ FastArgs a) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     typename K::Thread th;
+    pdl_enter();
     int tile = blockIdx.x * a.tiles_per_cta;
     const int end = min(tile + a.tiles_per_cta, a.total_tiles);
     if (tile < end) K::prefetch(a, (cplx*)fast_smem, tile, threadIdx.x);
@@ -848,6 +911,7 @@ using Plan640 = Plan<640, 64, 5, 8, 16>;
 #ifdef SSW_TUNE
 using Plan3840b = Plan<3840, 480, 5, 8, 8, 12>;   // small radices, more threads per line pair
 using Plan3840c = Plan<3840, 384, 15, 8, 8, 4>;
+using Plan3840d = Plan<3840, 128, 15, 16, 16>;   // two butterflies per thread (more ILP, half the warps)
 #endif
 // other common video formats: 720p, 1440p, 8K in both orientations
 using Plan1280 = Plan<1280, 96, 5, 16, 16>;

@@ -1,5 +1,6 @@
 // Embedding scatter, extraction gather, similarity, N(0,1) marks, planar YIQ and synthetic frames.
 #pragma once
+#include "pdl.cuh"
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -23,6 +24,7 @@ __global__ void embed_scatter_kernel(float* __restrict__ planes, long long plane
                                      const unsigned* __restrict__ idx, long long idx_stride, unsigned k,
                                      const float* __restrict__ marks, long long mark_stride, int n_marks,
                                      const unsigned* __restrict__ lens, int method, float alpha) {
+    pdl_enter();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned img = blockIdx.y;
     if (i >= k) return;
@@ -50,6 +52,7 @@ __global__ void extract_gather_kernel(const float* __restrict__ base, const floa
                                       long long plane_stride, const unsigned* __restrict__ idx,
                                       long long idx_stride, unsigned n, int method, float alpha,
                                       float* __restrict__ out, long long out_stride) {
+    pdl_enter();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned img = blockIdx.y;
     if (i >= n) return;
@@ -83,6 +86,7 @@ __device__ __forceinline__ bool shard_local(const ShardLayout& L, unsigned p, un
 __global__ void embed_scatter_shard_kernel(float* __restrict__ plane, ShardLayout L, const unsigned* __restrict__ idx,
                                            unsigned k, const float* __restrict__ marks, long long mark_stride,
                                            int n_marks, const unsigned* __restrict__ lens, int method, float alpha) {
+    pdl_enter();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
     unsigned long long q;
@@ -105,6 +109,7 @@ __global__ void embed_scatter_shard_kernel(float* __restrict__ plane, ShardLayou
 __global__ void extract_gather_shard_kernel(const float* __restrict__ base, const float* __restrict__ derived,
                                             ShardLayout L, const unsigned* __restrict__ idx, unsigned n, int method,
                                             float alpha, float* __restrict__ out) {
+    pdl_enter();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long q;
@@ -123,6 +128,7 @@ __global__ void extract_gather_shard_kernel(const float* __restrict__ base, cons
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ src, unsigned rows, unsigned cols, long long src_ld, long long src_bstride,
                  float* __restrict__ dst, long long dst_ld, long long dst_bstride) {
+    pdl_enter();
     __shared__ float tile[32][33];
     const float* s = src + (long long)blockIdx.z * src_bstride;
     float* d = dst + (long long)blockIdx.z * dst_bstride;
@@ -187,6 +193,7 @@ __device__ __forceinline__ float seq_sum_products(const float* __restrict__ x, c
 __global__ void __launch_bounds__(128)
 similarity_den_kernel(const float* __restrict__ extracted, unsigned n, long long ext_stride,
                       unsigned n_ext, float* __restrict__ den) {
+    pdl_enter();
     __shared__ float prod[4][kSeqBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned e = blockIdx.x * 4 + warp;
@@ -199,6 +206,7 @@ __global__ void __launch_bounds__(kSimMarks)
 similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned n,
                        const float* __restrict__ extracted, long long ext_stride, const float* __restrict__ den,
                        float* __restrict__ out, long long out_stride) {
+    pdl_enter();
     __shared__ float tile[kSimMarks][kSimChunk + 1];
     __shared__ float ex[kSimChunk];
     const size_t m0 = (size_t)blockIdx.x * kSimMarks;
@@ -246,6 +254,7 @@ constexpr int kPairsPerCta = 2;   // two warps per pair: one walks the numerator
 __global__ void __launch_bounds__(kPairsPerCta * 64)
 similarity_pairs_kernel(const float* __restrict__ marks, const float* __restrict__ extracted, unsigned n,
                         long long stride, unsigned n_pairs, float* __restrict__ out) {
+    pdl_enter();
     __shared__ float part[kPairsPerCta][2];
     __shared__ float prod[kPairsPerCta * 2][kSeqBlock];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -21,6 +21,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "pdl.cuh"
 
 namespace ssw {
 
@@ -109,6 +110,7 @@ __device__ __forceinline__ unsigned find_kth_bin(const unsigned* sh, unsigned k)
 __global__ void __launch_bounds__(512)
 topk_hist_kernel(const float* __restrict__ planes, long long plane_stride, unsigned n, unsigned k,
                  OrderConsts oc, TopkScratch ts) {
+    pdl_enter();
     __shared__ unsigned sh[kHistBins];
     __shared__ unsigned s_last;
     const unsigned img = blockIdx.y;
@@ -174,6 +176,7 @@ constexpr int kBlockRows = 128, kBlockCols = 256;
 __global__ void __launch_bounds__(512)
 topk_block_bin_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned k,
                       OrderConsts oc, TopkScratch ts) {
+    pdl_enter();
     // grid (x = slices of the block, y = image): per-CTA shared histogram -> global histogram -> the last CTA of
     // the image finds the bin (same ticket scheme as topk_hist_kernel; scratch is left zeroed)
     __shared__ unsigned sh[kHistBins];
@@ -233,6 +236,7 @@ __device__ __forceinline__ void topk_push(unsigned key, unsigned p, unsigned bin
 __global__ void __launch_bounds__(512)
 topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, unsigned n, OrderConsts oc,
                     TopkScratch ts) {
+    pdl_enter();
     const unsigned img = blockIdx.y;
     const float* plane = planes + (long long)img * plane_stride;
     const unsigned bin_sel = ts.sel_bin[img];
@@ -264,10 +268,74 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
     }
 }
 
+// ---- 1'+2 fused: every collect CTA bounds the k-th key itself -----------------------------------------
+// For short marks (k <= kFusedMaxK) a block of <= 8192 low-frequency coefficients (64 rows x 128 columns:
+// 8x the coefficients consumed) bounds the k-th key as tightly as the larger block of topk_block_bin (measured on
+// the synthetic 4K / 1080p frames: identical candidate counts), and 8192 L2-resident values cost a collect CTA
+// ~2 us -- less than the separate 16-CTA kernel with its global histogram, ticket and extra launch.
+// Every CTA derives the same bin from the same data, so no inter-CTA communication is needed.
+constexpr int kFusedRows = 64, kFusedCols = 128, kFusedMaxK = 1024;
+
+__global__ void __launch_bounds__(512, 4)
+topk_bin_collect_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned k,
+                        OrderConsts oc, TopkScratch ts) {
+    pdl_enter();
+    __shared__ unsigned sh[kHistBins];
+    const unsigned img = blockIdx.y;
+    const float* plane = planes + (long long)img * plane_stride;
+    const unsigned n = w * h;
+    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0;
+    const unsigned br = min(h, (unsigned)kFusedRows), bc = min(w, (unsigned)kFusedCols);
+    const unsigned total = br * bc;
+    __syncthreads();
+    constexpr int PER = kFusedRows * kFusedCols / 512, BATCH = 8;   // 2 x 8 independent loads in flight per thread
+#pragma unroll 1
+    for (int u0 = 0; u0 < PER; u0 += BATCH) {
+        float v[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const unsigned e = threadIdx.x + (u0 + u) * 512u;
+            const unsigned r = e / bc, c = e - r * bc;
+            v[u] = (e < total && e) ? __ldg(plane + r * w + c) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const unsigned e = threadIdx.x + (u0 + u) * 512u;
+            const unsigned r = e / bc, c = e - r * bc;
+            // row-major planes only (t_ld == 0): flat index == position; e == 0 is the DC term
+            if (e < total && e) atomicAdd(&sh[order_key(v[u], r * w + c, oc) >> (32 - kHistBits)], 1u);
+        }
+    }
+    __syncthreads();
+    const unsigned bin_sel = find_kth_bin(sh, k);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ts.sel_bin[img] = bin_sel;
+    // the collect pass proper (same as topk_collect_kernel)
+    unsigned* count = ts.cand_count + img;
+    unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
+    const unsigned n4 = n >> 2;
+    if ((((size_t)plane) & 15) == 0) {
+        const float4* p4 = (const float4*)plane;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+            const float4 q4 = __ldg(p4 + i);
+            const unsigned q = i << 2;
+            const float e[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (q + u) topk_push(order_key(e[u], q + u, oc), q + u, bin_sel, count, cand);
+        }
+        for (unsigned q = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+            if (q) topk_push(order_key(plane[q], q, oc), q, bin_sel, count, cand);
+    } else {
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
+            if (q) topk_push(order_key(plane[q], q, oc), q, bin_sel, count, cand);
+    }
+}
+
 // ---- 2'. distributed merge: concatenate the candidate lists gathered from all ranks --------------
 __global__ void __launch_bounds__(256)
 topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned* __restrict__ counts, unsigned n_lists,
                    unsigned list_cap, TopkScratch ts) {
+    pdl_enter();
     __shared__ unsigned off[65];
     if (threadIdx.x == 0) {
         unsigned run = 0;
@@ -361,6 +429,7 @@ __device__ __forceinline__ void topk_sort_body(const unsigned long long* __restr
 
 __global__ void __launch_bounds__(kSortThreads)
 topk_sort_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride) {
+    pdl_enter();
     extern __shared__ unsigned long long sc[];  // kTopkCap keys (exchange buffer of the cross-warp steps)
     const unsigned img = blockIdx.x;
     const unsigned total = ts.cand_count[img];

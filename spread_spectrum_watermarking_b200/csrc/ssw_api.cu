@@ -67,6 +67,8 @@ struct ssw_ctx {
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
+    bool pdl = true;                       // SSW_PDL=0: no programmatic dependent launches
+    bool topk_fused = true;                // SSW_TOPK_FUSED=0: separate topk_block_bin + topk_collect kernels for every k
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     int row_variant = 0;                   // SSW_ROW_VARIANT (tuning builds)
     bool prefetch = false;                 // SSW_PREFETCH=1: cp.async-staged forward row pass (RowFwdPF)
@@ -91,6 +93,22 @@ struct ssw_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
 };
+
+// Launch of a kernel that starts with pdl_enter() (pdl.cuh): with programmatic stream serialization the grid may
+// become resident while its predecessor on the stream drains; it touches no memory before its griddepcontrol.wait.
+// ONLY kernels that begin with pdl_enter() may be launched through this helper.  SSW_PDL=0 -> plain launches.
+template <class... KArgs, class... Args>
+static void launch_pdl(ssw_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);   // errors: cudaGetLastError at the call site
+}
 
 // Counts a kernel launch and, when profiling is on, brackets it with CUDA events on the context's
 // stream (the stream the kernel is launched on).
@@ -157,6 +175,8 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_COL_PAIRS")) c->col_pairs = atoi(s);
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
+    if (const char* s = getenv("SSW_PDL")) c->pdl = atoi(s) != 0;
+    if (const char* s = getenv("SSW_TOPK_FUSED")) c->topk_fused = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     if (const char* s = getenv("SSW_ROW_VARIANT")) c->row_variant = atoi(s);
     if (const char* s = getenv("SSW_PREFETCH")) c->prefetch = atoi(s) != 0;
@@ -404,7 +424,7 @@ static int launch_fast(ssw_ctx* c, const char* name, fast::FastArgs a, int w, in
     }
     {
         KScope ks(c, name);
-        kernel<<<(unsigned)tiles, K::THREADS, K::SMEM, c->stream>>>(a);
+        launch_pdl(c, kernel, (unsigned)tiles, K::THREADS, K::SMEM, c->stream, a);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -434,7 +454,7 @@ static int launch_fast_pf(ssw_ctx* c, const char* name, fast::FastArgs a, int w,
     a.tiles_per_cta = (int)per;
     {
         KScope ks(c, name);
-        kernel<<<(unsigned)((tiles + per - 1) / per), K::THREADS, K::SMEM, c->stream>>>(a);
+        launch_pdl(c, kernel, (unsigned)((tiles + per - 1) / per), K::THREADS, K::SMEM, c->stream, a);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -487,6 +507,8 @@ static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int 
             case 5: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840b, 1, PIX_RGB8>, 3>>(c, "fwd_rows", a, w, h, batch);
             case 6: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840, 1, PIX_RGB8>, 5>>(c, "fwd_rows", a, w, h, batch);
             case 7: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840c, 1, PIX_RGB8>, 3>>(c, "fwd_rows", a, w, h, batch);
+            case 8: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840d, 1, PIX_RGB8>, 4>>(c, "fwd_rows", a, w, h, batch);
+            case 9: return launch_fast<WithMinB<fast::RowFwd<fast::Plan3840d, 2, PIX_RGB8>, 2>>(c, "fwd_rows", a, w, h, batch);
             default: *done = false; break;
         }
     }
@@ -776,14 +798,22 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         TopkScratch ts = c->ts;
         ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0;
         ts.cand += (size_t)b0 * kTopkCap;
+        if (!full_hist && c->topk_fused && k <= (unsigned)kFusedMaxK && (unsigned)w * (unsigned)h >= (unsigned)kFusedMaxK) {
+            // short marks: every collect CTA bounds the k-th key itself from a small low-frequency block
+            KScope ks(c, "topk_bin_collect");
+            launch_pdl(c, topk_bin_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride,
+                       (unsigned)w, (unsigned)h, k, oc, ts);
+            CK(cudaGetLastError());
+            continue;
+        }
         if (full_hist) {
             KScope ks(c, "topk_hist");
-            topk_hist_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
+            launch_pdl(c, topk_hist_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
         } else {
             KScope ks(c, "topk_block_bin");
-            topk_block_bin_kernel<<<dim3(16, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
+            launch_pdl(c, topk_block_bin_kernel, dim3(16, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
-        { KScope ks(c, "topk_collect"); topk_collect_kernel<<<dim3(blocks, nb), 512, 0, c->stream>>>(d_planes + (size_t)b0 * n, stride, n, oc, ts); }
+        { KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts); }
         CK(cudaGetLastError());
     }
     const void* key = (const void*)topk_sort_kernel;
@@ -792,7 +822,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    { KScope ks(c, "topk_sort"); topk_sort_kernel<<<batch, kSortThreads, smem, c->stream>>>(c->ts, k, d_idx, idx_stride); }
+    { KScope ks(c, "topk_sort"); launch_pdl(c, topk_sort_kernel, batch, kSortThreads, smem, c->stream, c->ts, k, d_idx, idx_stride); }
     CK(cudaGetLastError());
     return SSW_OK;
 }
@@ -1017,7 +1047,7 @@ extern "C" int ssw_writer_embed(ssw_writer* wr, const float* const* marks, const
     CK(cudaMemcpyAsync(d_lens, hl.data(), n_marks * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
     {
         KScope ks(c, "embed_scatter");
-        embed_scatter_kernel<<<dim3((unsigned)((kmax + 255) / 256), 1), 256, 0, c->stream>>>(
+        launch_pdl(c, embed_scatter_kernel, dim3((unsigned)((kmax + 255) / 256), 1), 256, 0, c->stream, 
             wr->d_plane, 0, wr->d_idx, 0, (unsigned)kmax, d_marks, (long long)kmax, (int)n_marks, d_lens,
             wr->cfg.method, wr->cfg.alpha);
     }
@@ -1175,7 +1205,7 @@ static int reader_extract(ssw_reader* base, ssw_reader* derived, float* out, siz
     if (!out_on_device) CK(cudaMallocAsync(&d_out, n * sizeof(float), c->stream));
     {
         KScope ks(c, "extract_gather");
-        extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream>>>(
+        launch_pdl(c, extract_gather_kernel, dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream, 
             base->d_plane, derived->d_plane, 0, base->d_idx, 0, (unsigned)n, base->cfg.method, base->cfg.alpha, d_out, 0);
     }
     CK(cudaGetLastError());
@@ -1236,7 +1266,7 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
         if (n_marks > 0x7FFFFFFFull || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
         {
             KScope ks(c, "similarity_pairs");
-            similarity_pairs_kernel<<<(unsigned)((n_marks + kPairsPerCta - 1) / kPairsPerCta), kPairsPerCta * 64, 0, c->stream>>>(
+            launch_pdl(c, similarity_pairs_kernel, (unsigned)((n_marks + kPairsPerCta - 1) / kPairsPerCta), kPairsPerCta * 64, 0, c->stream, 
                 d_bank, d_ext, (unsigned)n, (long long)n, (unsigned)n_marks, d_out);
         }
         CK(cudaGetLastError());
@@ -1248,11 +1278,11 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
     CK(cudaMallocAsync(&d_den, n_ext * sizeof(float), c->stream));
     {
         KScope ks(c, "similarity_den");
-        similarity_den_kernel<<<(unsigned)((n_ext + 3) / 4), 128, 0, c->stream>>>(d_ext, (unsigned)n, (long long)n, (unsigned)n_ext, d_den);
+        launch_pdl(c, similarity_den_kernel, (unsigned)((n_ext + 3) / 4), 128, 0, c->stream, d_ext, (unsigned)n, (long long)n, (unsigned)n_ext, d_den);
     }
     {
         KScope ks(c, "similarity_bank");
-        similarity_bank_kernel<<<dim3((unsigned)gx, (unsigned)n_ext), kSimMarks, 0, c->stream>>>(
+        launch_pdl(c, similarity_bank_kernel, dim3((unsigned)gx, (unsigned)n_ext), kSimMarks, 0, c->stream, 
             d_bank, n_marks, (unsigned)n, d_ext, (long long)n, d_den, d_out, (long long)n_marks);
     }
     CK(cudaGetLastError());
@@ -1401,7 +1431,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
             rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k, c->topk_full_hist);
             if (rc == SSW_OK) {
                 KScope ks(c, "embed_scatter");
-                embed_scatter_kernel<<<dim3((unsigned)((k + 255) / 256), nb), 256, 0, c->stream>>>(
+                launch_pdl(c, embed_scatter_kernel, dim3((unsigned)((k + 255) / 256), nb), 256, 0, c->stream, 
                     d_planes, (long long)np, d_idx, (long long)k, (unsigned)k, marks + (size_t)b0 * n, (long long)n, 1,
                     nullptr, cfg->method, cfg->alpha);
             }
@@ -1457,7 +1487,7 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         if (rc == SSW_OK) {
             {
                 KScope ks(c, "extract_gather");
-                extract_gather_kernel<<<dim3((unsigned)((n + 255) / 256), nb), 256, 0, c->stream>>>(
+                launch_pdl(c, extract_gather_kernel, dim3((unsigned)((n + 255) / 256), nb), 256, 0, c->stream, 
                     pb, pd, (long long)np, d_idx, (long long)n, (unsigned)n, cfg->method, cfg->alpha,
                     extracted + (size_t)b0 * n, (long long)n);
             }
@@ -1751,7 +1781,7 @@ extern "C" int ssw_transpose_dev(ssw_ctx* c, const float* src, uint32_t rows, ui
     CKS(ctx_bind(c));
     {
         KScope ks(c, "transpose");
-        transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32, batch), 256, 0, c->stream>>>(
+        launch_pdl(c, transpose_kernel, dim3((cols + 31) / 32, (rows + 31) / 32, batch), 256, 0, c->stream, 
             src, rows, cols, src_ld, src_bstride, dst, dst_ld, dst_bstride);
     }
     CK(cudaGetLastError());
@@ -1782,7 +1812,7 @@ extern "C" int ssw_shard_topk_bin_dev(ssw_ctx* c, const float* plane, const ssw_
     {
         KScope ks(c, "topk_block_bin");
         // local plane [ncols][height]: "width" of the block kernel is the local line length
-        topk_block_bin_kernel<<<dim3(16, 1), 512, 0, c->stream>>>(plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
+        launch_pdl(c, topk_block_bin_kernel, dim3(16, 1), 512, 0, c->stream, plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -1806,7 +1836,7 @@ extern "C" int ssw_shard_topk_collect_dev(ssw_ctx* c, const float* plane, const 
     const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((n / 4 + 511) / 512, (size_t)c->sm_count * 4));
     {
         KScope ks(c, "topk_collect");
-        topk_collect_kernel<<<dim3(blocks, 1), 512, 0, c->stream>>>(plane, 0, (unsigned)n, oc, ts);
+        launch_pdl(c, topk_collect_kernel, dim3(blocks, 1), 512, 0, c->stream, plane, 0, (unsigned)n, oc, ts);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -1826,7 +1856,7 @@ extern "C" int ssw_shard_topk_merge_dev(ssw_ctx* c, const uint64_t* lists_dev, c
     CK(cudaMemsetAsync(overflow_dev, 0, sizeof(uint32_t), c->stream));
     {
         KScope ks(c, "topk_concat");
-        topk_concat_kernel<<<1, 256, 0, c->stream>>>((const unsigned long long*)lists_dev, counts_dev, n_lists, (unsigned)kTopkCap, ts);
+        launch_pdl(c, topk_concat_kernel, 1, 256, 0, c->stream, (const unsigned long long*)lists_dev, counts_dev, n_lists, (unsigned)kTopkCap, ts);
     }
     const void* key = (const void*)topk_sort_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
@@ -1834,7 +1864,7 @@ extern "C" int ssw_shard_topk_merge_dev(ssw_ctx* c, const uint64_t* lists_dev, c
         CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    { KScope ks(c, "topk_sort"); topk_sort_kernel<<<1, kSortThreads, smem, c->stream>>>(ts, (unsigned)k, idx_dev, 0); }
+    { KScope ks(c, "topk_sort"); launch_pdl(c, topk_sort_kernel, 1, kSortThreads, smem, c->stream, ts, (unsigned)k, idx_dev, 0); }
     CK(cudaGetLastError());
     return SSW_OK;
 }
@@ -1856,7 +1886,7 @@ extern "C" int ssw_shard_embed_dev(ssw_ctx* c, float* plane, const ssw_shard* sh
     CKS(ctx_bind(c));
     {
         KScope ks(c, "embed_scatter");
-        embed_scatter_shard_kernel<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(
+        launch_pdl(c, embed_scatter_shard_kernel, (unsigned)((k + 255) / 256), 256, 0, c->stream, 
             plane, shard_layout(sh), idx_dev, (unsigned)k, marks_dev, (long long)mark_stride, (int)n_marks, lens_dev,
             cfg->method, cfg->alpha);
     }
@@ -1875,7 +1905,7 @@ extern "C" int ssw_shard_extract_dev(ssw_ctx* c, const float* base_plane, const 
     CKS(ctx_bind(c));
     {
         KScope ks(c, "extract_gather");
-        extract_gather_shard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        launch_pdl(c, extract_gather_shard_kernel, (unsigned)((n + 255) / 256), 256, 0, c->stream, 
             base_plane, derived_plane, shard_layout(sh), idx_dev, (unsigned)n, cfg->method, cfg->alpha, out_dev);
     }
     CK(cudaGetLastError());

@@ -292,4 +292,35 @@ int emul_fast_unit_to_u8_mismatches(const float* v, int n) {
     return bad;
 }
 
+// byte_to_float / unpack4_unit (PRMT + FADD form) against u8_to_unit for every byte value in every byte lane
+int emul_fast_byte_unpack_mismatches(void) {
+    int bad = 0;
+    for (unsigned v = 0; v < 256; ++v) {
+        const unsigned w0 = v | ((255u - v) << 8) | (((v * 7u) & 255u) << 16) | (((v * 13u + 5u) & 255u) << 24);
+        const unsigned w1 = (w0 << 8) | (w0 >> 24), w2 = (w0 << 16) | (w0 >> 16);
+        const unsigned ws[3] = {w0, w1, w2};
+        float c[12];
+        unpack4_unit(w0, w1, w2, c);
+        for (int i = 0; i < 12; ++i) bad += (c[i] != u8_to_unit((ws[i / 4] >> (8 * (i % 4))) & 255u));
+    }
+    return bad;
+}
+
+// pack_u8x4 (two round-toward-zero adds + PRMT gather) against unit_to_u8 over ALL 2^32 float bit patterns,
+// split over `parts` callers (part p covers the bit patterns congruent to ... a contiguous 1/parts range)
+long long emul_fast_pack_u8_mismatches(unsigned part, unsigned parts) {
+    long long bad = 0;
+    const unsigned long long total = 1ull << 32, lo = total * part / parts, hi = total * (part + 1) / parts;
+    for (unsigned long long b = lo; b < hi; b += 4) {
+        float o[4];
+        unsigned want = 0;
+        for (int i = 0; i < 4; ++i) {
+            o[i] = ssw_host_u2f((unsigned)(b + i));
+            want |= unit_to_u8(o[i]) << (8 * i);
+        }
+        bad += (pack_u8x4(o) != want);
+    }
+    return bad;
+}
+
 }  // extern "C"

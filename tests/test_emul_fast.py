@@ -27,6 +27,25 @@ def test_unit_to_u8_fast_is_exact(emul):
     assert emul.emul_fast_unit_to_u8_mismatches(ptr(v), len(v)) == 0
 
 
+def test_byte_unpack_is_exact(emul):
+    """u8 -> float through PRMT + FADD (0x4B0000bb - 2^23) instead of I2F: every byte value, every byte lane"""
+    emul.emul_fast_byte_unpack_mismatches.restype = ctypes.c_int
+    assert emul.emul_fast_byte_unpack_mismatches() == 0
+
+
+def test_pack_u8x4_is_exact_for_every_float(emul):
+    """round(clamp(v)*255) through two round-toward-zero adds and a PRMT gather == the reference rounding
+    (image::into_rgb8 after src/yiq.rs:139-147) for ALL 2^32 f32 bit patterns (NaNs, infinities, denormals)"""
+    from concurrent.futures import ThreadPoolExecutor
+    f = emul.emul_fast_pack_u8_mismatches
+    f.restype = ctypes.c_longlong
+    f.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    parts = 16
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        bad = sum(ex.map(lambda p: f(p, parts), range(parts)))
+    assert bad == 0
+
+
 def test_plan_table(emul):
     for n in FAST:
         assert emul.emul_fast_has_plan(n) == 1
