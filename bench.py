@@ -101,7 +101,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -111,6 +111,13 @@ class Clocks:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(',')])
+
+    def settle(self, timeout=5.0):
+        """Block until the sampler has delivered its first row: nvidia-smi's start-up (NVML initialisation takes driver
+        locks for ~100 ms) must be over before the warm-up begins, or it lands inside a timed region of a few ms."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.01)
 
     def stop(self):
         if not self.proc:
@@ -359,6 +366,7 @@ def run_ours(args, wl):
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+        clocks.settle()
     l0 = ctx.launch_count
     ms_total = timed(step, K, W)
     launches = (ctx.launch_count - l0) * K // (K + W)
@@ -579,6 +587,7 @@ def run_c4(args, wl):
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+        clocks.settle()
     l0 = ctx.launch_count
     ms_total = timed(step, K, W)
     launches = (ctx.launch_count - l0) * K // (K + W)
@@ -678,7 +687,7 @@ def run_c4(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--steps', type=int, default=None, help='default: 200 (ours), 3 (reference arm)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
@@ -686,6 +695,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='tuning runs: only 3 end-to-end steps')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = 3 if args.impl == 'reference' else 200
     if args.impl == 'reference':
         return run_reference(args, wl)
     if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:  # convenience: re-launch under torchrun

@@ -14,8 +14,8 @@
 //      topk_hist    : (repair path) the same histogram over the whole plane, one read;
 //   2. topk_collect : second read, every element whose bin >= that bin is appended to a small
 //                     candidate list (k + one bin's worth of elements);
-//   3. topk_sort    : one CTA bitonic-sorts the candidates by the composite key and emits the first
-//                     k indices.
+//   3. topk_rank    : the rank of a candidate is the number of candidates with a larger composite key
+//                     (unique keys); a few CTAs count, ranks < k are written to their place.
 // Candidate overflow (pathological spectra with > kTopkCap near-equal keys) is flagged and the host
 // re-runs the exact general path (radix sort of all candidates, select_general.cuh).
 #pragma once
@@ -27,7 +27,7 @@ namespace ssw {
 
 constexpr int kHistBits = 12;
 constexpr int kHistBins = 1 << kHistBits;
-constexpr int kTopkCap = 8192;  // candidates per image held by the single-CTA sort (64 KB of smem)
+constexpr int kTopkCap = 8192;  // candidates per image (64 KB of shared memory in topk_rank)
 
 struct OrderConsts {
     int mode;  // SSW_ORDER_*
@@ -169,59 +169,46 @@ topk_hist_kernel(const float* __restrict__ planes, long long plane_stride, unsig
 // the bin holding the k-th largest key of the top-left block (where natural images keep their
 // energy) is a valid -- and for natural images tight -- selection bin for topk_collect: every
 // top-k element of the plane lies in a bin >= it.  One CTA per image reads <= 32k coefficients
-// instead of one full pass over the plane.  A loose bound (noise-like spectra) only costs a
-// candidate overflow, which is detected by topk_sort and repaired with the full histogram.
-constexpr int kBlockRows = 128, kBlockCols = 256;
+// instead of one full pass over the plane (8k for marks of <= 1024 values: on the synthetic 4K / 1080p frames
+// and k = 1000 the 64 x 128 block gives the same candidate count as the 128 x 256 one).  A loose bound (noise-like spectra) only costs a
+// candidate overflow, which is detected by topk_rank and repaired with the full histogram.
+constexpr int kBlockRows = 128, kBlockCols = 256;        // block for long marks
+constexpr int kSmallRows = 64, kSmallCols = 128, kSmallMaxK = 1024;   // short marks: 8x the coefficients consumed
+constexpr int kBinThreads = 1024;
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kBinThreads)
 topk_block_bin_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned k,
                       OrderConsts oc, TopkScratch ts) {
+    // ONE CTA per image: shared histogram -> bin, no global histogram / fence / ticket round trips (the block is
+    // at most 32k L2-resident coefficients: 32 per thread, 16 independent loads in flight).
     pdl_enter();
-    // grid (x = slices of the block, y = image): per-CTA shared histogram -> global histogram -> the last CTA of
-    // the image finds the bin (same ticket scheme as topk_hist_kernel; scratch is left zeroed)
     __shared__ unsigned sh[kHistBins];
-    __shared__ unsigned s_last;
-    const unsigned img = blockIdx.y;
+    const unsigned img = blockIdx.x;
     const float* plane = planes + (long long)img * plane_stride;
     for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const unsigned br = min(h, (unsigned)kBlockRows), bc = min(w, (unsigned)kBlockCols);
+    const bool small = k <= (unsigned)kSmallMaxK;
+    const unsigned br = min(h, (unsigned)(small ? kSmallRows : kBlockRows)), bc = min(w, (unsigned)(small ? kSmallCols : kBlockCols));
     const unsigned total = br * bc;
-    for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * gridDim.x * blockDim.x) {
-        float v[4];
-        unsigned p[4];
+    __syncthreads();
+    constexpr unsigned BATCH = 16;
+    for (unsigned e0 = threadIdx.x; e0 < total; e0 += BATCH * kBinThreads) {
+        float v[BATCH];
+        unsigned p[BATCH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {   // independent loads in flight
-            const unsigned e = e0 + u * gridDim.x * blockDim.x;
+        for (unsigned u = 0; u < BATCH; ++u) {   // independent loads in flight
+            const unsigned e = e0 + u * kBinThreads;
             const unsigned r = e / bc, c = e - r * bc;
             const unsigned q = r * w + c;            // local position (w = local line length)
             p[u] = e < total ? flat_index(q, oc) : 0u;
             v[u] = p[u] ? __ldg(plane + q) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (unsigned u = 0; u < BATCH; ++u)
             if (p[u]) atomicAdd(&sh[order_key(v[u], p[u], oc) >> (32 - kHistBits)], 1u);
     }
     __syncthreads();
-    unsigned* gh = ts.hist + (size_t)img * kHistBins;
-    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x)
-        if (sh[i]) atomicAdd(&gh[i], sh[i]);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&ts.ticket[img], 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) {
-        sh[i] = __ldcg(&gh[i]);
-        gh[i] = 0;
-    }
-    __syncthreads();
     const unsigned b = find_kth_bin(sh, k);
-    if (threadIdx.x == 0) {
-        ts.sel_bin[img] = b;
-        ts.ticket[img] = 0;
-    }
+    if (threadIdx.x == 0) ts.sel_bin[img] = b;
 }
 
 // ---- 2. collect candidates -----------------------------------------------------------------------
@@ -268,69 +255,6 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
     }
 }
 
-// ---- 1'+2 fused: every collect CTA bounds the k-th key itself -----------------------------------------
-// For short marks (k <= kFusedMaxK) a block of <= 8192 low-frequency coefficients (64 rows x 128 columns:
-// 8x the coefficients consumed) bounds the k-th key as tightly as the larger block of topk_block_bin (measured on
-// the synthetic 4K / 1080p frames: identical candidate counts), and 8192 L2-resident values cost a collect CTA
-// ~2 us -- less than the separate 16-CTA kernel with its global histogram, ticket and extra launch.
-// Every CTA derives the same bin from the same data, so no inter-CTA communication is needed.
-constexpr int kFusedRows = 64, kFusedCols = 128, kFusedMaxK = 1024;
-
-__global__ void __launch_bounds__(512, 4)
-topk_bin_collect_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned k,
-                        OrderConsts oc, TopkScratch ts) {
-    pdl_enter();
-    __shared__ unsigned sh[kHistBins];
-    const unsigned img = blockIdx.y;
-    const float* plane = planes + (long long)img * plane_stride;
-    const unsigned n = w * h;
-    for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0;
-    const unsigned br = min(h, (unsigned)kFusedRows), bc = min(w, (unsigned)kFusedCols);
-    const unsigned total = br * bc;
-    __syncthreads();
-    constexpr int PER = kFusedRows * kFusedCols / 512, BATCH = 8;   // 2 x 8 independent loads in flight per thread
-#pragma unroll 1
-    for (int u0 = 0; u0 < PER; u0 += BATCH) {
-        float v[BATCH];
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const unsigned e = threadIdx.x + (u0 + u) * 512u;
-            const unsigned r = e / bc, c = e - r * bc;
-            v[u] = (e < total && e) ? __ldg(plane + r * w + c) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-            const unsigned e = threadIdx.x + (u0 + u) * 512u;
-            const unsigned r = e / bc, c = e - r * bc;
-            // row-major planes only (t_ld == 0): flat index == position; e == 0 is the DC term
-            if (e < total && e) atomicAdd(&sh[order_key(v[u], r * w + c, oc) >> (32 - kHistBits)], 1u);
-        }
-    }
-    __syncthreads();
-    const unsigned bin_sel = find_kth_bin(sh, k);
-    if (blockIdx.x == 0 && threadIdx.x == 0) ts.sel_bin[img] = bin_sel;
-    // the collect pass proper (same as topk_collect_kernel)
-    unsigned* count = ts.cand_count + img;
-    unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
-    const unsigned n4 = n >> 2;
-    if ((((size_t)plane) & 15) == 0) {
-        const float4* p4 = (const float4*)plane;
-        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-            const float4 q4 = __ldg(p4 + i);
-            const unsigned q = i << 2;
-            const float e[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (q + u) topk_push(order_key(e[u], q + u, oc), q + u, bin_sel, count, cand);
-        }
-        for (unsigned q = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
-            if (q) topk_push(order_key(plane[q], q, oc), q, bin_sel, count, cand);
-    } else {
-        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x)
-            if (q) topk_push(order_key(plane[q], q, oc), q, bin_sel, count, cand);
-    }
-}
-
 // ---- 2'. distributed merge: concatenate the candidate lists gathered from all ranks --------------
 __global__ void __launch_bounds__(256)
 topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned* __restrict__ counts, unsigned n_lists,
@@ -341,7 +265,7 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
         unsigned run = 0;
         for (unsigned l = 0; l < n_lists; ++l) { off[l] = run; run += min(counts[l], list_cap); }
         off[n_lists] = run;
-        ts.cand_count[0] = run;  // > kTopkCap is reported as overflow by topk_sort
+        ts.cand_count[0] = run;  // > kTopkCap is reported as overflow by topk_rank
     }
     __syncthreads();
     for (unsigned l = 0; l < n_lists; ++l) {
@@ -351,97 +275,55 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
     }
 }
 
-// ---- 3. sort candidates, emit the first k indices ------------------------------------------------
-// Bitonic network over 256*E keys, E consecutive keys per thread held in registers: strides < E are
-// compare-exchanges inside a thread, strides < 32*E go through warp shuffles, and only the few
-// strides >= 32*E cross warps through shared memory (6 of the 66 steps at 2048 keys).
-constexpr int kSortThreads = 256;
+// ---- 3. order the candidates, emit the first k indices ------------------------------------------
+// The composite keys are unique, so the position of a candidate in the descending order is simply the number
+// of candidates with a larger key.  With ~k + one bin of candidates (1049 for k = 1000 on the 4K frame) the
+// n^2 comparisons (1.1 M) spread over kRankCtas CTAs take ~1 us -- far less than a single-CTA bitonic network,
+// whose 66 dependent exchange steps (shuffles, shared-memory round trips, barriers) cost 12-14 us.
+// CTA b ranks candidates [64 b, 64 b + 64) (+ strides of 64 * gridDim.x); 4 thread groups split the comparison
+// range.  The last CTA to finish (ticket) reports overflow and clears the per-image counters for the next call.
+constexpr int kRankThreads = 256, kRankCtas = 32;
 
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int mask) {
-    const unsigned lo = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)v, mask);
-    const unsigned hi = __shfl_xor_sync(0xFFFFFFFFu, (unsigned)(v >> 32), mask);
-    return ((unsigned long long)hi << 32) | lo;
-}
-
-template <int E>
-__device__ __forceinline__ void bitonic_sort_desc(unsigned long long (&v)[E], unsigned long long* sc) {
-    // The size / stride loops stay ROLLED on purpose: one CTA runs this once, so a fully unrolled network
-    // (hundreds of KB of straight-line code) would execute at instruction-fetch speed.
-    const unsigned tid = threadIdx.x;
-#pragma unroll 1
-    for (unsigned size = 2; size <= (unsigned)(kSortThreads * E); size <<= 1) {
-#pragma unroll 1
-        for (unsigned stride = size >> 1; stride >= (unsigned)E; stride >>= 1) {
-            const unsigned tmask = stride / E;  // partner thread = tid ^ tmask, same slot
-            unsigned long long o[E];
-            if (tmask < 32u) {
-#pragma unroll
-                for (int i = 0; i < E; ++i) o[i] = shfl_xor_u64(v[i], (int)tmask);
-            } else {
-#pragma unroll
-                for (int i = 0; i < E; ++i) sc[i * kSortThreads + tid] = v[i];
-                __syncthreads();
-#pragma unroll
-                for (int i = 0; i < E; ++i) o[i] = sc[i * kSortThreads + (tid ^ tmask)];
-                __syncthreads();
-            }
-            // all E slots of a thread share the direction bits (stride, size >= E)
-            const bool keep_max = (((tid * E) & stride) == 0) == (((tid * E) & size) == 0);
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                const bool gt = v[i] > o[i];
-                v[i] = (gt == keep_max) ? v[i] : o[i];
-            }
-        }
-        // strides < E: compare-exchanges inside the thread (at most log2(E) steps, unrolled per stride)
-#pragma unroll
-        for (unsigned stride = E >> 1; stride > 0; stride >>= 1) {
-            if (stride < size) {
-#pragma unroll
-                for (int i = 0; i < E; ++i) {
-                    if ((i & stride) == 0) {
-                        const bool desc = ((tid * E + i) & size) == 0;
-                        const unsigned long long a = v[i], b = v[i + stride];
-                        if ((a < b) == desc) { v[i] = b; v[i + stride] = a; }
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int E>
-__device__ __forceinline__ void topk_sort_body(const unsigned long long* __restrict__ cand, unsigned cnt, unsigned k,
-                                               unsigned* __restrict__ out, unsigned long long* sc) {
-    unsigned long long v[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const unsigned idx = threadIdx.x * E + i;
-        v[i] = idx < cnt ? __ldcg(cand + idx) : 0ull;
-    }
-    bitonic_sort_desc<E>(v, sc);
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const unsigned idx = threadIdx.x * E + i;
-        if (idx < k) out[idx] = idx < cnt ? (0xFFFFFFFFu - (unsigned)(v[i] & 0xFFFFFFFFull)) : 0u;
-    }
-}
-
-__global__ void __launch_bounds__(kSortThreads)
-topk_sort_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride) {
+__global__ void __launch_bounds__(kRankThreads)
+topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride) {
     pdl_enter();
-    extern __shared__ unsigned long long sc[];  // kTopkCap keys (exchange buffer of the cross-warp steps)
-    const unsigned img = blockIdx.x;
-    const unsigned total = ts.cand_count[img];
+    extern __shared__ unsigned long long keys[];  // up to kTopkCap candidates
+    __shared__ unsigned rank[64];
+    const unsigned img = blockIdx.y, tid = threadIdx.x;
+    const unsigned total = __ldcg(ts.cand_count + img);
     const unsigned cnt = total < (unsigned)kTopkCap ? total : (unsigned)kTopkCap;
     const unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
     unsigned* out = idx_out + (long long)img * idx_stride;
-    if (cnt <= 8u * kSortThreads) topk_sort_body<8>(cand, cnt, k, out, sc);
-    else if (cnt <= 16u * kSortThreads) topk_sort_body<16>(cand, cnt, k, out, sc);
-    else topk_sort_body<32>(cand, cnt, k, out, sc);
-    if (threadIdx.x == 0) {
-        if (total > (unsigned)kTopkCap || cnt < k) atomicAdd(ts.overflow, 1u);
-        ts.cand_count[img] = 0;
+    if (blockIdx.x * 64u < cnt) {
+        for (unsigned j = tid; j < cnt; j += kRankThreads) keys[j] = __ldcg(cand + j);
+        const unsigned slot = tid & 63u, part = tid >> 6;
+        const unsigned j0 = (unsigned)(((unsigned long long)cnt * part) >> 2), j1 = (unsigned)(((unsigned long long)cnt * (part + 1)) >> 2);
+        for (unsigned base = blockIdx.x * 64u; base < cnt; base += gridDim.x * 64u) {
+            if (tid < 64u) rank[tid] = 0u;
+            __syncthreads();   // keys (first round) and rank[] ready
+            const unsigned i = base + slot;
+            if (i < cnt) {
+                const unsigned long long mine = keys[i];
+                unsigned above = 0;
+#pragma unroll 8
+                for (unsigned j = j0; j < j1; ++j) above += (keys[j] > mine) ? 1u : 0u;   // broadcast reads
+                atomicAdd(&rank[slot], above);
+            }
+            __syncthreads();
+            if (tid < 64u && i < cnt && rank[tid] < k) out[rank[tid]] = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
+            __syncthreads();
+        }
+    }
+    if (blockIdx.x == 0)   // fewer candidates than ranks asked for (reported as overflow): defined output
+        for (unsigned r = cnt + tid; r < k; r += kRankThreads) out[r] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ts.ticket + img, 1u) == gridDim.x - 1) {   // every CTA of the image has read the counters
+            if (total > (unsigned)kTopkCap || cnt < k) atomicAdd(ts.overflow, 1u);
+            ts.cand_count[img] = 0;
+            ts.ticket[img] = 0;
+        }
     }
 }
 

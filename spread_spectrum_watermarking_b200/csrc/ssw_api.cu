@@ -68,7 +68,7 @@ struct ssw_ctx {
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     bool pdl = true;                       // SSW_PDL=0: no programmatic dependent launches
-    bool topk_fused = true;                // SSW_TOPK_FUSED=0: separate topk_block_bin + topk_collect kernels for every k
+    bool stage_rows = true;                // SSW_STAGE_ROWS=0: inverse row pass reads the original pixels straight from global memory
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     int row_variant = 0;                   // SSW_ROW_VARIANT (tuning builds)
     bool prefetch = false;                 // SSW_PREFETCH=1: cp.async-staged forward row pass (RowFwdPF)
@@ -176,7 +176,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_PDL")) c->pdl = atoi(s) != 0;
-    if (const char* s = getenv("SSW_TOPK_FUSED")) c->topk_fused = atoi(s) != 0;
+    if (const char* s = getenv("SSW_STAGE_ROWS")) c->stage_rows = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     if (const char* s = getenv("SSW_ROW_VARIANT")) c->row_variant = atoi(s);
     if (const char* s = getenv("SSW_PREFETCH")) c->prefetch = atoi(s) != 0;
@@ -594,7 +594,17 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
         a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
         apply_seg(c, &a);
         if (dst_type == PIX_PLANE) rc = launch_fast<fast::RowInv<P, G, PIX_PLANE, PIX_PLANE>>(c, "inv_rows_plane", a, w, h, batch);
-        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
+        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) {
+            bool staged = false;
+            if constexpr ((3 * P::N) % 16 == 0 && fast::RowInv<P, G, PIX_RGB8, PIX_RGB8, true>::SMEM <= fast::kMaxSmem) {
+                // original pixels staged with cp.async (rows are whole 16-byte chunks when the frame is 16-byte aligned)
+                if (c->stage_rows && aligned(d_src, 16)) {
+                    staged = true;
+                    rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8, true>>(c, "inv_rows", a, w, h, batch);
+                }
+            }
+            if (!staged) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
+        }
         else if (dst_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB32F>>(c, "inv_rows_src32f", a, w, h, batch);
         else if (src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB32F, PIX_RGB8>>(c, "inv_rows_rgb32f_src8", a, w, h, batch);
         else rc = launch_fast<fast::RowInv<P, G, PIX_RGB32F, PIX_RGB32F>>(c, "inv_rows_rgb32f", a, w, h, batch);
@@ -798,31 +808,29 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         TopkScratch ts = c->ts;
         ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0;
         ts.cand += (size_t)b0 * kTopkCap;
-        if (!full_hist && c->topk_fused && k <= (unsigned)kFusedMaxK && (unsigned)w * (unsigned)h >= (unsigned)kFusedMaxK) {
-            // short marks: every collect CTA bounds the k-th key itself from a small low-frequency block
-            KScope ks(c, "topk_bin_collect");
-            launch_pdl(c, topk_bin_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride,
-                       (unsigned)w, (unsigned)h, k, oc, ts);
-            CK(cudaGetLastError());
-            continue;
-        }
         if (full_hist) {
             KScope ks(c, "topk_hist");
             launch_pdl(c, topk_hist_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
         } else {
             KScope ks(c, "topk_block_bin");
-            launch_pdl(c, topk_block_bin_kernel, dim3(16, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
+            launch_pdl(c, topk_block_bin_kernel, dim3(nb), kBinThreads, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
         { KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts); }
         CK(cudaGetLastError());
     }
-    const void* key = (const void*)topk_sort_kernel;
+    const void* key = (const void*)topk_rank_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
     if (c->smem_attr.find(key) == c->smem_attr.end()) {
-        CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(topk_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    { KScope ks(c, "topk_sort"); launch_pdl(c, topk_sort_kernel, batch, kSortThreads, smem, c->stream, c->ts, k, d_idx, idx_stride); }
+    for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
+        const unsigned nb = std::min(65535u, batch - b0);
+        TopkScratch ts = c->ts;
+        ts.ticket += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap;
+        KScope ks(c, "topk_rank");
+        launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, nb), kRankThreads, smem, c->stream, ts, k, d_idx + (long long)b0 * idx_stride, idx_stride);
+    }
     CK(cudaGetLastError());
     return SSW_OK;
 }
@@ -1812,7 +1820,7 @@ extern "C" int ssw_shard_topk_bin_dev(ssw_ctx* c, const float* plane, const ssw_
     {
         KScope ks(c, "topk_block_bin");
         // local plane [ncols][height]: "width" of the block kernel is the local line length
-        launch_pdl(c, topk_block_bin_kernel, dim3(16, 1), 512, 0, c->stream, plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
+        launch_pdl(c, topk_block_bin_kernel, dim3(1), kBinThreads, 0, c->stream, plane, 0, sh->height, sh->ncols, (unsigned)k, oc, ts);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -1858,13 +1866,13 @@ extern "C" int ssw_shard_topk_merge_dev(ssw_ctx* c, const uint64_t* lists_dev, c
         KScope ks(c, "topk_concat");
         launch_pdl(c, topk_concat_kernel, 1, 256, 0, c->stream, (const unsigned long long*)lists_dev, counts_dev, n_lists, (unsigned)kTopkCap, ts);
     }
-    const void* key = (const void*)topk_sort_kernel;
+    const void* key = (const void*)topk_rank_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
     if (c->smem_attr.find(key) == c->smem_attr.end()) {
-        CK(cudaFuncSetAttribute(topk_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(topk_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    { KScope ks(c, "topk_sort"); launch_pdl(c, topk_sort_kernel, 1, kSortThreads, smem, c->stream, ts, (unsigned)k, idx_dev, 0); }
+    { KScope ks(c, "topk_rank"); launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, 1), kRankThreads, smem, c->stream, ts, (unsigned)k, idx_dev, 0); }
     CK(cudaGetLastError());
     return SSW_OK;
 }

@@ -9,7 +9,7 @@ import sys
 
 NAMES = [('RowFwd', 'fwd_rows'), ('RowInv', 'inv_rows'), ('ColPass', None), ('Line1Fwd', 'fwd_line1'), ('Line1Inv', 'inv_line1'),
          ('topk_collect', 'topk_collect'), ('topk_hist', 'topk_hist'), ('topk_block_bin', 'topk_block_bin'),
-         ('topk_sort', 'topk_sort'), ('similarity_bank', 'similarity_bank'), ('transpose_kernel', 'transpose')]
+         ('topk_rank', 'topk_rank'), ('similarity_bank', 'similarity_bank'), ('transpose_kernel', 'transpose')]
 UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 
 raw = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
