@@ -332,20 +332,15 @@ SSW_HD void load_luma4(const void* src, long long pix4 /* index of the first of 
 }
 
 // 4 pixels of one row: new luma y[4] (+ chroma of the original pixels) -> destination
-// `staged` != nullptr: the 12 source bytes of these 4 pixels were copied to shared memory (3 words at staged[0..2])
 template <int DST, int SRC>
-SSW_HD void store_pix4(const void* src, void* dst, long long pix4, const float* y, const unsigned* staged = nullptr) {
+SSW_HD void store_pix4(const void* src, void* dst, long long pix4, const float* y) {
     if constexpr (DST == PIX_PLANE) {
         st4((float*)dst + pix4, y[0], y[1], y[2], y[3]);
     } else {
         float c[12];
         if constexpr (SRC == PIX_RGB8) {
-            if (staged) {
-                unpack4_unit(staged[0], staged[1], staged[2], c);
-            } else {
-                const unsigned* p = (const unsigned*)((const unsigned char*)src + 3 * pix4);
-                unpack4_unit(ldw(p), ldw(p + 1), ldw(p + 2), c);
-            }
+            const unsigned* p = (const unsigned*)((const unsigned char*)src + 3 * pix4);
+            unpack4_unit(ldw(p), ldw(p + 1), ldw(p + 2), c);
         } else {
             const float* p = (const float*)src + 3 * pix4;
             const f4 v0 = ld4(p), v1 = ld4(p + 4), v2 = ld4(p + 8);
@@ -479,40 +474,14 @@ struct RowFwd {
     }
 };
 
-// asynchronous global -> shared copies (LDGSTS: no registers, no scoreboard stall)
-SSW_HD void async_copy16(void* smem_dst, const void* gmem_src) {
-#if defined(__CUDA_ARCH__)
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-#else
-    __builtin_memcpy(smem_dst, gmem_src, 16);
-#endif
-}
-SSW_HD void async_commit_wait_all() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#endif
-}
-SSW_HD void async_wait_all() {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#endif
-}
-
 // ------------------------------------------------------------------------------------------------
 // inverse row pass: plane rows -> DCT-III along x -> scale -> plane | Y' + I,Q(original pixels) -> RGB
 // ------------------------------------------------------------------------------------------------
-// PF_ (RGB8 -> RGB8 only): the original pixels of the tile's rows, needed by the last phase for I and Q, are
-// copied to a shared-memory staging area with cp.async at the start of the kernel, so their HBM latency hides
-// behind the transform instead of stalling the output phase (23 % of that kernel's stall samples).
-template <class P_, int G_, int DST_, int SRC_, bool PF_ = false>
+template <class P_, int G_, int DST_, int SRC_>
 struct RowInv {
     using P = P_;
-    static_assert(!PF_ || (DST_ == PIX_RGB8 && SRC_ == PIX_RGB8), "staged source rows: RGB8 only (callers check (3 N) % 16 == 0)");
     static constexpr int G = G_, DST = DST_, SRC = SRC_, THREADS = G_ * P_::T, NPH = 2 + 2 * P_::NST;
-    static constexpr bool PF = PF_;
-    static constexpr int ROW_BYTES = 3 * P_::N, FFT_BYTES = G_ * P_::PITCH * (int)sizeof(cplx);
-    static constexpr int SMEM = FFT_BYTES + (PF_ ? G_ * 2 * ROW_BYTES : 0);
+    static constexpr int SMEM = G_ * P_::PITCH * (int)sizeof(cplx);
     static constexpr int MINB = 0;
     using Thread = ThreadState<P_>;
     static int tiles_per_image(int w, int h) { (void)w; return ((h + 1) / 2 + G - 1) / G; }
@@ -526,16 +495,6 @@ struct RowInv {
         const int ra = 2 * ((tile - img * a.tiles_per_image) * G + g), rb = ra + 1;
         const bool ha = ra < a.h, hb = rb < a.h;
         if constexpr (PH == 0) {
-            if constexpr (PF) {   // stage the 2G source rows of the tile (all threads of the CTA)
-                constexpr int CH = ROW_BYTES / 16;
-                const int row0 = 2 * ((tile - img * a.tiles_per_image) * G);
-                const unsigned char* srcb = (const unsigned char*)image_base<SRC>(a.src, img, a.src_stride) + 3 * ((long long)row0 * N);
-                unsigned char* stage = (unsigned char*)smem + FFT_BYTES;
-                for (int e = tid; e < 2 * G * CH; e += THREADS) {
-                    const int r = e / CH, ch = e - r * CH;
-                    if (row0 + r < a.h) async_copy16(stage + r * ROW_BYTES + 16 * ch, srcb + (long long)r * ROW_BYTES + 16 * ch);
-                }
-            }
             const float* ia = a.plane + img * a.plane_stride + (long long)ra * N;
             const float* ib = ia + N;
             const bool seg = a.seg_shift >= 0;   // coefficient lines held as all-to-all blocks (sharded frames)
@@ -557,18 +516,11 @@ struct RowInv {
             }
         } else if constexpr (PH < NPH - 1) {
             fft_phase<P, PH>(s, a.tw, t, th.v);
-            if constexpr (PF && PH == NPH - 2) async_wait_all();   // own copies landed; the barrier publishes everybody's
         } else {
             if (!ha) return;
             const void* src = (DST == PIX_PLANE) ? nullptr : image_base<SRC>(a.src, img, a.src_stride);
             void* dst = const_cast<void*>(image_base<DST>(a.dst, img, a.dst_stride));
             const long long row = (long long)ra * N;
-            const unsigned* sa = nullptr;
-            const unsigned* sb = nullptr;
-            if constexpr (PF) {
-                sa = (const unsigned*)((const unsigned char*)smem + FFT_BYTES + (2 * g) * ROW_BYTES);
-                sb = (const unsigned*)((const unsigned char*)sa + ROW_BYTES);
-            }
 #pragma unroll
             for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
                 const int u = t + it * T;
@@ -578,8 +530,8 @@ struct RowInv {
                     float ya[4], yb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { ya[i] = f[i].x * a.scale0; yb[i] = -f[i].y * a.scale0; }
-                    store_pix4<DST, SRC>(src, dst, row + 4 * u, ya, PF ? sa + 3 * u : nullptr);
-                    if (hb) store_pix4<DST, SRC>(src, dst, row + N + 4 * u, yb, PF ? sb + 3 * u : nullptr);
+                    store_pix4<DST, SRC>(src, dst, row + 4 * u, ya);
+                    if (hb) store_pix4<DST, SRC>(src, dst, row + N + 4 * u, yb);
                 }
             }
         }
@@ -809,6 +761,20 @@ struct Line1Inv {
 // cp.async (LDGSTS, no registers, no scoreboard stall), so only the first tile of a CTA waits for HBM.
 // Shared memory: G line-pair buffers + G * 2 rows * 3N bytes of staging.
 // ------------------------------------------------------------------------------------------------
+SSW_HD void async_copy16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+    __builtin_memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+SSW_HD void async_commit_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 template <class P_, int G_>
 struct RowFwdPF {
     using P = P_;

@@ -68,7 +68,6 @@ struct ssw_ctx {
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     bool pdl = true;                       // SSW_PDL=0: no programmatic dependent launches
-    bool stage_rows = true;                // SSW_STAGE_ROWS=0: inverse row pass reads the original pixels straight from global memory
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     int row_variant = 0;                   // SSW_ROW_VARIANT (tuning builds)
     bool prefetch = false;                 // SSW_PREFETCH=1: cp.async-staged forward row pass (RowFwdPF)
@@ -176,7 +175,6 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_PDL")) c->pdl = atoi(s) != 0;
-    if (const char* s = getenv("SSW_STAGE_ROWS")) c->stage_rows = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     if (const char* s = getenv("SSW_ROW_VARIANT")) c->row_variant = atoi(s);
     if (const char* s = getenv("SSW_PREFETCH")) c->prefetch = atoi(s) != 0;
@@ -594,17 +592,7 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
         a.src = d_src; a.plane = d_plane; a.dst = d_dst; a.scale0 = scale;
         apply_seg(c, &a);
         if (dst_type == PIX_PLANE) rc = launch_fast<fast::RowInv<P, G, PIX_PLANE, PIX_PLANE>>(c, "inv_rows_plane", a, w, h, batch);
-        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) {
-            bool staged = false;
-            if constexpr ((3 * P::N) % 16 == 0 && fast::RowInv<P, G, PIX_RGB8, PIX_RGB8, true>::SMEM <= fast::kMaxSmem) {
-                // original pixels staged with cp.async (rows are whole 16-byte chunks when the frame is 16-byte aligned)
-                if (c->stage_rows && aligned(d_src, 16)) {
-                    staged = true;
-                    rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8, true>>(c, "inv_rows", a, w, h, batch);
-                }
-            }
-            if (!staged) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
-        }
+        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB8>>(c, "inv_rows", a, w, h, batch);
         else if (dst_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB8, PIX_RGB32F>>(c, "inv_rows_src32f", a, w, h, batch);
         else if (src_type == PIX_RGB8) rc = launch_fast<fast::RowInv<P, G, PIX_RGB32F, PIX_RGB8>>(c, "inv_rows_rgb32f_src8", a, w, h, batch);
         else rc = launch_fast<fast::RowInv<P, G, PIX_RGB32F, PIX_RGB32F>>(c, "inv_rows_rgb32f", a, w, h, batch);

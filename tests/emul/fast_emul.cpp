@@ -139,15 +139,7 @@ int emul_fast_row_inv(int dst_type, int src_type, float* plane, const void* src,
             emulate<K>(a, a.tiles_per_image * batch);
         };
         if (dst_type == PIX_PLANE) run(RowInv<P, G, PIX_PLANE, PIX_PLANE>{});
-        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) {
-            // the cp.async-staged variant is what the device runs for 16-byte aligned frames; emulate it when it applies
-            if constexpr ((3 * P::N) % 16 == 0 && RowInv<P, G, PIX_RGB8, PIX_RGB8, true>::SMEM <= kMaxSmem) {
-                if ((((size_t)src) & 15) == 0) run(RowInv<P, G, PIX_RGB8, PIX_RGB8, true>{});
-                else run(RowInv<P, G, PIX_RGB8, PIX_RGB8>{});
-            } else {
-                run(RowInv<P, G, PIX_RGB8, PIX_RGB8>{});
-            }
-        }
+        else if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) run(RowInv<P, G, PIX_RGB8, PIX_RGB8>{});
         else if (dst_type == PIX_RGB8) run(RowInv<P, G, PIX_RGB8, PIX_RGB32F>{});
         else if (src_type == PIX_RGB8) run(RowInv<P, G, PIX_RGB32F, PIX_RGB8>{});
         else run(RowInv<P, G, PIX_RGB32F, PIX_RGB32F>{});
