@@ -92,13 +92,38 @@ def load_traffic():
 # clocks sampler (nvidia-smi during the timed region)
 # ------------------------------------------------------------------------------------------------
 class Clocks:
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md: start before, stop after).
+    Sampler: NVML in this process (the library behind nvidia-smi; three cheap queries every 50 ms, initialised
+    before the warm-up).  The nvidia-smi CLI polled with -lms was observed to stall the device for 10-40 ms now
+    and then (2 of 19 runs: a 270 us step measured as 470-520 us, only in the loop it sampled); it remains
+    the fallback when NVML cannot be loaded."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         self.index, self.proc, self.rows = index, None, []
+        self.nvml, self.handle, self.t, self.stop_flag, self.max_query_ms = None, None, None, False, 0.0
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '200'],
@@ -108,26 +133,44 @@ class Clocks:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = (('hw_slowdown', n.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ('sw_thermal_slowdown', n.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', n.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            t0 = time.perf_counter()
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([sm, self.mx, None] + ['Active' if mask & bit else 'Not Active' for _, bit in names])
+            except Exception:
+                pass
+            self.max_query_ms = max(self.max_query_ms, (time.perf_counter() - t0) * 1e3)
+            time.sleep(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(',')])
 
     def settle(self, timeout=5.0):
-        """Block until the sampler has delivered its first row: nvidia-smi's start-up (NVML initialisation takes driver
-        locks for ~100 ms) must be over before the warm-up begins, or it lands inside a timed region of a few ms."""
+        """Block until the sampler has delivered its first row (NVML / nvidia-smi start-up takes driver locks)."""
         t0 = time.time()
-        while self.proc and not self.rows and time.time() - t0 < timeout and self.proc.poll() is None:
+        while not self.rows and time.time() - t0 < timeout and (self.nvml or (self.proc and self.proc.poll() is None)):
             time.sleep(0.01)
 
     def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        if not self.nvml and not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampler unavailable']}
         time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -135,10 +178,13 @@ class Clocks:
             except Exception:
                 continue
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
+                if str(v).lower().startswith('active'):
                     reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+        out = {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+               'samples': len(sm), 'reasons': sorted(reasons), 'sampler': 'nvml' if self.nvml else 'nvidia-smi -lms 200'}
+        if self.nvml:
+            out['max_query_ms'] = round(self.max_query_ms, 3)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

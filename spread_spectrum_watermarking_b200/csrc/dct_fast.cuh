@@ -71,6 +71,7 @@ struct FastArgs {
     // sample m of line l lives at (((c*ranks + g)*lines + l) << seg_shift) + (m & (seg_len-1)) with
     // s = m >> seg_shift, g = s >> chunk_shift, c = s & (chunks-1)      (seg_len and chunks: powers of two)
     int seg_shift, chunk_shift, seg_ranks, seg_lines;
+    int pdl_late;   // 0: release the dependent grid at the first instruction; 1: before the last phase (see pdl.cuh)
     int dbg_skip;   // tuning builds only (-DSSW_TUNE): 1 = no global loads, 2 = no global stores, 4 = no FFT stages
 };
 
@@ -854,9 +855,11 @@ __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel(const
     // loop state cost registers in the widest kernels.)
     extern __shared__ __align__(16) unsigned char fast_smem[];
     typename K::Thread th;
-    pdl_enter();
+    if (!a.pdl_late) pdl_trigger();
+    pdl_wait();
     static_for<K::NPH>([&](auto ph) {
         constexpr int p = decltype(ph)::value;
+        if constexpr (p == K::NPH - 1) { if (a.pdl_late) pdl_trigger(); }   // only the output phase is left
         K::template phase<p>(a, (cplx*)fast_smem, blockIdx.x, threadIdx.x, th);
         if constexpr (p + 1 < K::NPH) __syncthreads();
     });
@@ -867,7 +870,8 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel_pf(const __grid_constant__ FastArgs a) {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     typename K::Thread th;
-    pdl_enter();
+    if (!a.pdl_late) pdl_trigger();
+    pdl_wait();
     int tile = blockIdx.x * a.tiles_per_cta;
     const int end = min(tile + a.tiles_per_cta, a.total_tiles);
     if (tile < end) K::prefetch(a, (cplx*)fast_smem, tile, threadIdx.x);
@@ -879,6 +883,7 @@ __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fast_kernel_pf(co
         if (tile + 1 < end) K::prefetch(a, (cplx*)fast_smem, tile + 1, threadIdx.x);
         static_for<K::NPH - 1>([&](auto ph) {
             constexpr int p = decltype(ph)::value + 1;
+            if constexpr (p == K::NPH - 1) { if (a.pdl_late && tile + 1 == end) pdl_trigger(); }
             K::template phase<p>(a, (cplx*)fast_smem, tile, threadIdx.x, th);
             __syncthreads();
         });

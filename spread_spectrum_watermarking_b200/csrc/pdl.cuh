@@ -10,11 +10,24 @@
 
 namespace ssw {
 
-__device__ __forceinline__ void pdl_enter() {
+// 1: the short kernels (ordering, scatter/gather, similarity) release their dependents at their first instruction;
+// 0: implicitly when they exit.  Written once per context (ssw_ctx_create), read-only for kernels.
+__device__ int g_pdl_small_early = 1;
+
+__device__ __forceinline__ void pdl_trigger() {
 #if defined(__CUDA_ARCH__)
     asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
+}
+
+__device__ __forceinline__ void pdl_enter() {
+    if (g_pdl_small_early) pdl_trigger();
+    pdl_wait();
 }
 
 }  // namespace ssw

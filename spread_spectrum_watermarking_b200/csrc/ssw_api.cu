@@ -68,6 +68,9 @@ struct ssw_ctx {
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     bool pdl = true;                       // SSW_PDL=0: no programmatic dependent launches
+    int pdl_mode = 1;                      // SSW_PDL_MODE: 0 dependents released at kernel start everywhere; 1 (default) line kernels
+                                           // before their output phase, short kernels at exit; 2 line kernels late, short kernels at start
+                                           // (C2 step, 4 fresh processes each: 270.2 / 265.8 / 270.3 us)
     int col_variant = 0;                   // SSW_COL_VARIANT (tuning builds, -DSSW_TUNE)
     int row_variant = 0;                   // SSW_ROW_VARIANT (tuning builds)
     bool prefetch = false;                 // SSW_PREFETCH=1: cp.async-staged forward row pass (RowFwdPF)
@@ -84,7 +87,9 @@ struct ssw_ctx {
     int max_smem = 227 * 1024;
     unsigned* h_flag = nullptr;  // pinned
     int last_fallbacks = 0;
-    size_t chunk_bytes = 96u << 20;  // planes of one fused sub-batch are sized to stay L2-resident
+    // planes of one fused sub-batch.  Sub-batches that stay L2-resident (96 MB) were the better choice before the
+    // programmatic launches; now larger launches win (C3, 64 x 1080p: 96 MB 34.7, 320 MB 38.0, 640 MB 38.8, 1100 MB 39.4 Gpix/s)
+    size_t chunk_bytes = (size_t)2 << 30;
     // per-kernel CUDA-event profiling (bench.py roofline attribution); off by default
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t a, b; };
@@ -175,6 +180,11 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_CHUNK_MB")) c->chunk_bytes = (size_t)atoll(s) << 20;
     if (const char* s = getenv("SSW_NO_FAST")) c->use_fast = atoi(s) == 0;
     if (const char* s = getenv("SSW_PDL")) c->pdl = atoi(s) != 0;
+    if (const char* s = getenv("SSW_PDL_MODE")) c->pdl_mode = atoi(s);
+    {
+        const int small_early = (c->pdl_mode == 1) ? 0 : 1;
+        CK(cudaMemcpyToSymbol(g_pdl_small_early, &small_early, sizeof(int)));
+    }
     if (const char* s = getenv("SSW_COL_VARIANT")) c->col_variant = atoi(s);
     if (const char* s = getenv("SSW_ROW_VARIANT")) c->row_variant = atoi(s);
     if (const char* s = getenv("SSW_PREFETCH")) c->prefetch = atoi(s) != 0;
@@ -412,6 +422,7 @@ static int launch_fast(ssw_ctx* c, const char* name, fast::FastArgs a, int w, in
     if (LINE1) CKS(line1_tables<typename K::P>(c, &a.tw, &a.t4));
     else CKS(fast_tables<typename K::P>(c, &a.tw, &a.t4));
     a.tiles_per_image = K::tiles_per_image(w, h);
+    a.pdl_late = c->pdl_mode != 0;
     const long long tiles = (long long)a.tiles_per_image * batch;
     if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
     auto kernel = fast::fast_kernel<K>;
@@ -433,6 +444,7 @@ template <class K>
 static int launch_fast_pf(ssw_ctx* c, const char* name, fast::FastArgs a, int w, int h, int batch) {
     CKS(fast_tables<typename K::P>(c, &a.tw, &a.t4));
     a.tiles_per_image = K::tiles_per_image(w, h);
+    a.pdl_late = c->pdl_mode != 0;
     const long long tiles = (long long)a.tiles_per_image * batch;
     if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
     auto kernel = fast::fast_kernel_pf<K>;

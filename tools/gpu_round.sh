@@ -20,6 +20,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fast_kernel|topk_|similarity' -s 60 -c 20 -f -o $OUT/prof_$TAG \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 if [ "$2" == "ref" ]; then
-  SSW_REF_BUDGET_S=100 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
+  SSW_REF_BUDGET_S=60 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
 fi
 ls $OUT | wc -l
