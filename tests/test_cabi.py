@@ -121,3 +121,30 @@ def test_host_side_image_and_mark_adapters(wm):
     assert wm._mark_data(m) is m.data() or (wm._mark_data(m) == m.data()).all()
     s = wm.Similarity(6.5)
     assert s.exceeds_sigma(6.0) and not s.exceeds_sigma(6.5)      # strict >, src/algorithm.rs:677-679
+
+
+def test_every_pdl_launched_kernel_waits_before_touching_memory():
+    """launch_pdl (programmatic stream serialization) lets a grid start while its predecessor drains, so every kernel
+    that goes through it MUST begin with pdl_enter() / pdl_wait() (csrc/pdl.cuh).  Static check of the sources:
+    each kernel named at a launch_pdl call site has the wait as its first statement."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'spread_spectrum_watermarking_b200', 'csrc')
+    src = {f: open(os.path.join(root, f)).read() for f in os.listdir(root) if f.endswith(('.cu', '.cuh', '.h'))}
+    api = src['ssw_api.cu']
+    launched = set(re.findall(r'launch_pdl\(c,\s*([A-Za-z_0-9]+)\s*,', api))
+    launched.discard('kernel')   # the template wrappers fast_kernel / fast_kernel_pf, checked below
+    assert len(launched) >= 10, launched
+    all_src = '\n'.join(src.values())
+    for k in sorted(launched):
+        m = re.search(r'\b' + k + r'\s*\([^{;]*\)\s*\{\s*(?://[^\n]*\n\s*)*(\w+)\(\);', all_src)
+        assert m, 'definition of %s not found' % k
+        assert m.group(1) in ('pdl_enter', 'pdl_wait'), '%s starts with %s' % (k, m.group(1))
+    for wrapper in ('fast_kernel', 'fast_kernel_pf'):
+        body = src['dct_fast.cuh'].split('fast::' + wrapper)[0] if False else src['dct_fast.cuh']
+        i = body.index(wrapper + '(const __grid_constant__ FastArgs a)')
+        head = body[i:i + 600]
+        assert 'pdl_wait();' in head and head.index('pdl_wait();') < head.index('phase<'), wrapper
+    # and nothing else is launched with the attribute: the generic fallback kernels keep <<< >>>
+    assert 'cudaLaunchAttributeProgrammaticStreamSerialization' not in all_src.replace(api, '')
+    assert api.count('cudaLaunchAttributeProgrammaticStreamSerialization') == 1
