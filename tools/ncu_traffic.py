@@ -4,6 +4,7 @@ profiles/dram_traffic.json (bench.py's roofline.traffic).  Usage: python tools/n
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 
@@ -24,7 +25,9 @@ for r in rows[2:]:
         if pat in k:
             name = nm
             if pat == 'ColPass':
-                name = 'inv_cols' if '(bool)1' in k else 'fwd_cols'
+                # ColPass<Plan<...>, G, TEAMS, INVERSE, MINB>: ncu prints the bool as (bool)1 or as 1 depending on the version
+                m = re.search(r'ColPass<.*>,\s*\d+,\s*\d+,\s*(?:\(bool\))?(\d),\s*\d+>\s*>', k)
+                name = 'inv_cols' if (m and m.group(1) == '1') else 'fwd_cols'
             break
     if not name:
         continue
