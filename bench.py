@@ -42,6 +42,31 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault('NCCL_DEBUG', 'WARN')
 os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
+# ... and because NCCL prints that banner with a plain printf to fd 1 whatever NCCL_DEBUG_FILE says (seen on every
+# multi-GPU run), fd 1 itself points at stderr while the benchmark runs; emit() restores it for the one JSON line.
+_REAL_STDOUT_FD = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    """print the one JSON line on the real stdout"""
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+        os.close(_REAL_STDOUT_FD)
+        _REAL_STDOUT_FD = None
+    sys.stdout.write(json.dumps(obj) + '\n')
+    sys.stdout.flush()
+
+
 MARK_LEN = 1000
 ALPHA = 0.1
 BANK_MARKS = 100000   # BASELINE.json configs[4]: bank of 100k stored marks of length 1000
@@ -300,7 +325,7 @@ def run_reference(args, wl):
     sample = ('each step = %d frames (one per host thread) of %dx%d embed+extract by the restated reference '
               '(oracle/ssw_oracle.c, full stable sort); %d of %d requested steps fitted the %.0f s budget'
               % (cores, wl['w'], wl['h'], k, args.steps, budget))
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': v, 'unit': 'Mpix/s',
         'n_gpus': args.gpus, 'steps': k, 'warmup': warm, 'ms_per_step': total / k * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -309,7 +334,7 @@ def run_reference(args, wl):
         'cpu_baseline': {'value': v, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -543,7 +568,7 @@ def run_ours(args, wl):
         cpu = cpu_baseline(wl, f0, [marks_h[i] for i in range(len(f0))])
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
             'regions_ms_per_step': [round(m / K, 6) for m in ms_regions],
@@ -560,7 +585,7 @@ def run_ours(args, wl):
             'roofline': roofline, 'kernels': kernels, 'whole_step': dict(step_algo, **whole),
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk,
             'min_similarity': float(sims.min()),
-        }), flush=True)
+        })
     if bank is not None:
         bank.close()
     ctx.close()
@@ -722,7 +747,7 @@ def run_c4(args, wl):
            'd2h_bytes_per_step': fb + MARK_LEN * 4, 'steps': Ke, 'ms_per_step': e2e_ms / Ke,
            'api': 'sharded.ShardedWriter.mark_rgb8 + ShardedReader.extract (per-rank rows in pinned host memory)'}
     if rank == 0:
-        print(json.dumps({
+        emit({
             'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -733,7 +758,7 @@ def run_c4(args, wl):
                                       '(2 per embed, 1 per image per extract), distributed top-k' % world},
             'roofline': roofline, 'kernels': kernels, 'kernel_ms_per_step': kernel_ms,
             'cpu_baseline': None, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'similarity': sim,
-        }), flush=True)
+        })
     state.clear()
     if world > 1:
         dist.destroy_process_group()
@@ -758,6 +783,7 @@ def main():
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29533')] + sys.argv
         raise SystemExit(subprocess.call(cmd))
+    protect_stdout()
     if args.workload == 'c4':
         return run_c4(args, wl)
     run_ours(args, wl)
