@@ -36,11 +36,40 @@ struct DctPlanDev {
 };
 
 SSW_HD cplx mk(float x, float y) { cplx c; c.x = x; c.y = y; return c; }
+// Complex arithmetic.  On the device every operation is written with the packed FP32 instructions of sm_100
+// (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2): a complex number is one 64-bit register pair, ptxas folds the
+// lane swaps / per-lane negations / scalar broadcasts below into operand modifiers (R.F32x2.LO_HI.NP, R.F32),
+// so a complex add is ONE instruction and a complex multiply TWO (instead of 2 and 4).  Same flop rate as the
+// scalar forms, half the issue slots -- the line kernels are issue-bound, not FMA-pipe-bound.
+// The host forms (tests/emul, built with -ffp-contract=off) round every product separately; the device forms
+// round a.x*b first and fuse the second product -- both are within the 1e-5 coefficient tolerance of the oracle.
+#if defined(__CUDA_ARCH__)
+#define SSW_PACKED 1
+SSW_HD cplx cadd(cplx a, cplx b) { return __fadd2_rn(a, b); }
+SSW_HD cplx csub(cplx a, cplx b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+SSW_HD cplx cbc(float v) { return make_float2(v, v); }                    // broadcast
+SSW_HD cplx cswap_np(cplx a) { return make_float2(-a.y, a.x); }           // a * (+i)
+SSW_HD cplx cswap_pn(cplx a) { return make_float2(a.y, -a.x); }           // a * (-i)
+SSW_HD cplx cscale2(cplx a, float f) { return __fmul2_rn(a, cbc(f)); }
+SSW_HD cplx cfma_s(cplx a, float f, cplx c) { return __ffma2_rn(a, cbc(f), c); }   // a*f + c
+SSW_HD cplx cmul_lanes(cplx a, float fx, float fy) { return __fmul2_rn(a, make_float2(fx, fy)); }   // (a.x*fx, a.y*fy)
+// the same with the products rounded on their own whatever follows (nz = -0.0f at run time: ptxas contracts FMUL2 + FADD2)
+SSW_HD cplx cmul_lanes_x(cplx a, float fx, float fy, float nz) { return __ffma2_rn(a, make_float2(fx, fy), make_float2(nz, nz)); }
+// a * b = b.x * a + b.y * (i a)
+SSW_HD cplx cmul(cplx a, cplx b) { return __ffma2_rn(cswap_np(a), cbc(b.y), __fmul2_rn(a, cbc(b.x))); }
+SSW_HD cplx mul_mi(cplx a) { return cswap_pn(a); }  // a * (-i)
+SSW_HD cplx mul_pi(cplx a) { return cswap_np(a); }  // a * (+i)
+#else
 SSW_HD cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
 SSW_HD cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+SSW_HD cplx cscale2(cplx a, float f) { return mk(a.x * f, a.y * f); }
+SSW_HD cplx cfma_s(cplx a, float f, cplx c) { return mk(a.x * f + c.x, a.y * f + c.y); }
+SSW_HD cplx cmul_lanes(cplx a, float fx, float fy) { return mk(a.x * fx, a.y * fy); }
+SSW_HD cplx cmul_lanes_x(cplx a, float fx, float fy, float nz) { (void)nz; return mk(a.x * fx, a.y * fy); }
 SSW_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 SSW_HD cplx mul_mi(cplx a) { return mk(a.y, -a.x); }  // a * (-i)
 SSW_HD cplx mul_pi(cplx a) { return mk(-a.y, a.x); }  // a * (+i)
+#endif
 SSW_HD int padi(int a) { return a + (a >> 5); }
 
 SSW_HD unsigned fastdiv(unsigned j, unsigned magic) {
@@ -64,8 +93,8 @@ SSW_HD cplx tw_mul(cplx v) {
     else if constexpr (4 * m == R) return mul_mi(v);
     else if constexpr (2 * m == R) return mk(-v.x, -v.y);
     else if constexpr (4 * m == 3 * R) return mul_pi(v);
-    else if constexpr (8 * m == R) { const float h = 0.70710678118654752440f; return mk((v.x + v.y) * h, (v.y - v.x) * h); }
-    else if constexpr (8 * m == 3 * R) { const float h = 0.70710678118654752440f; return mk((v.y - v.x) * h, -(v.x + v.y) * h); }
+    else if constexpr (8 * m == R) { const float h = 0.70710678118654752440f; return cscale2(cadd(v, mul_mi(v)), h); }        // (1-i)/sqrt2
+    else if constexpr (8 * m == 3 * R) { const float h = 0.70710678118654752440f; return cscale2(csub(mul_mi(v), v), h); }   // (-1-i)/sqrt2
     else if constexpr (R == 16 && m == 1) return cmul(v, mk(0.92387953251128675613f, -0.38268343236508977173f));
     else if constexpr (R == 16 && m == 3) return cmul(v, mk(0.38268343236508977173f, -0.92387953251128675613f));
     else if constexpr (R == 16 && m == 9) return cmul(v, mk(-0.92387953251128675613f, 0.38268343236508977173f));
@@ -88,8 +117,8 @@ template <> struct Dft<3> {
         const float s = 0.86602540378443864676f;
         cplx t = cadd(x[1], x[2]);
         cplx d = csub(x[1], x[2]);
-        cplx m1 = mk(x[0].x - 0.5f * t.x, x[0].y - 0.5f * t.y);
-        cplx e = mk(s * d.y, -s * d.x);  // (-i*s)*d
+        cplx m1 = cfma_s(t, -0.5f, x[0]);
+        cplx e = cscale2(mul_mi(d), s);  // (-i*s)*d
         x[0] = cadd(x[0], t);
         x[1] = cadd(m1, e);
         x[2] = csub(m1, e);
@@ -109,15 +138,15 @@ template <> struct Dft<5> {
         const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
         cplx a1 = cadd(x[1], x[4]), a2 = cadd(x[2], x[3]);
         cplx b1 = csub(x[1], x[4]), b2 = csub(x[2], x[3]);
-        cplx r1 = mk(x[0].x + c1 * a1.x + c2 * a2.x, x[0].y + c1 * a1.y + c2 * a2.y);
-        cplx r2 = mk(x[0].x + c2 * a1.x + c1 * a2.x, x[0].y + c2 * a1.y + c1 * a2.y);
-        cplx i1 = mk(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
-        cplx i2 = mk(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+        cplx r1 = cfma_s(a2, c2, cfma_s(a1, c1, x[0]));
+        cplx r2 = cfma_s(a2, c1, cfma_s(a1, c2, x[0]));
+        cplx i1 = cfma_s(b2, s2, cscale2(b1, s1));
+        cplx i2 = cfma_s(b2, -s1, cscale2(b1, s2));
         x[0] = cadd(x[0], cadd(a1, a2));
-        x[1] = mk(r1.x + i1.y, r1.y - i1.x);
-        x[4] = mk(r1.x - i1.y, r1.y + i1.x);
-        x[2] = mk(r2.x + i2.y, r2.y - i2.x);
-        x[3] = mk(r2.x - i2.y, r2.y + i2.x);
+        x[1] = cadd(r1, mul_mi(i1));
+        x[4] = csub(r1, mul_mi(i1));
+        x[2] = cadd(r2, mul_mi(i2));
+        x[3] = csub(r2, mul_mi(i2));
     }
 };
 
@@ -279,13 +308,14 @@ SSW_HD void gstage_store(cplx* s, int n, int tpr, int tp, const GenericRegs& rg)
 //   out: xa_k, xb_k (position k) and xa_r, xb_r (position n-k; only valid if 0 < k and k != n-k)
 // ------------------------------------------------------------------------------------------------
 SSW_HD void dct2_post(cplx zk, cplx zr, cplx t, float& xa_k, float& xb_k, float& xa_r, float& xb_r) {
-    const float sr = zk.x + zr.x, si = zk.y - zr.y;  // S = Z[k] + conj(Z[n-k])
-    const float dr = zk.x - zr.x, di = zk.y + zr.y;  // D = Z[k] - conj(Z[n-k])
-    xa_k = t.x * sr - t.y * si;                      // Re(t S)
-    xb_k = t.x * di + t.y * dr;                      // Im(t D)
-    // t_{n-k} = -i conj(t_k) = (-t.y, -t.x);  S' = conj(S), D' = -conj(D)
-    xa_r = -t.y * sr - t.x * si;                     // Re(t' conj(S))
-    xb_r = t.x * dr - t.y * di;                      // Im(t' (-conj(D)))
+    // with S = Z[k] + conj(Z[n-k]) = (sr, si), D = Z[k] - conj(Z[n-k]) = (dr, di):
+    //   P = Z[k] + Z[n-k] = (sr, di),  Q = Z[k] - Z[n-k] = (dr, si)
+    //   (xa_k, xb_k) = (Re(t S), Im(t D))                     =  t.x P + t.y (i Q)
+    //   (xa_r, xb_r) = (Re(t' conj S), Im(t' (-conj D)))      = -t.y P + t.x (i Q),   t' = t_{n-k} = -i conj(t_k)
+    const cplx p = cadd(zk, zr), iq = mul_pi(csub(zk, zr));
+    const cplx a = cfma_s(iq, t.y, cscale2(p, t.x));
+    const cplx b = cfma_s(iq, t.x, cscale2(p, -t.y));
+    xa_k = a.x; xb_k = a.y; xa_r = b.x; xb_r = b.y;
 }
 
 // DCT-III pre pass: from the two coefficient lines to conj(Z) (so that a *forward* FFT yields
@@ -293,12 +323,12 @@ SSW_HD void dct2_post(cplx zk, cplx zr, cplx t, float& xa_k, float& xb_k, float&
 //   pa,pb = lines A,B at k;  qa,qb = lines A,B at n-k (0 when k == 0)
 //   zk -> index k, zr -> index n-k
 SSW_HD void dct3_pre(float pa, float pb, float qa, float qb, cplx t, cplx& zk, cplx& zr) {
-    // conjZ[k] = 1/4 t_k ((pa+qb) - i (pb-qa))
-    const float ur = 0.25f * (pa + qb), ui = -0.25f * (pb - qa);
-    zk = mk(t.x * ur - t.y * ui, t.x * ui + t.y * ur);
-    // conjZ[n-k] = 1/4 t_{n-k} ((qa+pb) - i (qb-pa)),  t_{n-k} = (-t.y, -t.x)
-    const float vr = 0.25f * (qa + pb), vi = -0.25f * (qb - pa);
-    zr = mk(-t.y * vr + t.x * vi, -t.y * vi - t.x * vr);
+    // conjZ[k]   = 1/4 t_k     ((pa+qb) - i (pb-qa)) = t_k     * 1/4 (conj(p) + swap(q))
+    // conjZ[n-k] = 1/4 t_{n-k} ((qa+pb) - i (qb-pa)) = t_{n-k} * 1/4 (conj(q) + swap(p)),  t_{n-k} = (-t.y, -t.x)
+    const cplx u = cscale2(cadd(mk(pa, -pb), mk(qb, qa)), 0.25f);
+    const cplx v = cscale2(cadd(mk(qa, -qb), mk(pb, pa)), 0.25f);
+    zk = cmul(u, t);
+    zr = cmul(v, mk(-t.y, -t.x));
 }
 
 }  // namespace ssw

@@ -73,6 +73,9 @@ struct FastArgs {
     int seg_shift, chunk_shift, seg_ranks, seg_lines;
     int pdl_late;   // 0: release the dependent grid at the first instruction; 1: before the last phase (see pdl.cuh)
     int dbg_skip;   // tuning builds only (-DSSW_TUNE): 1 = no global loads, 2 = no global stores, 4 = no FFT stages
+    float neg_zero; // -0.0f, deliberately a RUN-TIME value: fma.f32x2(m, c, -0) is the separately rounded product m*c that
+                    // the reference's un-fused colour arithmetic needs, in a form ptxas cannot contract with the following add
+                    // (it does contract mul.rn.f32x2 + add.rn.f32x2 into FFMA2, even under --fmad=false)
 };
 
 // position of 4 consecutive samples [m, m+4) of line `line` inside a segmented source
@@ -168,7 +171,8 @@ SSW_HD void stage_load(const cplx* s, int t, cplx* v) {
     }
 }
 
-template <class P, int S>
+// TWS: the twiddle table lives in shared memory (plain loads; __ldg is for global memory only)
+template <class P, int S, bool TWS = false>
 SSW_HD void stage_store(cplx* s, const cplx* tw, int t, cplx* v) {
     using I = StageInfo<P, S>;
 #pragma unroll
@@ -179,7 +183,7 @@ SSW_HD void stage_store(cplx* s, const cplx* tw, int t, cplx* v) {
             if constexpr (I::NS > 1) {
                 const cplx* twk = tw + I::TW + k;
 #pragma unroll
-                for (int r = 1; r < I::R; ++r) x[r] = cmul(x[r], SSW_LDG(twk + (r - 1) * I::NS));
+                for (int r = 1; r < I::R; ++r) x[r] = cmul(x[r], TWS ? twk[(r - 1) * I::NS] : SSW_LDG(twk + (r - 1) * I::NS));
             }
             Dft<I::R>::run(x);
             const int j0 = (j - k) * I::R + k;
@@ -194,11 +198,11 @@ SSW_HD void stage_store(cplx* s, const cplx* tw, int t, cplx* v) {
 }
 
 // phases 1 .. 2*NST of every kernel: the FFT of the team's line pair
-template <class P, int PH>
+template <class P, int PH, bool TWS = false>
 SSW_HD void fft_phase(cplx* s, const cplx* tw, int t, cplx* v) {
     constexpr int S = (PH - 1) / 2;
     if constexpr (((PH - 1) & 1) == 0) stage_load<P, S>(s, t, v);
-    else stage_store<P, S>(s, tw, t, v);
+    else stage_store<P, S, TWS>(s, tw, t, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -374,6 +378,117 @@ SSW_HD void store_pix4(const void* src, void* dst, long long pix4, const float* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two rows at once (device): lane x = row A, lane y = row B of the CTA's row pair, packed FP32 (FADD2 / FMUL2 /
+// FFMA2).  Every lane performs exactly the IEEE operations of the scalar helpers above -- separately rounded
+// products (fma(m, c, -0) == rn(m*c)), the same association -- so the results are bit-identical to them; the host
+// forms (tests/emul) simply call the scalar helpers per row.
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+SSW_HD float2 prod2(float m, float2 c, float nz) { return __ffma2_rn(make_float2(m, m), c, make_float2(nz, nz)); }   // rn(m*c) per lane
+SSW_HD float2 mat3x2(float m0, float m1, float m2, float2 a, float2 b, float2 c, float nz) {
+    return __fadd2_rn(__fadd2_rn(prod2(m0, a, nz), prod2(m1, b, nz)), prod2(m2, c, nz));
+}
+SSW_HD float2 unit_of2(float2 x) {
+    const float c_hi = 0.0039215688593685626983642578125f, c_lo = -2.31917579870781060424633324146270751953125e-10f;
+    return __ffma2_rn(x, make_float2(c_hi, c_hi), __fmul2_rn(x, make_float2(c_lo, c_lo)));
+}
+template <int J>
+SSW_HD float2 byte_to_float2(unsigned wa, unsigned wb) {
+    return __fadd2_rn(make_float2(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7540u + J)),
+                                  __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7540u + J))), make_float2(-8388608.0f, -8388608.0f));
+}
+SSW_HD void unpack4_unit2(const unsigned* wa, const unsigned* wb, float2* c) {
+    c[0] = unit_of2(byte_to_float2<0>(wa[0], wb[0])); c[1] = unit_of2(byte_to_float2<1>(wa[0], wb[0]));
+    c[2] = unit_of2(byte_to_float2<2>(wa[0], wb[0])); c[3] = unit_of2(byte_to_float2<3>(wa[0], wb[0]));
+    c[4] = unit_of2(byte_to_float2<0>(wa[1], wb[1])); c[5] = unit_of2(byte_to_float2<1>(wa[1], wb[1]));
+    c[6] = unit_of2(byte_to_float2<2>(wa[1], wb[1])); c[7] = unit_of2(byte_to_float2<3>(wa[1], wb[1]));
+    c[8] = unit_of2(byte_to_float2<0>(wa[2], wb[2])); c[9] = unit_of2(byte_to_float2<1>(wa[2], wb[2]));
+    c[10] = unit_of2(byte_to_float2<2>(wa[2], wb[2])); c[11] = unit_of2(byte_to_float2<3>(wa[2], wb[2]));
+}
+// four (A,B) pairs of unit values -> one RGB8 word per row
+SSW_HD void pack_u8x4x2(const float2* o, float nz, unsigned& wa, unsigned& wb) {
+    unsigned ma[4], mb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 c = make_float2(fminf(fmaxf(o[i].x, 0.0f), 1.0f), fminf(fmaxf(o[i].y, 0.0f), 1.0f));   // NaN -> 0
+        // the product must be rounded to f32 BEFORE the +0.5 (round half away from zero of the f32 value): prod2, not
+        // FMUL2 -- ptxas would contract FMUL2 + FADD2.RZ into one FFMA2.RZ
+        const float2 m = __fadd2_rz(__fadd2_rz(prod2(255.0f, c, nz), make_float2(0.5f, 0.5f)), make_float2(8388608.0f, 8388608.0f));
+        ma[i] = __float_as_uint(m.x); mb[i] = __float_as_uint(m.y);
+    }
+    wa = __byte_perm(__byte_perm(ma[0], ma[1], 0x0040u), __byte_perm(ma[2], ma[3], 0x0040u), 0x5410u);
+    wb = __byte_perm(__byte_perm(mb[0], mb[1], 0x0040u), __byte_perm(mb[2], mb[3], 0x0040u), 0x5410u);
+}
+#endif
+
+// 4 pixels of row A (pixel index pa4) and of row B (pb4) -> luma pairs y2[i] = (A_i, B_i).  Rows that do not exist
+// (hb false: odd frame height) read row A again and are zeroed.
+template <int SRC>
+SSW_HD void load_luma4x2(const void* src, long long pa4, long long pb4, bool hb, float nz, cplx* y2) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (SRC == PIX_RGB8) {
+        const unsigned* qa = (const unsigned*)((const unsigned char*)src + 3 * pa4);
+        const unsigned* qb = (const unsigned*)((const unsigned char*)src + 3 * (hb ? pb4 : pa4));
+        const unsigned wa[3] = {ldw(qa), ldw(qa + 1), ldw(qa + 2)}, wb[3] = {ldw(qb), ldw(qb + 1), ldw(qb + 2)};
+        float2 c[12];
+        unpack4_unit2(wa, wb, c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y2[i] = mat3x2(0.30f, 0.59f, 0.11f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+        if (!hb) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y2[i].y = 0.f;
+        }
+        return;
+    }
+#endif
+    (void)nz;
+    float ya[4], yb[4] = {0.f, 0.f, 0.f, 0.f};
+    load_luma4<SRC>(src, pa4, ya);
+    if (hb) load_luma4<SRC>(src, pb4, yb);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y2[i] = mk(ya[i], yb[i]);
+}
+
+// new luma pairs y2[i] = (A_i, B_i) of 4 pixels of rows A and B (+ chroma of the original pixels) -> destination
+template <int DST, int SRC>
+SSW_HD void store_pix4x2(const void* src, void* dst, long long pa4, long long pb4, bool hb, float nz, const cplx* y2) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (DST == PIX_RGB8 && SRC == PIX_RGB8) {
+        const unsigned* qa = (const unsigned*)((const unsigned char*)src + 3 * pa4);
+        const unsigned* qb = (const unsigned*)((const unsigned char*)src + 3 * (hb ? pb4 : pa4));
+        const unsigned wa[3] = {ldw(qa), ldw(qa + 1), ldw(qa + 2)}, wb[3] = {ldw(qb), ldw(qb + 1), ldw(qb + 2)};
+        float2 c[12], o[12];
+        unpack4_unit2(wa, wb, c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 ci = mat3x2(0.60f, -0.28f, -0.32f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+            const float2 cq = mat3x2(0.21f, -0.52f, 0.31f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+            // src/yiq.rs:163-165 rows of YIQ_TO_RGB_MATRIX, (m0*y + m1*i) + m2*q, m0 == 1
+            o[3 * i] = __fadd2_rn(__fadd2_rn(y2[i], prod2(0.948262f, ci, nz)), prod2(0.624013f, cq, nz));
+            o[3 * i + 1] = __fadd2_rn(__fadd2_rn(y2[i], prod2(-0.276066f, ci, nz)), prod2(-0.639810f, cq, nz));
+            o[3 * i + 2] = __fadd2_rn(__fadd2_rn(y2[i], prod2(-1.105450f, ci, nz)), prod2(1.729860f, cq, nz));
+        }
+        unsigned* da = (unsigned*)((unsigned char*)dst + 3 * pa4);
+        unsigned* db = (unsigned*)((unsigned char*)dst + 3 * pb4);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            unsigned ua, ub;
+            pack_u8x4x2(o + 4 * j, nz, ua, ub);
+            da[j] = ua;
+            if (hb) db[j] = ub;
+        }
+        return;
+    }
+#endif
+    (void)nz;
+    float ya[4], yb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ya[i] = y2[i].x; yb[i] = y2[i].y; }
+    store_pix4<DST, SRC>(src, dst, pa4, ya);
+    if (hb) store_pix4<DST, SRC>(src, dst, pb4, yb);
+}
+
 // FFT-input positions of 4 consecutive samples m = 4u..4u+3 (Makhoul): 2u, N-1-2u, 2u+1, N-2-2u.
 // scatter (a_i, b_i) = sample i of line A / line B
 template <class P>
@@ -386,6 +501,18 @@ SSW_HD void put4(cplx* s, int u, const float* a, const float* b) {
         s[P::idx(2 * u + 1)] = mk(a[2], b[2]);
         s[P::idx(P::N - 2 - 2 * u)] = mk(a[3], b[3]);
         s[P::idx(P::N - 1 - 2 * u)] = mk(a[1], b[1]);
+    }
+}
+template <class P>
+SSW_HD void put4x2(cplx* s, int u, const cplx* y2) {   // y2[i] = (sample i of line A, of line B)
+    if constexpr (!P::PAD) {
+        st4(&s[2 * u].x, y2[0].x, y2[0].y, y2[2].x, y2[2].y);
+        st4(&s[P::N - 2 - 2 * u].x, y2[3].x, y2[3].y, y2[1].x, y2[1].y);
+    } else {
+        s[P::idx(2 * u)] = y2[0];
+        s[P::idx(2 * u + 1)] = y2[2];
+        s[P::idx(P::N - 2 - 2 * u)] = y2[3];
+        s[P::idx(P::N - 1 - 2 * u)] = y2[1];
     }
 }
 template <class P>
@@ -431,18 +558,18 @@ struct RowFwd {
             for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
                 const int u = t + it * T;
                 if (u < N / 4) {
-                    float ya[4] = {0.f, 0.f, 0.f, 0.f}, yb[4] = {0.f, 0.f, 0.f, 0.f};
+                    cplx y2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y2[i] = mk(0.f, 0.f);
 #ifdef SSW_TUNE
-                    if (a.dbg_skip & 1) { ya[0] = (float)u; yb[1] = 1.f; } else
+                    if (a.dbg_skip & 1) { y2[0].x = (float)u; y2[1].y = 1.f; } else
 #endif
                     if (SRC == PIX_PLANE && a.seg_shift >= 0) {
-                        if (ha) load_luma4<SRC>(src, seg_index(a, ra, 4 * u), ya);
-                        if (hb) load_luma4<SRC>(src, seg_index(a, rb, 4 * u), yb);
+                        if (ha) load_luma4x2<SRC>(src, seg_index(a, ra, 4 * u), seg_index(a, hb ? rb : ra, 4 * u), hb, a.neg_zero, y2);
                     } else {
-                        if (ha) load_luma4<SRC>(src, rowa + 4 * u, ya);
-                        if (hb) load_luma4<SRC>(src, rowa + N + 4 * u, yb);
+                        if (ha) load_luma4x2<SRC>(src, rowa + 4 * u, rowa + N + 4 * u, hb, a.neg_zero, y2);
                     }
-                    put4<P>(s, u, ya, yb);
+                    put4x2<P>(s, u, y2);
                 }
             }
         } else if constexpr (PH < NPH - 1) {
@@ -528,11 +655,10 @@ struct RowInv {
                 if (u < N / 4) {
                     cplx f[4];
                     get4<P>(s, u, f);
-                    float ya[4], yb[4];
+                    cplx y2[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { ya[i] = f[i].x * a.scale0; yb[i] = -f[i].y * a.scale0; }
-                    store_pix4<DST, SRC>(src, dst, row + 4 * u, ya);
-                    if (hb) store_pix4<DST, SRC>(src, dst, row + N + 4 * u, yb);
+                    for (int i = 0; i < 4; ++i) y2[i] = cmul_lanes_x(f[i], a.scale0, -a.scale0, a.neg_zero);   // feeds the colour adds: no contraction
+                    store_pix4x2<DST, SRC>(src, dst, row + 4 * u, row + N + 4 * u, hb, a.neg_zero, y2);
                 }
             }
         }
@@ -647,7 +773,7 @@ struct ColPass {
 // P_ is the plan of the M-point FFT.  Verified against the oracle by tests/test_emul_fast.py.
 // ------------------------------------------------------------------------------------------------
 SSW_HD cplx cconj(cplx a) { return mk(a.x, -a.y); }
-SSW_HD cplx cscale(cplx a, float f) { return mk(a.x * f, a.y * f); }
+SSW_HD cplx cscale(cplx a, float f) { return cscale2(a, f); }
 
 template <class P>
 SSW_HD cplx line1_w(const cplx* t4, int k) {  // W_N^k = exp(-2 pi i k / N) = t4[4k], N = 2*P::N, k <= N/4

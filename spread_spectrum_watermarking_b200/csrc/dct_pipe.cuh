@@ -1,0 +1,349 @@
+// Column passes of the full-frame DCT as persistent, warp-specialised TMA pipelines (sm_100a).
+//
+// Same arithmetic as ColPass (dct_fast.cuh) -- replaces the column half of /root/reference/src/dct2d.rs:171-206 --
+// but restructured around the asynchronous copy engine:
+//   * one CTA per SM slot, looping over its column tiles (tile = 2*G adjacent columns x N rows);
+//   * a PRODUCER warp: one elected thread issues cp.async.bulk.tensor (TMA) loads of the next tile into one of two
+//     tile buffers, signalled by mbarriers (complete_tx), and TMA stores of the finished tile back to the plane,
+//     retired with cp.async.bulk.wait_group.read before the buffer is loaded again;
+//   * COMPUTE warps: TEAMS teams of P::T threads run the FFT of TEAMS line pairs per round out of a separate FFT
+//     buffer, synchronising with named barriers (bar.sync id, count) instead of CTA-wide barriers;
+//   * the Makhoul even/odd reordering is done by the TMA descriptor: the plane is addressed as a 4-D tensor
+//     (column, row parity, row pair, image), so a tile arrives as [even rows ascending | odd rows ascending] and the
+//     first FFT stage reads sample n of the permuted sequence at row  n < N/2 ? n : 3N/2-1-n  ("semi-Makhoul");
+//     the coefficient side of the tile uses the natural 3-D view (column, row, image).
+// Buffers of one CTA: BUF[2] (tile as it lives in the plane: N rows x 2G floats, once as input and once -- in the
+// slots of the line pairs already consumed -- as output), FFT (TEAMS line pairs), optional copies of the twiddle tables.
+//
+// Like every fast kernel the compute part is written as PHASES, `ColPipe::phase<PH>(...)`, executed for all compute
+// threads between barriers; tests/emul runs the same phase functions on the CPU with memcpy standing in for the TMA.
+#pragma once
+#include "dct_fast.cuh"
+
+namespace ssw {
+namespace fast {
+
+struct PipeArgs {
+    int w, h, batch;
+    int tiles_per_image, total_tiles;
+    float scale0, scalen;      // forward: factors for k == 0 / k > 0; inverse: scale0 = output scale
+    const cplx* tw;            // stage twiddles (global copy)
+    const cplx* t4;            // exp(-i*pi*k/(2N)) (global copy)
+    int pdl_late;
+};
+
+// largest divisor of n that is <= cap (rows per TMA box)
+constexpr int box_rows(int n, int cap) {
+    int best = 1;
+    for (int d = 1; d <= cap; ++d) if (n % d == 0) best = d;
+    return best;
+}
+
+// MINB_: CTAs the kernel is meant to keep resident per SM (1 or 2) -- bounds registers and shared memory per CTA
+template <class P_, int G_, int TEAMS_, bool INVERSE_, int MINB_ = 1>
+struct ColPipe {
+    using P = P_;
+    static_assert(G_ % TEAMS_ == 0 && (G_ == 2 || G_ == 4), "tile = 2 or 4 line pairs, whole rounds");
+    static_assert(P_::N % 2 == 0, "even line length (row parity split)");
+    static constexpr int G = G_, TEAMS = TEAMS_, ROUNDS = G_ / TEAMS_, N = P_::N, T = P_::T;
+    static constexpr bool INVERSE = INVERSE_;
+    static constexpr int NC = TEAMS_ * P_::T;          // compute threads
+    static constexpr int THREADS = NC + 32;            // + the producer warp
+    static constexpr int ROWB = 8 * G_;                // bytes per tile row (2G floats)
+    static constexpr int BUF_BYTES = N * ROWB;
+    // pitch between the FFT buffers of the teams (float2 units): offsets of 8 words (4 teams) / 16 words (2 teams) mod 32
+    // keep the stride-R0 first-stage stores of TEAMS line pairs on distinct banks
+    static constexpr int WANT = (TEAMS_ >= 4) ? 4 : 8;
+    static constexpr int PITCH = P_::LINE + ((WANT - P_::LINE % 16) + 16) % 16;
+    static constexpr int FFT_BYTES = TEAMS_ * PITCH * (int)sizeof(cplx);
+    static constexpr int TW_BYTES = ((P_::TW_TOTAL * 8 + 15) / 16) * 16;
+    static constexpr int T4_BYTES = (((N / 2 + 1) * 8 + 15) / 16) * 16;
+    static constexpr int BAR_BYTES = 64;
+    static constexpr int BASE_BYTES = 2 * BUF_BYTES + FFT_BYTES + BAR_BYTES;
+    static constexpr int MINB = MINB_;
+    static constexpr int LIMIT = (228 * 1024) / MINB_ - 1024;   // 1 KB per resident CTA is reserved by the system
+    // twiddle tables in shared memory when they fit (they would otherwise compete for the few KB of L1 that are left)
+    static constexpr bool TW_SMEM = BASE_BYTES + TW_BYTES <= LIMIT;
+    static constexpr bool T4_SMEM = BASE_BYTES + (TW_SMEM ? TW_BYTES : 0) + T4_BYTES <= LIMIT;
+    static constexpr int SMEM = BASE_BYTES + (TW_SMEM ? TW_BYTES : 0) + (T4_SMEM ? T4_BYTES : 0);
+    static constexpr bool FITS = BASE_BYTES <= LIMIT;
+    static constexpr int OFF_FFT = 2 * BUF_BYTES, OFF_TW = OFF_FFT + FFT_BYTES, OFF_T4 = OFF_TW + (TW_SMEM ? TW_BYTES : 0),
+                         OFF_BAR = OFF_T4 + (T4_SMEM ? T4_BYTES : 0);
+    // TMA boxes: the sample side is the 4-D parity view (N/2 row pairs per parity), the coefficient side the 3-D view
+    static constexpr int RB_HALF = box_rows(N / 2, 256), RB_FULL = box_rows(N, 256);
+    static constexpr int NBOX_HALF = (N / 2) / RB_HALF, NBOX_FULL = N / RB_FULL;
+    static_assert((RB_HALF * ROWB) % 128 == 0 && (RB_FULL * ROWB) % 128 == 0, "TMA boxes must start on 128-byte boundaries");
+    using Thread = ThreadState<P_>;
+    static int tiles_per_image(int w, int h) { (void)h; return (w + 2 * G - 1) / (2 * G); }
+
+    // row of the tile buffer that holds sample n of the Makhoul-permuted sequence
+    static SSW_HD int semi(int n) { return n < N / 2 ? n : 3 * N / 2 - 1 - n; }
+
+    // ---- compute phases of one round `rd` (line pairs rd*TEAMS .. rd*TEAMS+TEAMS-1 of the tile) ------------------
+    //   phase 0              : forward: first FFT stage, operands straight from the tile buffer (semi-Makhoul rows),
+    //                                   lanes interleave (butterfly, pair) so that a warp reads whole rows
+    //                          inverse: DCT-III pre pass, coefficient rows (natural order) -> FFT buffers
+    //   phase 1 .. 2*NST-1   : forward: store of stage 0 is part of phase 0; phases (2s-1, 2s) = (load, store) of stage s >= 1
+    //                          inverse: phases (2s+1, 2s+2) = (load, store) of stage s >= 0      [one more phase, see NPH_INV]
+    //   last phase           : forward: DCT-II post pass, FFT buffers -> coefficient rows of the tile buffer
+    //                          inverse: FFT buffers -> sample rows (semi-Makhoul) of the tile buffer
+    // Barriers: phases that hand data from one team mapping to the (pair-interleaved) CTA mapping are separated by a
+    // barrier over all compute threads, the stages in between only by the team's own barrier.
+    static constexpr int NPH_FWD = 2 * P_::NST;       // 0: S0 load+store | 1..2(NST-1): stages 1.. | last: post
+    static constexpr int NPH_INV = 2 * P_::NST + 2;   // 0: pre | 1..2NST: stages 0.. | last: output
+
+    // forward phase 0: stage 0 from the tile buffer
+    static SSW_HD void fwd_stage0(const cplx* buf, cplx* fft, int rd, int c) {
+        using I = StageInfo<P, 0>;
+        constexpr int R = I::R, NB = I::NB;
+        const int qq = c % TEAMS, jj = c / TEAMS;   // c < NC: jj < T
+        const int q = rd * TEAMS + qq;
+        cplx* s = fft + qq * PITCH;
+#pragma unroll
+        for (int it = 0; it < (NB + T - 1) / T; ++it) {
+            const int j = jj + it * T;
+            if (j < NB) {
+                cplx x[R];
+                static_for<R>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    x[r] = buf[semi(j + r * NB) * G + q];
+                });
+                Dft<R>::run(x);
+                const int j0 = j * R, b0 = P::idx(j0);
+                static_for<R>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    s[idx_off<P, r, (R == 16)>(b0, j0)] = x[r];
+                });
+            }
+        }
+    }
+
+    // forward last phase: post pass -> coefficient rows (natural order) in the slots of this round's pairs
+    static SSW_HD void fwd_post(cplx* buf, const cplx* fft, const cplx* t4, int rd, int c, float scale0, float scalen) {
+#pragma unroll 2
+        for (int e = c; e < (N / 2 + 1) * TEAMS; e += NC) {
+            const int k = e / TEAMS, qq = e - k * TEAMS;
+            const int kr = k ? N - k : 0;
+            const cplx* s = fft + qq * PITCH;
+            float xa, xb, ya, yb;
+            dct2_post(s[P::idx(k)], s[P::idx(kr)], t4[k], xa, xb, ya, yb);
+            const float sk = k ? scalen : scale0;
+            const int q = rd * TEAMS + qq;
+            buf[k * G + q] = cmul_lanes(mk(xa, xb), sk, sk);
+            if (k && kr != k) buf[kr * G + q] = cmul_lanes(mk(ya, yb), scalen, scalen);
+        }
+    }
+
+    // inverse phase 0: pre pass, coefficient rows of this round's pairs -> FFT buffers
+    static SSW_HD void inv_pre(const cplx* buf, cplx* fft, const cplx* t4, int rd, int c) {
+#pragma unroll 2
+        for (int e = c; e < (N / 2 + 1) * TEAMS; e += NC) {
+            const int k = e / TEAMS, qq = e - k * TEAMS;
+            const int kr = k ? N - k : 0;
+            const int q = rd * TEAMS + qq;
+            cplx* s = fft + qq * PITCH;
+            const cplx pv = buf[k * G + q];
+            cplx qv = mk(0.f, 0.f);
+            if (k) qv = buf[kr * G + q];
+            cplx zk, zr;
+            dct3_pre(pv.x, pv.y, qv.x, qv.y, t4[k], zk, zr);
+            s[P::idx(k)] = zk;
+            if (k && kr != k) s[P::idx(kr)] = zr;
+        }
+    }
+
+    // inverse last phase: FFT buffers -> sample rows (semi-Makhoul order) in the slots of this round's pairs
+    static SSW_HD void inv_out(cplx* buf, const cplx* fft, int rd, int c, float scale) {
+#pragma unroll 4
+        for (int e = c; e < N * TEAMS; e += NC) {
+            const int n = e / TEAMS, qq = e - n * TEAMS;
+            const int q = rd * TEAMS + qq;
+            const cplx f = fft[qq * PITCH + P::idx(semi(n))];   // row n of the buffer holds FFT position semi(n) (an involution)
+            buf[n * G + q] = cmul_lanes(f, scale, -scale);
+        }
+    }
+
+    // all phases of one round, as the emulation and the kernel run them; `sync_all(id)` / `sync_team()` are supplied
+    // by the caller (named barriers on the device, nothing on the CPU where phases run one after the other)
+    template <int PH>
+    static SSW_HD void phase(const PipeArgs& a, cplx* buf, cplx* fft, const cplx* tw, const cplx* t4, int rd, int c, Thread& th) {
+        const int g = c / T, t = c - g * T;       // team mapping of the middle stages
+        cplx* s = fft + g * PITCH;
+        if constexpr (!INVERSE) {
+            if constexpr (PH == 0) fwd_stage0(buf, fft, rd, c);
+            else if constexpr (PH == NPH_FWD - 1) fwd_post(buf, fft, t4, rd, c, a.scale0, a.scalen);
+            else fft_phase<P, PH + 2, TW_SMEM>(s, tw, t, th.v);   // PH 1 -> fft_phase 3 (load of stage 1), ...
+        } else {
+            if constexpr (PH == 0) inv_pre(buf, fft, t4, rd, c);
+            else if constexpr (PH == NPH_INV - 1) inv_out(buf, fft, rd, c, a.scale0);
+            else fft_phase<P, PH, TW_SMEM>(s, tw, t, th.v);       // PH 1 -> fft_phase 1 (load of stage 0), ...
+        }
+    }
+    static constexpr int NPHASES = INVERSE_ ? NPH_INV : NPH_FWD;
+    // true: the barrier AFTER phase PH must cover all compute threads (the next phase uses another thread mapping)
+    template <int PH> struct AllAfter {
+        static constexpr bool value = INVERSE_ ? (PH == 0 || PH >= NPH_INV - 2) : (PH == 0 || PH >= NPH_FWD - 2);
+    };
+};
+
+#if defined(__CUDACC__)
+// ---- PTX wrappers: mbarrier, TMA, named barriers ---------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol error traps (reported as a launch failure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spin > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const void* map, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void* map, unsigned bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* map, unsigned src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* map, unsigned src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct alignas(64) TmaMap { unsigned long long v[16]; };   // CUtensorMap (128 bytes, 64-byte aligned)
+
+// map_s: sample side  (4-D: column, parity, row pair, image);  map_c: coefficient side (3-D: column, row, image)
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, K::MINB)
+col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaMap map_s, const __grid_constant__ TmaMap map_c) {
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
+    constexpr int NC = K::NC;
+    const int tid = threadIdx.x;
+    const unsigned sbase = smem_u32(pipe_smem);
+    const unsigned bar_full0 = sbase + K::OFF_BAR, bar_ready0 = bar_full0 + 16;   // full[2], ready[2]
+    cplx* fft = (cplx*)(pipe_smem + K::OFF_FFT);
+    const cplx* tw = a.tw;
+    const cplx* t4 = a.t4;
+
+    if (tid == 0) {
+        mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1);
+        mbar_init(bar_ready0, 1); mbar_init(bar_ready0 + 8, 1);
+        fence_mbar_init();
+    }
+    if (!a.pdl_late) pdl_trigger();
+    // twiddle tables are read-only inputs written long before the previous kernel: stage them before the dependency wait
+    if constexpr (K::TW_SMEM) {
+        cplx* d = (cplx*)(pipe_smem + K::OFF_TW);
+        for (int i = tid; i < K::P::TW_TOTAL; i += K::THREADS) d[i] = __ldg(a.tw + i);
+        tw = d;
+    }
+    if constexpr (K::T4_SMEM) {
+        cplx* d = (cplx*)(pipe_smem + K::OFF_T4);
+        for (int i = tid; i < K::N / 2 + 1; i += K::THREADS) d[i] = __ldg(a.t4 + i);
+        t4 = d;
+    }
+    __syncthreads();
+    pdl_wait();
+
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
+
+    if (tid >= NC) {
+        // ===================== producer warp =====================
+        if (tid == NC) {
+            auto issue_load = [&](int j) {
+                const int tile = first + j * step, b = j & 1;
+                const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
+                const unsigned dst = sbase + b * K::BUF_BYTES, bar = bar_full0 + 8 * b;
+                mbar_expect_tx(bar, K::BUF_BYTES);
+                if constexpr (!K::INVERSE) {
+                    for (int par = 0; par < 2; ++par)
+                        for (int bx = 0; bx < K::NBOX_HALF; ++bx)
+                            tma_load_4d(dst + (par * (K::N / 2) + bx * K::RB_HALF) * K::ROWB, &map_s, bar, c0, par, bx * K::RB_HALF, img);
+                } else {
+                    for (int bx = 0; bx < K::NBOX_FULL; ++bx)
+                        tma_load_3d(dst + bx * K::RB_FULL * K::ROWB, &map_c, bar, c0, bx * K::RB_FULL, img);
+                }
+            };
+            auto issue_store = [&](int j) {
+                const int tile = first + j * step, b = j & 1;
+                const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
+                const unsigned src = sbase + b * K::BUF_BYTES;
+                if constexpr (!K::INVERSE) {
+                    for (int bx = 0; bx < K::NBOX_FULL; ++bx)
+                        tma_store_3d(&map_c, src + bx * K::RB_FULL * K::ROWB, c0, bx * K::RB_FULL, img);
+                } else {
+                    for (int par = 0; par < 2; ++par)
+                        for (int bx = 0; bx < K::NBOX_HALF; ++bx)
+                            tma_store_4d(&map_s, src + (par * (K::N / 2) + bx * K::RB_HALF) * K::ROWB, c0, par, bx * K::RB_HALF, img);
+                }
+                tma_commit();
+            };
+            if (nt > 0) issue_load(0);
+            if (nt > 1) issue_load(1);
+            for (int j = 0; j < nt; ++j) {
+                const int b = j & 1;
+                mbar_wait(bar_ready0 + 8 * b, (j >> 1) & 1);   // the compute warps have finished tile j (results in BUF[b])
+                issue_store(j);
+                if (j + 2 < nt) {
+                    tma_wait_read0();                          // the store has read BUF[b]: it may be overwritten
+                    issue_load(j + 2);
+                }
+            }
+            tma_wait_all0();                                   // all stores complete before the CTA exits
+        }
+        return;
+    }
+
+    // ===================== compute warps =====================
+    typename K::Thread th;
+    const int team = tid / K::T;
+    for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        cplx* buf = (cplx*)(pipe_smem + b * K::BUF_BYTES);
+        mbar_wait(bar_full0 + 8 * b, (j >> 1) & 1);            // tile j has landed in BUF[b]
+#pragma unroll 1
+        for (int rd = 0; rd < K::ROUNDS; ++rd) {
+            static_for<K::NPHASES>([&](auto ph) {
+                constexpr int p = decltype(ph)::value;
+                if constexpr (p == K::NPHASES - 1) { if (a.pdl_late && j + 1 == nt && rd + 1 == K::ROUNDS) pdl_trigger(); }
+                K::template phase<p>(a, buf, fft, tw, t4, rd, tid, th);
+                if constexpr (p + 1 < K::NPHASES) {
+                    if constexpr (K::template AllAfter<p>::value) named_sync(1, NC);
+                    else named_sync(2 + team, K::T);
+                }
+            });
+            if (rd + 1 < K::ROUNDS) named_sync(1, NC);         // FFT buffers are free for the next round
+        }
+        fence_proxy_async();                                   // generic-proxy writes of BUF[b] -> visible to the TMA store
+        named_sync(1, NC);                                     // (also: FFT buffers free for the next tile)
+        if (tid == 0) mbar_arrive(bar_ready0 + 8 * b);
+    }
+}
+#endif
+
+}  // namespace fast
+}  // namespace ssw

@@ -30,6 +30,7 @@ __global__ void embed_scatter_kernel(float* __restrict__ planes, long long plane
     if (i >= k) return;
     float* plane = planes + (long long)img * plane_stride;
     const unsigned p = idx[(long long)img * idx_stride + i];
+    if (p == 0xFFFFFFFFu) return;   // the ordering of this frame failed (candidate overflow, reported): leave it unmarked
     const float* mk0 = marks + (long long)img * n_marks * mark_stride;
     const float orig = plane[p];
     if (n_marks == 1) {
@@ -57,6 +58,7 @@ __global__ void extract_gather_kernel(const float* __restrict__ base, const floa
     const unsigned img = blockIdx.y;
     if (i >= n) return;
     const unsigned p = idx[(long long)img * idx_stride + i];
+    if (p == 0xFFFFFFFFu) { out[(long long)img * out_stride + i] = 0.f; return; }   // ordering failed (reported): defined output
     const float b = base[(long long)img * plane_stride + p];
     const float d = derived[(long long)img * plane_stride + p];
     float r;
@@ -246,6 +248,125 @@ similarity_bank_kernel(const float* __restrict__ bank, size_t n_marks, unsigned 
     }
     const size_t m = m0 + t;
     if (m < n_marks) out[(long long)e * out_stride + m] = __fdiv_rn(nom, __fsqrt_rn(__ldg(den + e)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bank search at HBM speed (default): ONE WARP PER STORED MARK.  The extracted vector sits in shared memory, every
+// lane streams float4s of the mark row (fully coalesced 512-byte warp reads, all loads of a row in flight at once),
+// four partial sums per lane, then a fixed-shape reduction ((a0+a1)+(a2+a3), xor-shuffle tree) -- deterministic, and
+// within a few ulp of the sequential loop of src/algorithm.rs:696-714 (the contract asks for 1e-3 relative; the
+// bit-identical one-thread-per-mark kernel above stays available: SSW_SIM_EXACT=1).
+// The denominator is the sequentially summed one of similarity_den_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpSimThreads = 256;       // 8 warps per CTA
+constexpr int kWarpSimMaxN = 8192;         // extracted vector staged in shared memory (32 KB)
+
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kWarpSimThreads)
+similarity_bank_warp_kernel(const float* __restrict__ bank, size_t n_marks, unsigned n,
+                            const float* __restrict__ extracted, long long ext_stride, const float* __restrict__ den,
+                            float* __restrict__ out, long long out_stride) {
+    pdl_enter();
+    __shared__ __align__(16) float ex[kWarpSimMaxN];
+    const unsigned e = blockIdx.y;
+    const float* ext = extracted + (long long)e * ext_stride;
+    for (unsigned j = threadIdx.x; j < n; j += kWarpSimThreads) ex[j] = __ldg(ext + j);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = (size_t)blockIdx.x * (kWarpSimThreads / 32) + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * (kWarpSimThreads / 32);
+    const float rden = __fsqrt_rn(__ldg(den + e));
+    const unsigned n4 = n >> 2;
+    const float4* ex4 = (const float4*)ex;
+    for (size_t m = warp0; m < n_marks; m += nwarps) {
+        const float* row = bank + m * n;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if ((((size_t)row) & 15) == 0) {
+            const float4* r4 = (const float4*)row;
+            unsigned j = lane;
+            for (; j + 7 * 32 < n4; j += 8 * 32) {       // 8 independent 16-byte loads per lane in flight
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_stream4(r4 + j + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 x = ex4[j + 32 * u];
+                    a0 = fmaf(x.x, v[u].x, a0); a1 = fmaf(x.y, v[u].y, a1); a2 = fmaf(x.z, v[u].z, a2); a3 = fmaf(x.w, v[u].w, a3);
+                }
+            }
+            for (; j < n4; j += 32) {
+                const float4 v = ld_stream4(r4 + j), x = ex4[j];
+                a0 = fmaf(x.x, v.x, a0); a1 = fmaf(x.y, v.y, a1); a2 = fmaf(x.z, v.z, a2); a3 = fmaf(x.w, v.w, a3);
+            }
+            for (unsigned t = (n4 << 2) + lane; t < n; t += 32) a0 = fmaf(ex[t], __ldg(row + t), a0);
+        } else {
+            for (unsigned t = lane; t < n; t += 32) a0 = fmaf(ex[t], __ldg(row + t), a0);
+        }
+        float sum = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) out[(long long)e * out_stride + m] = __fdiv_rn(sum, rden);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused extraction + 1:1 score of the batch pipelines: one CTA per frame gathers the n coefficient pairs, applies the
+// extraction function (bit-faithful, as extract_gather_kernel), stores the vector and -- when marks are given --
+// reduces sum(e*m) and sum(e*e) in a fixed-shape tree (per-thread strided partial sums, xor-shuffle tree per warp,
+// warps in order): deterministic, within a few ulp of the sequential loop of src/algorithm.rs:696-714.
+// An index list that starts with 0xFFFFFFFF marks a frame whose ordering failed (candidate overflow): the vector is
+// zero-filled and the score is NaN instead of reading coefficients at arbitrary places.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGatherSimThreads = 1024;
+constexpr unsigned kBadIndex = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(kGatherSimThreads)
+extract_gather_sim_kernel(const float* __restrict__ base, const float* __restrict__ derived, long long plane_stride,
+                          const unsigned* __restrict__ idx, long long idx_stride, unsigned n, int method, float alpha,
+                          float* __restrict__ out, long long out_stride, const float* __restrict__ marks, long long mark_stride,
+                          float* __restrict__ sim) {
+    pdl_enter();
+    __shared__ float red[2][kGatherSimThreads / 32];
+    const unsigned img = blockIdx.x;
+    const unsigned* ix = idx + (long long)img * idx_stride;
+    const float* b0 = base + (long long)img * plane_stride;
+    const float* d0 = derived + (long long)img * plane_stride;
+    const bool bad = ix[0] == kBadIndex;
+    float num = 0.f, den = 0.f;
+    for (unsigned i = threadIdx.x; i < n; i += kGatherSimThreads) {
+        float r = 0.f;
+        if (!bad) {
+            const unsigned p = ix[i];
+            const float b = b0[p], d = d0[p];
+            if (method == 1) r = __fdiv_rn(__fsub_rn(d, b), alpha);
+            else if (method == 2) r = __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
+            else r = __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
+        }
+        out[(long long)img * out_stride + i] = r;
+        if (marks) {
+            num = fmaf(r, __ldg(marks + (long long)img * mark_stride + i), num);
+            den = fmaf(r, r, den);
+        }
+    }
+    if (!sim) return;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        num += __shfl_xor_sync(0xFFFFFFFFu, num, d);
+        den += __shfl_xor_sync(0xFFFFFFFFu, den, d);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = num; red[1][warp] = den; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, q = 0.f;
+        for (int wv = 0; wv < kGatherSimThreads / 32; ++wv) { a += red[0][wv]; q += red[1][wv]; }
+        sim[img] = bad ? __int_as_float(0x7FC00000) : __fdiv_rn(a, __fsqrt_rn(q));
+    }
 }
 
 // 1:1 form: extracted vector i against mark i (the fused extract pipeline).

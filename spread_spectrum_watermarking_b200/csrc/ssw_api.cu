@@ -1,5 +1,6 @@
 // libssw: C ABI over the sm_100a kernels (see include/ssw.h for the reference items each entry
 // point mirrors).  Host orchestration only -- no arithmetic of the hot path runs on the CPU.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -11,11 +12,13 @@
 #include <memory>
 #include <random>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/ssw.h"
 #include "dct_kernels.cuh"
 #include "fast_dispatch.h"
+#include "dct_pipe.cuh"
 #include "mark_kernels.cuh"
 #include "select_kernels.cuh"
 #include "select_general.cuh"
@@ -77,6 +80,12 @@ struct ssw_ctx {
     int pf_tiles = 0;                      // SSW_PF_TILES: tiles per CTA of the prefetching kernels (0 = automatic)
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
+    int col_pipe = 1;                      // SSW_COL_PIPE: 0 ColPass (one CTA per tile); 1..3 persistent TMA pipelines (dct_pipe.cuh):
+                                           // 1 = 8 columns, 4 teams; 2 = 8 columns, 2 teams x 2 rounds; 3 = 4 columns, 2 teams (2 CTAs / SM)
+    void* encode_tiled = nullptr;          // cuTensorMapEncodeTiled (driver entry point, resolved once)
+    struct MapKey { const void* p; int w, h, batch, g; bool operator<(const MapKey& o) const {
+        return std::tie(p, w, h, batch, g) < std::tie(o.p, o.w, o.h, o.batch, o.g); } };
+    std::map<MapKey, std::pair<fast::TmaMap, fast::TmaMap>> tma_maps;   // plane -> (sample-side 4-D map, coefficient-side 3-D map)
     struct { bool active = false; int seg_shift = -1, chunk_shift = 0, ranks = 1, lines = 0; } seg;  // ssw_lines_forward_seg_dev
     TopkScratch ts{};
     unsigned ts_batch = 0;
@@ -191,6 +200,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_PF_TILES")) c->pf_tiles = atoi(s);
     if (const char* s = getenv("SSW_TOPK_FULL_HIST")) c->topk_full_hist = atoi(s) != 0;
     if (const char* s = getenv("SSW_FORCE_LINE1")) c->force_line1 = atoi(s) != 0;
+    if (const char* s = getenv("SSW_COL_PIPE")) c->col_pipe = atoi(s);
     *out = c.release();
     return SSW_OK;
 }
@@ -478,6 +488,7 @@ static fast::FastArgs fast_args(int w, int h) {
     a.src_stride = a.plane_stride = a.dst_stride = (long long)w * h;
     a.seg_shift = -1;
     a.dbg_skip = 0;
+    a.neg_zero = -0.0f;
     return a;
 }
 
@@ -570,10 +581,112 @@ static int launch_col_variant(ssw_ctx* c, const fast::FastArgs& a, int w, int h,
     }
 }
 
+// ---- persistent TMA column pipelines (dct_pipe.cuh) ---------------------------------------------------------------
+// tensor maps of a coefficient plane [batch][h][w] f32 for tiles of 2*g columns:
+//   sample side      4-D (column, row parity, row pair, image)  -- even rows / odd rows as separate boxes (Makhoul split)
+//   coefficient side 3-D (column, row, image)
+static int tma_maps_for(ssw_ctx* c, const float* plane, int w, int h, int batch, int g, int rb_half, int rb_full,
+                        const std::pair<fast::TmaMap, fast::TmaMap>** out) {
+    const ssw_ctx::MapKey key{plane, w, h, batch, g};
+    auto it = c->tma_maps.find(key);
+    if (it != c->tma_maps.end()) { *out = &it->second; return SSW_OK; }
+    if (!c->encode_tiled) {
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &c->encode_tiled, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !c->encode_tiled)
+            return fail(SSW_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    }
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn enc = (EncodeFn)c->encode_tiled;
+    static_assert(sizeof(CUtensorMap) == sizeof(fast::TmaMap), "tensor map size");
+    std::pair<fast::TmaMap, fast::TmaMap> maps;
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    {
+        CUtensorMap m;
+        const cuuint64_t dims[4] = {(cuuint64_t)w, 2, (cuuint64_t)h / 2, (cuuint64_t)batch};
+        const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)w * 8, (cuuint64_t)w * h * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)(2 * g), 1, (cuuint32_t)rb_half, 1};
+        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)plane, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SSW_ERR_CUDA, "cuTensorMapEncodeTiled (4-D sample view) failed: " + std::to_string((int)r));
+        std::memcpy(&maps.first, &m, sizeof(m));
+    }
+    {
+        CUtensorMap m;
+        const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)(2 * g), (cuuint32_t)rb_full, 1};
+        const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)plane, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SSW_ERR_CUDA, "cuTensorMapEncodeTiled (3-D coefficient view) failed: " + std::to_string((int)r));
+        std::memcpy(&maps.second, &m, sizeof(m));
+    }
+    if (c->tma_maps.size() > 4096) c->tma_maps.clear();   // planes come and go (cudaMallocAsync): bounded cache
+    *out = &c->tma_maps.emplace(key, maps).first->second;
+    return SSW_OK;
+}
+
+template <class K>
+static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch, float* d_plane, float scale0, float scalen) {
+    using P = typename K::P;
+    fast::PipeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.w = w; a.h = h; a.batch = batch; a.scale0 = scale0; a.scalen = scalen;
+    CKS(fast_tables<P>(c, &a.tw, &a.t4));
+    a.tiles_per_image = K::tiles_per_image(w, h);
+    const long long tiles = (long long)a.tiles_per_image * batch;
+    if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
+    a.total_tiles = (int)tiles;
+    a.pdl_late = c->pdl_mode != 0;
+    const std::pair<fast::TmaMap, fast::TmaMap>* maps;
+    CKS(tma_maps_for(c, d_plane, w, h, batch, K::G, K::RB_HALF, K::RB_FULL, &maps));
+    auto kernel = fast::col_pipe_kernel<K>;
+    const void* key = (const void*)kernel;
+    auto it = c->smem_attr.find(key);
+    if (it == c->smem_attr.end()) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K::THREADS, K::SMEM));
+        it = c->smem_attr.emplace(key, std::max(1, occ)).first;   // value: resident CTAs per SM
+    }
+    const long long slots = (long long)it->second * c->sm_count;
+    const unsigned grid = (unsigned)std::min<long long>(tiles, slots);
+    {
+        KScope ks(c, name);
+        launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a, maps->first, maps->second);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+// *done = true when a pipeline ran
+static int pipe_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen, bool* done) {
+    *done = false;
+    if (c->col_pipe <= 0 || !aligned(d_plane, 16) || (w % 4) || (h & 1)) return SSW_OK;
+    const char* name = inverse ? "inv_cols" : "fwd_cols";
+    int rc = SSW_OK;
+    auto run = [&](auto k) { using K = decltype(k); rc = launch_col_pipe<K>(c, name, w, h, batch, d_plane, scale0, scalen); *done = true; };
+    if (h == 2160) {
+        using P = fast::Plan2160;
+        if (c->col_pipe == 2) { if (inverse) run(fast::ColPipe<P, 4, 2, true>{}); else run(fast::ColPipe<P, 4, 2, false>{}); }
+        else if (c->col_pipe == 3) { if (inverse) run(fast::ColPipe<P, 2, 2, true, 2>{}); else run(fast::ColPipe<P, 2, 2, false, 2>{}); }
+        else { if (inverse) run(fast::ColPipe<P, 4, 4, true>{}); else run(fast::ColPipe<P, 4, 4, false>{}); }
+    } else if (h == 1080) {
+        using P = fast::Plan1080;
+        if (c->col_pipe == 2) { if (inverse) run(fast::ColPipe<P, 4, 4, true, 1>{}); else run(fast::ColPipe<P, 4, 4, false, 1>{}); }
+        else { if (inverse) run(fast::ColPipe<P, 4, 4, true, 2>{}); else run(fast::ColPipe<P, 4, 4, false, 2>{}); }
+    }
+    return rc;
+}
+
 static int fast_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen,
                     bool* done) {
     *done = false;
     if (!c->use_fast || (w % 4) || !aligned(d_plane, 16)) return SSW_OK;
+    CKS(pipe_col(c, inverse, w, h, batch, d_plane, scale0, scalen, done));
+    if (*done) return SSW_OK;
     int rc = SSW_OK;
     *done = fast::with_plan(h, [&](auto p) {
         using P = decltype(p);

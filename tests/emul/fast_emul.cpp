@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../spread_spectrum_watermarking_b200/csrc/fast_dispatch.h"
+#include "../../spread_spectrum_watermarking_b200/csrc/dct_pipe.cuh"
 
 using namespace ssw;
 using namespace ssw::fast;
@@ -73,9 +74,66 @@ FastArgs base_args(int w, int h) {
     return a;
 }
 
+// persistent TMA column pipelines (dct_pipe.cuh): memcpy stands in for the tensor-map copies -- the sample side of a
+// tile is [even rows | odd rows] (the 4-D parity view), the coefficient side the rows in natural order; columns past
+// the frame read as zero and are not written back (TMA out-of-bounds rules)
+template <class K>
+void emulate_col_pipe(PipeArgs a, float* plane, const cplx* tw, const cplx* t4) {
+    constexpr int N = K::N, G = K::G;
+    std::vector<cplx> buf((size_t)N * G), fft((size_t)K::TEAMS * K::PITCH + 8);
+    std::vector<typename K::Thread> th(K::NC);
+    a.tiles_per_image = K::tiles_per_image(a.w, a.h);
+    a.total_tiles = a.tiles_per_image * a.batch;
+    auto sample_row = [](int n) { return n < N / 2 ? 2 * n : 2 * (n - N / 2) + 1; };   // buffer row -> frame row (sample side)
+    for (int tile = 0; tile < a.total_tiles; ++tile) {
+        const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * G;
+        float* pl = plane + (size_t)img * a.w * a.h;
+        for (int n = 0; n < N; ++n) {
+            const int r = K::INVERSE ? n : sample_row(n);
+            for (int x = 0; x < 2 * G; ++x) {
+                const float v = (c0 + x < a.w) ? pl[(size_t)r * a.w + c0 + x] : 0.f;
+                ((float*)&buf[(size_t)n * G])[x] = v;
+            }
+        }
+        for (int rd = 0; rd < K::ROUNDS; ++rd)
+            static_for<K::NPHASES>([&](auto ph) {
+                constexpr int p = decltype(ph)::value;
+                for (int c = 0; c < K::NC; ++c) K::template phase<p>(a, buf.data(), fft.data(), tw, t4, rd, c, th[c]);
+            });
+        for (int n = 0; n < N; ++n) {
+            const int r = K::INVERSE ? sample_row(n) : n;
+            for (int x = 0; x < 2 * G; ++x)
+                if (c0 + x < a.w) pl[(size_t)r * a.w + c0 + x] = ((float*)&buf[(size_t)n * G])[x];
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// variant: 1 = 4 pairs x 4 teams, 2 = 4 pairs x 2 teams (2 rounds), 3 = 2 pairs x 2 teams
+int emul_col_pipe(int variant, int inverse, int w, int h, int batch, float* plane, float scale0, float scalen) {
+    if ((w % 4) || (h & 1)) return -2;
+    bool ran = false;
+    return with_plan(h, [&](auto p) {
+        using P = decltype(p);
+        Tables<P> tb;
+        PipeArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.w = w; a.h = h; a.batch = batch; a.scale0 = scale0; a.scalen = scalen;
+        const cplx* tw = (const cplx*)tb.tw.data();
+        const cplx* t4 = (const cplx*)tb.t4.data();
+        auto run = [&](auto k) { emulate_col_pipe<decltype(k)>(a, plane, tw, t4); ran = true; };
+        if constexpr (ColPipe<P, 4, 4, false>::FITS && (box_rows(P::N / 2, 256) * 16) % 128 == 0) {
+            if (variant == 3) { if (inverse) run(ColPipe<P, 2, 2, true, 2>{}); else run(ColPipe<P, 2, 2, false, 2>{}); return; }
+        }
+        if constexpr (ColPipe<P, 4, 4, false>::FITS) {
+            if (variant == 2) { if (inverse) run(ColPipe<P, 4, 2, true>{}); else run(ColPipe<P, 4, 2, false>{}); }
+            else { if (inverse) run(ColPipe<P, 4, 4, true>{}); else run(ColPipe<P, 4, 4, false>{}); }
+        }
+    }) && ran ? 0 : -2;
+}
 
 int emul_fast_has_plan(int n) { return has_plan(n) ? 1 : 0; }
 int emul_fast_col_pairs(int n) { int g = -1; with_plan(n, [&](auto p) { g = ColG<decltype(p)>::value; }); return g; }

@@ -208,3 +208,20 @@ def test_prefetching_row_kernel_is_bit_identical(emul, so, n, h, per):
     assert emul.emul_fast_row_fwd(0, ptr(rgb2), n, h, 2, ptr(a), f32(1.0), f32(1.0)) == 0
     assert emul.emul_fast_row_fwd_pf(ptr(rgb2), n, h, 2, ptr(b), per) == 0
     assert (a == b).all()
+
+
+@pytest.mark.parametrize('n,variant', [(2160, 1), (2160, 2), (2160, 3), (1080, 1), (1920, 1), (2048, 1), (720, 1), (1440, 1)])
+@pytest.mark.parametrize('inverse', [0, 1])
+def test_col_pipe_matches_col_pass(emul, n, variant, inverse):
+    """persistent TMA column pipelines (csrc/dct_pipe.cuh), phases run on the CPU with memcpy standing in for the tensor-map
+    copies (parity-split sample side, natural coefficient side, zero fill / clipping of columns past the frame): the
+    planes must be bit-identical to the one-CTA-per-tile column kernels, whose arithmetic they share"""
+    w = 20   # 20 columns: tiles of 8 (4) columns, the last one partly outside the frame
+    rng = np.random.default_rng(n + variant)
+    a = (rng.random((2, n, w)).astype(np.float32) - 0.5) * 3.0
+    ref = a.copy()
+    got = a.copy()
+    assert emul.emul_fast_col(inverse, w, n, 2, ptr(ref), f32(1.0 if inverse else 0.7), f32(1.0 if inverse else 1.3)) == 0
+    assert emul.emul_col_pipe(variant, inverse, w, n, 2, ptr(got), f32(1.0 if inverse else 0.7), f32(1.0 if inverse else 1.3)) == 0
+    assert np.abs(ref).max() > 1.0
+    assert np.array_equal(ref, got)
