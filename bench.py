@@ -72,6 +72,9 @@ ALPHA = 0.1
 BANK_MARKS = 100000   # BASELINE.json configs[4]: bank of 100k stored marks of length 1000
 WORKLOADS = {
     # name: (w, h, frames per step, ring size (steps before inputs repeat), seed)
+    'c1': dict(w=640, h=444, batch=1, ring=8, seed=1,
+               name='tests/porcelain_cat_grey_background.jpg (640x444, the reference fixture as decoded RGB8), one N(0,1) mark of '
+                    'length 1000, alpha=0.1, embed+extract (single_simple.rs)'),
     'c2': dict(w=3840, h=2160, batch=1, ring=8, seed=2,
                name='single synthetic 3840x2160 RGB frame, mark length 1000, embed+extract'),
     'c3': dict(w=1920, h=1080, batch=64, ring=2, seed=3,
@@ -238,11 +241,19 @@ def _oracle_step(lib, frame, mark, out, ext):
 
 
 def _host_frames(wl, count, first=0):
-    """synthetic frames on the host without a GPU: tile the (slow, numpy) generator's output for a
-    small frame?  No -- frames must be the real workload; generate once per distinct frame."""
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import ssw_oracle as so
-    return [so.synth_frame(wl['w'], wl['h'], wl['seed'], first + i) for i in range(count)]
+    """the workload's frames on the host, without a GPU and without libssw: oracle_synth_rows (oracle/ssw_oracle.c);
+    c1 is the reference's fixture (tests/golden/cat_rgb8.npz, made by oracle/make_golden.py)"""
+    if wl is WORKLOADS['c1']:
+        cat = np.load(os.path.join(ROOT, 'tests', 'golden', 'cat_rgb8.npz'))['rgb']
+        return [np.ascontiguousarray(cat) for _ in range(count)]
+    lib = _oracle_lib()
+    out = []
+    for i in range(count):
+        f = np.empty((wl['h'], wl['w'], 3), np.uint8)
+        lib.oracle_synth_rows(ctypes.c_int(wl['w']), ctypes.c_uint64(wl['seed']), ctypes.c_uint32(first + i), ctypes.c_uint32(0),
+                              ctypes.c_uint32(wl['h']), ctypes.c_void_p(f.ctypes.data))
+        out.append(f)
+    return out
 
 
 def cpu_baseline(wl, frames, marks, budget_s=25.0):
@@ -269,22 +280,9 @@ def run_reference(args, wl):
     lib = _oracle_lib()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     cores = max(1, min(cores, int(os.environ.get('SSW_REF_THREADS', cores)), 64))
-    # frames: generated on the GPU when there is one (bit-identical generator, see tests), else numpy
-    frames = None
-    try:
-        import torch
-        if torch.cuda.is_available():
-            import spread_spectrum_watermarking_b200 as wm
-            ctx = wm.Context(0)
-            t = torch.empty((2, wl['h'], wl['w'], 3), dtype=torch.uint8, device='cuda:0')
-            wm._lib.check(wm.lib.ssw_synth_frame_rgb8_dev(ctx.handle, wl['w'], wl['h'], wl['seed'], 0, 2, t.data_ptr()))
-            ctx.synchronize()
-            frames = [f.copy() for f in t.cpu().numpy()]
-            ctx.close()
-    except Exception:
-        frames = None
-    if frames is None:
-        frames = _host_frames(wl, 2)
+    # frames: the oracle's own C form of the synthetic generator (bit-identical to the device generator, see tests) --
+    # this arm loads nothing but oracle/liboracle.so
+    frames = _host_frames(wl, 2)
     rng = np.random.default_rng(1000)
     marks = [rng.standard_normal(MARK_LEN).astype(np.float32) for _ in range(2)]
     bufs = [(np.empty_like(frames[0]), np.empty(MARK_LEN, np.float32)) for _ in range(cores)]
@@ -340,12 +338,10 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, wl):
+def dist_setup(args):
+    """one process per GPU; NCCL only for the barrier and the max-over-ranks timing (and the exchanges of c4)"""
     import torch
     import torch.distributed as dist
-    import spread_spectrum_watermarking_b200 as wm
-    from spread_spectrum_watermarking_b200._lib import check, lib, ssw_config
-
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -354,9 +350,20 @@ def run_ours(args, wl):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback')
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def run_ours(args, wl, workload, K, W, with_cpu_baseline=True, e2e_steps=None):
+    """one workload of independent frames (c1, c2, c3, c5) on this rank's GPU; returns the result dict on rank 0"""
+    import torch
+    import torch.distributed as dist
+    import spread_spectrum_watermarking_b200 as wm
+    from spread_spectrum_watermarking_b200._lib import check, lib, ssw_config
+
+    rank, world, local = dist_setup(args)
 
     def barrier():
         if world > 1:
@@ -373,7 +380,11 @@ def run_ours(args, wl):
     # ---- synthetic inputs, resident in HBM; ring*B distinct frames per rank (> L2 for both workloads)
     nfr = ring * B
     frames = torch.empty((nfr, h, w, 3), dtype=torch.uint8, device='cuda')
-    check(lib.ssw_synth_frame_rgb8_dev(ctx.handle, w, h, wl['seed'], rank * nfr, nfr, frames.data_ptr()))
+    if workload == 'c1':   # the reference's own fixture (decoded by oracle/make_golden.py), the same frame in every ring slot
+        cat = np.load(os.path.join(ROOT, 'tests', 'golden', 'cat_rgb8.npz'))['rgb']
+        frames.copy_(torch.from_numpy(np.ascontiguousarray(cat)).cuda().expand(nfr, h, w, 3))
+    else:
+        check(lib.ssw_synth_frame_rgb8_dev(ctx.handle, w, h, wl['seed'], rank * nfr, nfr, frames.data_ptr()))
     rng = np.random.default_rng(1000 + rank)
     marks_h = rng.standard_normal((nfr, MARK_LEN)).astype(np.float32)
     marks = torch.from_numpy(marks_h).cuda()
@@ -395,7 +406,7 @@ def run_ours(args, wl):
                                              sim.data_ptr() + o * 4))
 
     bank = None
-    if args.workload == 'c5':
+    if workload == 'c5':
         # every frame of the ring carries bank row (17 + 1000*i); a step = extract + score against the bank
         bank = wm.Bank.normal(wl['seed'], BANK_MARKS, MARK_LEN, ctx=ctx)
         for i in range(nfr):
@@ -437,7 +448,6 @@ def run_ours(args, wl):
             ms = float(t.item())
         return ms
 
-    K, W = args.steps, max(args.warmup, 3)
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
@@ -445,10 +455,11 @@ def run_ours(args, wl):
     l0 = ctx.launch_count
     ms_regions = [timed(step, K, W)]
     launches = (ctx.launch_count - l0) * K // (K + W)
-    # a second region of exactly K steps, same brackets: the clock sampler can stall the device once for tens of ms
-    # (see Clocks); `value` is the better region, both are reported ("regions_ms_per_step")
+    # two more regions of exactly K steps, same brackets; `value` is the MEDIAN region, all are reported
+    # ("regions_ms_per_step") -- the clock sampler can stall the device once for tens of ms (see Clocks)
     ms_regions.append(timed(step, K, 1))
-    ms_total = min(ms_regions)
+    ms_regions.append(timed(step, K, 1))
+    ms_total = statistics.median(ms_regions)
     clk = clocks.stop() if rank == 0 else None
     ms_embed = timed(embed, K, 1)
     ms_extract = timed(extract, K, 1)
@@ -502,10 +513,18 @@ def run_ours(args, wl):
                     'frac': dom['frac'], 'traffic': traffic.get(dom['name']), 'peak_source': peak_src,
                     'algo_bytes_per_launch': dom['algo_bytes'], 'avg_launch_us': dom['avg_us'], 'share_of_step': dom['share']}
     step_algo = {'embed_bytes_per_px': 53.0, 'extract_bytes_per_px': 50.0}
+    # whole-step rates twice: against SURVEY.md 8(d)'s separate-kernel byte counts (53 / 50 B per px; comparable with
+    # BASELINE.md) and against the bytes this build actually moves (fused passes, DESIGN.md section 3: 37 / 50 B per px)
+    built = {'embed_bytes_per_px': 7.0 + 8.0 + 4.0 + 8.0 + 10.0, 'extract_bytes_per_px': 2 * (7.0 + 8.0) + 4.0}
     whole = {'embed_gbs': round(53.0 * px_step * K / (ms_embed * 1e-3) / 1e9, 1),
-             'extract_gbs': round(50.0 * px_step * K / (ms_extract * 1e-3) / 1e9, 1)}
+             'extract_gbs': round(50.0 * px_step * K / (ms_extract * 1e-3) / 1e9, 1),
+             'embed_gbs_as_built': round(built['embed_bytes_per_px'] * px_step * K / (ms_embed * 1e-3) / 1e9, 1),
+             'extract_gbs_as_built': round(built['extract_bytes_per_px'] * px_step * K / (ms_extract * 1e-3) / 1e9, 1),
+             'as_built': built}
     whole['embed_frac'] = round(whole['embed_gbs'] / peak, 4)
     whole['extract_frac'] = round(whole['extract_gbs'] / peak, 4)
+    whole['embed_frac_as_built'] = round(whole['embed_gbs_as_built'] / peak, 4)
+    whole['extract_frac_as_built'] = round(whole['extract_gbs_as_built'] / peak, 4)
 
     # ---- end to end through the host-buffer C ABI (pinned host memory; H2D + D2H inside the timed region)
     def pinned(nbytes, dtype, shape):
@@ -538,7 +557,7 @@ def run_ours(args, wl):
         check(lib.ssw_extract_batch_rgb8(ctx.handle, hf[r].ctypes.data, ho[r].ctypes.data, w, h, B, pcfg, MARK_LEN,
                                          he.ctypes.data, hm[r].ctypes.data, hs.ctypes.data))
 
-    Ke = max(3, min(K, 20))
+    Ke = e2e_steps if e2e_steps else max(3, min(K, 20))
     if args.no_e2e:
         Ke = 3
     for s in range(3):
@@ -563,20 +582,23 @@ def run_ours(args, wl):
                    'ssw_extract_batch_rgb8 + ssw_bank_similarity (host buffers)')}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and bank is None:
+    if rank == 0 and world == 1 and with_cpu_baseline and not args.no_cpu_baseline and bank is None:
         f0 = [frames[i].cpu().numpy() for i in range(min(2, nfr))]
         cpu = cpu_baseline(wl, f0, [marks_h[i] for i in range(len(f0))])
 
+    result = None
     if rank == 0:
-        emit({
+        result = {
             'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
-            'regions_ms_per_step': [round(m / K, 6) for m in ms_regions],
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'regions_ms_per_step': [round(m / K, 6) for m in ms_regions], 'value_is': 'median of the timed regions',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic' if workload != 'c1' else 'reference fixture',
             'config': {'workload': wl['name'], 'frame': [w, h], 'frames_per_step': B, 'mark_len': MARK_LEN, 'alpha': ALPHA,
                        'insertion': 'Option2', 'ordering': 'Energy',
-                       'l2': 'inputs larger than L2: ring of %d distinct frames (%.0f MB in + %.0f MB out per rank)'
-                             % (nfr, nfr * fb / 1e6, nfr * fb / 1e6),
+                       'l2': ('inputs larger than L2: ring of %d distinct frames (%.0f MB in + %.0f MB out per rank)'
+                              % (nfr, nfr * fb / 1e6, nfr * fb / 1e6)) if workload != 'c1' else
+                             'L2 flushed?  no: the 0.85 MB fixture is L2-resident by nature; this line is the latency of the path on '
+                             'the reference\'s own test image, not a bandwidth figure',
                        'parallelism': 'independent frames per GPU, no collective',
                        'streams': 'extract: base and derived forward transforms run concurrently on two streams in the timed '
                                   'region; the per-kernel table / roofline times every kernel alone on one stream'},
@@ -585,12 +607,15 @@ def run_ours(args, wl):
             'roofline': roofline, 'kernels': kernels, 'whole_step': dict(step_algo, **whole),
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk,
             'min_similarity': float(sims.min()),
-        })
+        }
     if bank is not None:
         bank.close()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    for p_ in (_p1, _p2, _p3, _p4, _p5):
+        lib.ssw_host_free(p_)
+    del frames, outs, marks, ext, sim
+    torch.cuda.empty_cache()
+    return result
 
 
 # ------------------------------------------------------------------------------------------------
@@ -611,17 +636,7 @@ def run_c4(args, wl):
     from spread_spectrum_watermarking_b200 import sharded
     from spread_spectrum_watermarking_b200._lib import check, lib, ssw_config
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus:
-        raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)' % (args.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py (impl ours) needs a CUDA device: the product path has no CPU fallback')
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world, local = dist_setup(args)
     w = h = int(os.environ.get('SSW_C4_SIZE', wl['w']))
     ops = sharded.CudaOps(local)
     ctx = ops.ctx
@@ -746,8 +761,9 @@ def run_c4(args, wl):
     e2e = {'value': px * Ke / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 3 * fb + MARK_LEN * 4,
            'd2h_bytes_per_step': fb + MARK_LEN * 4, 'steps': Ke, 'ms_per_step': e2e_ms / Ke,
            'api': 'sharded.ShardedWriter.mark_rgb8 + ShardedReader.extract (per-rank rows in pinned host memory)'}
+    result = None
     if rank == 0:
-        emit({
+        result = ({
             'metric': 'Mpix/s embed & extract (full-frame DCT+top-k)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
             'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -757,11 +773,14 @@ def run_c4(args, wl):
                        'parallelism': 'rows sharded over %d rank(s); all-to-all transpose between the DCT passes '
                                       '(2 per embed, 1 per image per extract), distributed top-k' % world},
             'roofline': roofline, 'kernels': kernels, 'kernel_ms_per_step': kernel_ms,
+            'exposed_comm_ms_per_step': max(0.0, ms_total / K - kernel_ms),
             'cpu_baseline': None, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'similarity': sim,
+            'min_similarity': sim,
         })
     state.clear()
-    if world > 1:
-        dist.destroy_process_group()
+    del rows, hrows, hout
+    torch.cuda.empty_cache()
+    return result
 
 
 def main():
@@ -770,23 +789,45 @@ def main():
     ap.add_argument('--steps', type=int, default=None, help='default: 200 (ours), 3 (reference arm)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
+                    help='one workload only; default: the c2 line with the other configs as sub-objects '
+                         '(c1, c3, c5 at every N; c4 -- the row-sharded 32768^2 frame -- at N >= 2)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='tuning runs: only 3 end-to-end steps')
+    ap.add_argument('--no-extra', action='store_true', help='default invocation without the c1/c3/c4/c5 sub-objects')
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
     if args.steps is None:
         args.steps = 3 if args.impl == 'reference' else 200
     if args.impl == 'reference':
-        return run_reference(args, wl)
+        return run_reference(args, WORKLOADS[args.workload or 'c2'])
     if args.gpus > 1 and 'WORLD_SIZE' not in os.environ:  # convenience: re-launch under torchrun
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29533')] + sys.argv
         raise SystemExit(subprocess.call(cmd))
     protect_stdout()
+    K, W = args.steps, max(args.warmup, 3)
     if args.workload == 'c4':
-        return run_c4(args, wl)
-    run_ours(args, wl)
+        line = run_c4(args, WORKLOADS['c4'])
+    elif args.workload:
+        line = run_ours(args, WORKLOADS[args.workload], args.workload, K, W)
+    else:
+        # the driver's invocation: BASELINE.json configs[1] is the line; every other config rides along as a sub-object
+        # with its own value, per-kernel table and detection guard (a failed guard aborts the whole run)
+        line = run_ours(args, WORKLOADS['c2'], 'c2', K, W)
+        if not args.no_extra:
+            extra = {}
+            extra['c1'] = run_ours(args, WORKLOADS['c1'], 'c1', min(K, 100), W, with_cpu_baseline=False, e2e_steps=10)
+            extra['c3'] = run_ours(args, WORKLOADS['c3'], 'c3', max(3, min(K, 20)), W, with_cpu_baseline=False, e2e_steps=3)
+            extra['c5'] = run_ours(args, WORKLOADS['c5'], 'c5', min(K, 100), W, with_cpu_baseline=False, e2e_steps=5)
+            if args.gpus >= 2:
+                extra['c4'] = run_c4(args, WORKLOADS['c4'])
+            if line is not None:
+                line.update(extra)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+    if line is not None:
+        emit(line)
 
 
 if __name__ == '__main__':

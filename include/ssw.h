@@ -138,7 +138,10 @@ int ssw_reader_indices(ssw_reader* base, uint64_t* out_host, size_t n);
 int ssw_reader_destroy(ssw_reader* r);
 
 /* ---- Tester::similarity -- src/algorithm.rs:696-714.  One kernel thread walks one mark in the
- *      reference's sequential f32 order, so the result is bit-identical to the reference loop. */
+ *      reference's sequential f32 order, so the result is bit-identical to the reference loop.
+ *      Bank searches and the 1:1 scores of the fused pipelines default to a fixed-shape tree reduction
+ *      (deterministic, a few ulp from the sequential loop; north_star asks for 1e-3 relative) that runs at HBM
+ *      speed; SSW_SIM_EXACT=1 in the environment of ssw_ctx_create selects the sequential order there too. */
 int ssw_similarity(ssw_ctx* ctx, const float* extracted_host, const float* mark_host, size_t n, float* out);
 /* bank of stored marks [n_marks][n] resident on the device (README.md:62 "test against any number
  * of marks"); out is [n_extracted][n_marks]. */
@@ -170,8 +173,15 @@ int ssw_embed_batch_rgb8(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, 
 int ssw_extract_batch_rgb8(ssw_ctx* ctx, const uint8_t* base_rgb_host, const uint8_t* derived_rgb_host,
                            uint32_t width, uint32_t height, uint32_t batch, const ssw_config* cfg,
                            size_t n, float* extracted_host, const float* marks_host, float* sim_host);
-/* status of the last fused call: 0 ok, 1 = top-k candidate overflow (degenerate spectrum; the call
- * already re-ran the exact general path), checked after the stream is synchronised. */
+/* Number of frames of the fused calls since the last query whose ordered top-k could not be served by the
+ * candidate list (degenerate, noise-like spectrum: more than SSW_TOPK_CAP near-equal keys).  Synchronises the
+ * stream.  What the calls did with such frames:
+ *   _dev entry points (no host synchronisation inside, hence no repair): the frame is left UNMARKED (embed:
+ *     the output is the input up to the transform round trip; extract: the vector is zero, the score NaN) --
+ *     never modified through a wrong index list.  Callers poll this counter and re-run those frames through
+ *     the Writer / Reader API, which repairs (full-plane histogram, then the exact general sort).
+ *   host-buffer entry points: re-run the whole batch once with the full-plane histogram; if frames still
+ *     overflow they return SSW_ERR_UNSUPPORTED (outputs of those frames as above). */
 int ssw_ctx_last_topk_fallbacks(ssw_ctx* ctx);
 
 /* ---- synthetic frames for the benchmark (SURVEY.md section 8(d) generator, integer only) */

@@ -393,3 +393,38 @@ int oracle_forward_rgb8(const uint8_t* rgb, int width, int height, float* coeff)
     free(i); free(q);
     return 0;
 }
+
+/* Synthetic natural-image-like RGB8 frame of the benchmark (value-noise octaves 2..8 +
+ * dither, integer only).  Not part of the reference: the C form of ssw_oracle.py:synth_frame, so that the reference
+ * arm of bench.py can build its inputs without a GPU and without libssw.  rows [row0, row0 + n_rows) of frame `img`. */
+static uint64_t sm64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void oracle_synth_rows(int width, uint64_t seed, uint32_t img, uint32_t row0, uint32_t n_rows, uint8_t* out) {
+    const uint64_t base = seed ^ ((uint64_t)img * 0x9E3779B97F4A7C15ull);
+    for (uint32_t yl = 0; yl < n_rows; ++yl) {
+        const uint64_t y = (uint64_t)row0 + yl;
+        for (uint64_t x = 0; x < (uint64_t)width; ++x) {
+            uint8_t* o = out + ((size_t)yl * (size_t)width + x) * 3;
+            for (uint64_t c = 0; c < 3; ++c) {
+                uint64_t acc = 0;
+                for (uint64_t oct = 2; oct <= 8; ++oct) {
+                    const uint64_t s = 1ull << oct;
+                    const uint64_t X = x >> oct, Y = y >> oct, fx = x & (s - 1), fy = y & (s - 1);
+                    const uint64_t tag = base ^ (oct << 58) ^ (c << 56);
+                    const uint64_t l00 = sm64(tag ^ (Y << 28) ^ X) >> 56, l10 = sm64(tag ^ (Y << 28) ^ (X + 1)) >> 56;
+                    const uint64_t l01 = sm64(tag ^ ((Y + 1) << 28) ^ X) >> 56, l11 = sm64(tag ^ ((Y + 1) << 28) ^ (X + 1)) >> 56;
+                    const uint64_t top = l00 * (s - fx) + l10 * fx, bot = l01 * (s - fx) + l11 * fx;
+                    acc += ((top * (s - fy) + bot * fy) >> (2 * oct)) << oct;
+                }
+                const int64_t noise = (int64_t)(sm64(base ^ 0xABCDEFull ^ (c << 56) ^ (y << 28) ^ x) >> 61);
+                int64_t v = (int64_t)(acc / 508ull) + noise - 4;
+                o[c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+        }
+    }
+}

@@ -422,6 +422,23 @@ SSW_HD void pack_u8x4x2(const float2* o, float nz, unsigned& wa, unsigned& wb) {
 }
 #endif
 
+// 12 bytes (4 RGB8 pixels) of row A and of row B, as three words each -> luma pairs y2[i] = (A_i, B_i)
+SSW_HD void luma4x2_words(const unsigned* wa, const unsigned* wb, float nz, cplx* y2) {
+#if defined(__CUDA_ARCH__)
+    float2 c[12];
+    unpack4_unit2(wa, wb, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y2[i] = mat3x2(0.30f, 0.59f, 0.11f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+#else
+    (void)nz;
+    float ca[12], cb[12];
+    unpack4_unit(wa[0], wa[1], wa[2], ca);
+    unpack4_unit(wb[0], wb[1], wb[2], cb);
+    for (int i = 0; i < 4; ++i)
+        y2[i] = mk(rgb_to_y(ca[3 * i], ca[3 * i + 1], ca[3 * i + 2]), rgb_to_y(cb[3 * i], cb[3 * i + 1], cb[3 * i + 2]));
+#endif
+}
+
 // 4 pixels of row A (pixel index pa4) and of row B (pb4) -> luma pairs y2[i] = (A_i, B_i).  Rows that do not exist
 // (hb false: odd frame height) read row A again and are zeroed.
 template <int SRC>
@@ -431,10 +448,7 @@ SSW_HD void load_luma4x2(const void* src, long long pa4, long long pb4, bool hb,
         const unsigned* qa = (const unsigned*)((const unsigned char*)src + 3 * pa4);
         const unsigned* qb = (const unsigned*)((const unsigned char*)src + 3 * (hb ? pb4 : pa4));
         const unsigned wa[3] = {ldw(qa), ldw(qa + 1), ldw(qa + 2)}, wb[3] = {ldw(qb), ldw(qb + 1), ldw(qb + 2)};
-        float2 c[12];
-        unpack4_unit2(wa, wb, c);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) y2[i] = mat3x2(0.30f, 0.59f, 0.11f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+        luma4x2_words(wa, wb, nz, y2);
         if (!hb) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) y2[i].y = 0.f;
@@ -450,6 +464,43 @@ SSW_HD void load_luma4x2(const void* src, long long pa4, long long pb4, bool hb,
     for (int i = 0; i < 4; ++i) y2[i] = mk(ya[i], yb[i]);
 }
 
+// new luma pairs y2[i] = (A_i, B_i) of 4 pixels of rows A and B + the 12 original bytes of each row (chroma) -> the 12
+// output bytes of each row, as words.  oa / ob may alias wa / wb (the pipelines convert in place).
+SSW_HD void rgb8_out4x2_words(const unsigned* wa, const unsigned* wb, float nz, const cplx* y2, unsigned* oa, unsigned* ob) {
+#if defined(__CUDA_ARCH__)
+    float2 c[12], o[12];
+    unpack4_unit2(wa, wb, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 ci = mat3x2(0.60f, -0.28f, -0.32f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+        const float2 cq = mat3x2(0.21f, -0.52f, 0.31f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
+        // src/yiq.rs:163-165 rows of YIQ_TO_RGB_MATRIX, (m0*y + m1*i) + m2*q, m0 == 1
+        o[3 * i] = __fadd2_rn(__fadd2_rn(y2[i], prod2(0.948262f, ci, nz)), prod2(0.624013f, cq, nz));
+        o[3 * i + 1] = __fadd2_rn(__fadd2_rn(y2[i], prod2(-0.276066f, ci, nz)), prod2(-0.639810f, cq, nz));
+        o[3 * i + 2] = __fadd2_rn(__fadd2_rn(y2[i], prod2(-1.105450f, ci, nz)), prod2(1.729860f, cq, nz));
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) pack_u8x4x2(o + 4 * j, nz, oa[j], ob[j]);
+#else
+    (void)nz;
+    for (int row = 0; row < 2; ++row) {
+        const unsigned* wsrc = row ? wb : wa;
+        float c[12], o[12];
+        unpack4_unit(wsrc[0], wsrc[1], wsrc[2], c);
+        for (int i = 0; i < 4; ++i) {
+            const float y = row ? y2[i].y : y2[i].x;
+            const float ci = rgb_to_i(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+            const float cq = rgb_to_q(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+            o[3 * i] = SSW_FADD(SSW_FADD(y, SSW_FMUL(0.948262f, ci)), SSW_FMUL(0.624013f, cq));
+            o[3 * i + 1] = SSW_FADD(SSW_FADD(y, SSW_FMUL(-0.276066f, ci)), SSW_FMUL(-0.639810f, cq));
+            o[3 * i + 2] = SSW_FADD(SSW_FADD(y, SSW_FMUL(-1.105450f, ci)), SSW_FMUL(1.729860f, cq));
+        }
+        unsigned* od = row ? ob : oa;
+        od[0] = pack_u8x4(o); od[1] = pack_u8x4(o + 4); od[2] = pack_u8x4(o + 8);
+    }
+#endif
+}
+
 // new luma pairs y2[i] = (A_i, B_i) of 4 pixels of rows A and B (+ chroma of the original pixels) -> destination
 template <int DST, int SRC>
 SSW_HD void store_pix4x2(const void* src, void* dst, long long pa4, long long pb4, bool hb, float nz, const cplx* y2) {
@@ -458,25 +509,14 @@ SSW_HD void store_pix4x2(const void* src, void* dst, long long pa4, long long pb
         const unsigned* qa = (const unsigned*)((const unsigned char*)src + 3 * pa4);
         const unsigned* qb = (const unsigned*)((const unsigned char*)src + 3 * (hb ? pb4 : pa4));
         const unsigned wa[3] = {ldw(qa), ldw(qa + 1), ldw(qa + 2)}, wb[3] = {ldw(qb), ldw(qb + 1), ldw(qb + 2)};
-        float2 c[12], o[12];
-        unpack4_unit2(wa, wb, c);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 ci = mat3x2(0.60f, -0.28f, -0.32f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
-            const float2 cq = mat3x2(0.21f, -0.52f, 0.31f, c[3 * i], c[3 * i + 1], c[3 * i + 2], nz);
-            // src/yiq.rs:163-165 rows of YIQ_TO_RGB_MATRIX, (m0*y + m1*i) + m2*q, m0 == 1
-            o[3 * i] = __fadd2_rn(__fadd2_rn(y2[i], prod2(0.948262f, ci, nz)), prod2(0.624013f, cq, nz));
-            o[3 * i + 1] = __fadd2_rn(__fadd2_rn(y2[i], prod2(-0.276066f, ci, nz)), prod2(-0.639810f, cq, nz));
-            o[3 * i + 2] = __fadd2_rn(__fadd2_rn(y2[i], prod2(-1.105450f, ci, nz)), prod2(1.729860f, cq, nz));
-        }
+        unsigned ua[3], ub[3];
+        rgb8_out4x2_words(wa, wb, nz, y2, ua, ub);
         unsigned* da = (unsigned*)((unsigned char*)dst + 3 * pa4);
         unsigned* db = (unsigned*)((unsigned char*)dst + 3 * pb4);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            unsigned ua, ub;
-            pack_u8x4x2(o + 4 * j, nz, ua, ub);
-            da[j] = ua;
-            if (hb) db[j] = ub;
+            da[j] = ua[j];
+            if (hb) db[j] = ub[j];
         }
         return;
     }

@@ -19,6 +19,9 @@
 // threads between barriers; tests/emul runs the same phase functions on the CPU with memcpy standing in for the TMA.
 #pragma once
 #include "dct_fast.cuh"
+#if defined(__CUDACC__)
+#include "select_kernels.cuh"
+#endif
 
 namespace ssw {
 namespace fast {
@@ -30,6 +33,18 @@ struct PipeArgs {
     const cplx* tw;            // stage twiddles (global copy)
     const cplx* t4;            // exp(-i*pi*k/(2N)) (global copy)
     int pdl_late;
+#if defined(__CUDACC__)
+    // forward pass only: the selection bin of the ordering that follows (select_kernels.cuh), computed on the fly.  The
+    // tiles that produce the low-frequency block -- coefficient rows < hist_rows, columns < hist_cols -- add its
+    // histogram (top 12 key bits) to ts.hist[image]; the last of them (ticket) finds the bin of the block's k-th
+    // largest key, stores it in ts.sel_bin[image] and leaves histogram and ticket zeroed.  This replaces the
+    // topk_block_bin kernel on the latency chain of the step.  ts.hist == nullptr: no histogram (inverse passes, derived frames).
+    TopkScratch ts;
+    unsigned hist_k;
+    int hist_rows, hist_cols;
+    OrderConsts oc;
+    int tile_rot;   // tile = (first + j*step + total - tile_rot) % total: keeps the histogram tiles off the CTAs that get one tile more
+#endif
 };
 
 // largest divisor of n that is <= cap (rows per TMA box)
@@ -186,6 +201,144 @@ struct ColPipe {
     };
 };
 
+// =====================================================================================================================
+// Row passes as persistent, warp-specialised bulk-copy pipelines (RGB8 in / RGB8 out: the passes of the embed / extract
+// step).  Same arithmetic as RowFwd / RowInv (dct_fast.cuh) -- the row half of /root/reference/src/dct2d.rs:129-170 with
+// the colour conversion of /root/reference/src/yiq.rs:177-197 fused -- restructured like the column pipelines:
+//   * one CTA per SM slot looping over its tiles; tile = TEAMS row pairs = 2*TEAMS adjacent rows, which are CONTIGUOUS
+//     in memory on both sides, so every transfer is one linear bulk copy (cp.async.bulk, no tensor map);
+//   * a PRODUCER warp (one elected thread) moves the tiles, signalled by mbarriers:
+//       forward : A <- RGB8 rows of tile j+1 as soon as the conversion phase of tile j has consumed A;
+//                 B -> coefficient rows of tile j once the post pass has filled B;
+//       inverse : A <- coefficient rows (consumed by the pre pass); B <- original RGB8 rows, converted IN PLACE to the
+//                 output RGB8 rows by the last phase and stored from there; the next tile's originals follow the store;
+//   * COMPUTE teams of P::T threads own one row pair each; they never touch global memory except for twiddles, wait only
+//     on mbarriers (tile landed / buffer drained) and on their own team's named barrier between FFT stages, so the
+//     teams of a CTA drift apart and the conversion, FFT and post phases of different row pairs overlap on the SM.
+// Shared memory per CTA: A + B + TEAMS FFT buffers (22*N bytes per team: 84.5 KB for one 3840-point row pair -> two
+// CTAs per SM).
+// =====================================================================================================================
+struct RowPipeArgs {
+    int w, h, batch;
+    int tiles_per_image, total_tiles;
+    const unsigned char* pix;   // forward: source RGB8 frames; inverse: the original RGB8 frames (chroma)
+    float* plane;               // forward: destination coefficient planes; inverse: source
+    unsigned char* out;         // inverse: destination RGB8 frames
+    float scale0, scalen;       // forward: factors for k == 0 / k > 0; inverse: scale0 = output scale
+    const cplx* tw;
+    const cplx* t4;
+    int pdl_late;
+    float neg_zero;             // -0.0f at run time, see FastArgs
+};
+
+template <class P_, int TEAMS_, bool INVERSE_, int MINB_ = 2>
+struct RowPipe {
+    using P = P_;
+    static constexpr int N = P_::N, T = P_::T, TEAMS = TEAMS_, ROWS = 2 * TEAMS_, MINB = MINB_;
+    static constexpr bool INVERSE = INVERSE_;
+    static constexpr int NC = TEAMS_ * P_::T, THREADS = NC + 32;
+    static constexpr int PIX_ROW = 3 * N, COEF_ROW = 4 * N;              // bytes per row
+    static constexpr int PIX_BYTES = ROWS * PIX_ROW, COEF_BYTES = ROWS * COEF_ROW;
+    static_assert(PIX_BYTES % 16 == 0 && COEF_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+    static constexpr int A_BYTES = INVERSE_ ? COEF_BYTES : PIX_BYTES;    // input side
+    static constexpr int B_BYTES = INVERSE_ ? PIX_BYTES : COEF_BYTES;    // output side
+    static constexpr int al128(int b) { return (b + 127) / 128 * 128; }
+    static constexpr int OFF_A = 0, OFF_B = al128(A_BYTES), OFF_FFT = OFF_B + al128(B_BYTES);
+    static constexpr int FFT_BYTES = TEAMS_ * P_::PITCH * (int)sizeof(cplx);
+    static constexpr int OFF_BAR = OFF_FFT + al128(FFT_BYTES);
+    static constexpr int SMEM = OFF_BAR + 64;
+    static constexpr bool FITS = SMEM <= (228 * 1024) / MINB_ - 1024;
+    static constexpr int NPH = 2 + 2 * P_::NST;
+    using Thread = ThreadState<P_>;
+    static bool supports(int w, int h) { return w == N && h > 0 && h % ROWS == 0; }
+    static int tiles_per_image(int w, int h) { (void)w; return h / ROWS; }
+
+    // c: compute thread id (team g = c / T owns rows 2g, 2g+1 of the tile)
+    template <int PH>
+    static SSW_HD void phase(const RowPipeArgs& a, unsigned char* bufA, cplx* fft, unsigned char* bufB, int c, Thread& th) {
+        const int g = c / T, t = c - g * T;
+        cplx* s = fft + g * P::PITCH;
+        if constexpr (PH > 0 && PH < NPH - 1) {
+            fft_phase<P, PH>(s, a.tw, t, th.v);
+        } else if constexpr (!INVERSE && PH == 0) {
+            // staged RGB8 bytes -> luma -> Makhoul-ordered FFT input (RowFwd phase 0 without the global loads)
+            const unsigned* sa = (const unsigned*)(bufA + (2 * g) * PIX_ROW);
+            const unsigned* sb = (const unsigned*)(bufA + (2 * g + 1) * PIX_ROW);
+#pragma unroll
+            for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
+                const int u = t + it * T;
+                if (u < N / 4) {
+                    const unsigned wa[3] = {sa[3 * u], sa[3 * u + 1], sa[3 * u + 2]}, wb[3] = {sb[3 * u], sb[3 * u + 1], sb[3 * u + 2]};
+                    cplx y2[4];
+                    luma4x2_words(wa, wb, a.neg_zero, y2);
+                    put4x2<P>(s, u, y2);
+                }
+            }
+        } else if constexpr (!INVERSE) {
+            // DCT-II post pass -> coefficient rows in B (RowFwd last phase, shared-memory destination)
+            float* oa = (float*)(bufB + (2 * g) * COEF_ROW);
+            float* ob = oa + N;
+#pragma unroll 4
+            for (int k = t; k <= N / 2; k += T) {
+                const int kr = k ? N - k : 0;
+                float xa, xb, ya, yb;
+                dct2_post(s[P::idx(k)], s[P::idx(kr)], SSW_LDG(&a.t4[k]), xa, xb, ya, yb);
+                const float sk = k ? a.scalen : a.scale0;
+                oa[k] = xa * sk;
+                ob[k] = xb * sk;
+                if (k && kr != k) {
+                    oa[kr] = ya * a.scalen;
+                    ob[kr] = yb * a.scalen;
+                }
+            }
+        } else if constexpr (PH == 0) {
+            // DCT-III pre pass from the staged coefficient rows (RowInv phase 0)
+            const float* ia = (const float*)(bufA + (2 * g) * COEF_ROW);
+            const float* ib = ia + N;
+#pragma unroll 4
+            for (int k = t; k <= N / 2; k += T) {
+                const int kr = k ? N - k : 0;
+                const float pa = ia[k], pb = ib[k];
+                const float qa = k ? ia[kr] : 0.f, qb = k ? ib[kr] : 0.f;
+                cplx zk, zr;
+                dct3_pre(pa, pb, qa, qb, SSW_LDG(&a.t4[k]), zk, zr);
+                s[P::idx(k)] = zk;
+                if (k && kr != k) s[P::idx(kr)] = zr;
+            }
+        } else {
+            // FFT output -> new luma; + chroma of the original bytes in B -> output bytes, in place (RowInv last phase)
+            unsigned* wa = (unsigned*)(bufB + (2 * g) * PIX_ROW);
+            unsigned* wb = (unsigned*)(bufB + (2 * g + 1) * PIX_ROW);
+#pragma unroll
+            for (int it = 0; it < (N / 4 + T - 1) / T; ++it) {
+                const int u = t + it * T;
+                if (u < N / 4) {
+                    cplx f[4];
+                    get4<P>(s, u, f);
+                    cplx y2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y2[i] = cmul_lanes_x(f[i], a.scale0, -a.scale0, a.neg_zero);   // feeds the colour adds: no contraction
+                    const unsigned ia[3] = {wa[3 * u], wa[3 * u + 1], wa[3 * u + 2]}, ib[3] = {wb[3 * u], wb[3 * u + 1], wb[3 * u + 2]};
+                    unsigned oa[3], ob[3];
+                    rgb8_out4x2_words(ia, ib, a.neg_zero, y2, oa, ob);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { wa[3 * u + j] = oa[j]; wb[3 * u + j] = ob[j]; }
+                }
+            }
+        }
+    }
+};
+
+// default shape of the row pipelines of a plan: ~256 compute threads per CTA, two CTAs per SM when they fit
+template <class P> struct RowPipeCfg {
+    static constexpr int TEAMS = P::T >= 192 ? 1 : (P::T >= 96 ? 2 : 4);
+    static constexpr int MINB = RowPipe<P, TEAMS, false, 2>::FITS ? 2 : 1;
+    static constexpr bool OK = !P::PAD && RowPipe<P, TEAMS, false, MINB>::FITS && RowPipe<P, TEAMS, true, MINB>::FITS &&
+                               (TEAMS * P::T + 32) <= 1024;
+    using Fwd = RowPipe<P, TEAMS, false, MINB>;
+    using Inv = RowPipe<P, TEAMS, true, MINB>;
+};
+
 #if defined(__CUDACC__)
 // ---- PTX wrappers: mbarrier, TMA, named barriers ---------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -270,12 +423,13 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
 
     const int first = blockIdx.x, step = gridDim.x;
     const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
+    auto tile_of = [&](int j) { int t = first + j * step - a.tile_rot; return t < 0 ? t + a.total_tiles : t; };
 
     if (tid >= NC) {
         // ===================== producer warp =====================
         if (tid == NC) {
             auto issue_load = [&](int j) {
-                const int tile = first + j * step, b = j & 1;
+                const int tile = tile_of(j), b = j & 1;
                 const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
                 const unsigned dst = sbase + b * K::BUF_BYTES, bar = bar_full0 + 8 * b;
                 mbar_expect_tx(bar, K::BUF_BYTES);
@@ -289,7 +443,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
                 }
             };
             auto issue_store = [&](int j) {
-                const int tile = first + j * step, b = j & 1;
+                const int tile = tile_of(j), b = j & 1;
                 const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
                 const unsigned src = sbase + b * K::BUF_BYTES;
                 if constexpr (!K::INVERSE) {
@@ -338,9 +492,144 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
             });
             if (rd + 1 < K::ROUNDS) named_sync(1, NC);         // FFT buffers are free for the next round
         }
+        if constexpr (!K::INVERSE) {
+            if (a.ts.hist) {
+                const int tile = tile_of(j), img = tile / a.tiles_per_image;
+                const int c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
+                if (c0 < a.hist_cols) {                        // (uniform over the CTA)
+                    static_assert(K::FFT_BYTES >= (kHistBins + 40) * 4, "the FFT buffers double as the histogram");
+                    unsigned* sh = (unsigned*)fft;             // 4096 bins + scratch, free once the post passes are done
+                    named_sync(1, NC);                         // the post pass of every team has written its coefficient rows
+                    for (int i = tid; i < kHistBins; i += NC) sh[i] = 0u;
+                    named_sync(1, NC);
+                    const float* cf = (const float*)buf;       // row k of the tile: 2G adjacent columns starting at c0
+                    for (int e = tid; e < a.hist_rows * 2 * K::G; e += NC) {
+                        const int r = e / (2 * K::G), cc = e - r * (2 * K::G);
+                        const unsigned pidx = (unsigned)r * (unsigned)a.w + (unsigned)(c0 + cc);
+                        if (pidx && c0 + cc < a.hist_cols) atomicAdd(sh + (order_key(cf[e], pidx, a.oc) >> (32 - kHistBits)), 1u);
+                    }
+                    named_sync(1, NC);
+                    unsigned* gh = a.ts.hist + (size_t)img * kHistBins;
+                    for (int i = tid; i < kHistBins; i += NC)
+                        if (sh[i]) atomicAdd(gh + i, sh[i]);
+                    __threadfence();
+                    named_sync(1, NC);
+                    const unsigned n_hist_tiles = (unsigned)((a.hist_cols + 2 * K::G - 1) / (2 * K::G));
+                    if (tid == 0) sh[kHistBins + 36] = (atomicAdd(a.ts.ticket + img, 1u) == n_hist_tiles - 1u) ? 1u : 0u;
+                    named_sync(1, NC);
+                    if (sh[kHistBins + 36]) {                  // last histogram tile of this image: the block is complete
+                        __threadfence();
+                        for (int i = tid; i < kHistBins; i += NC) { sh[i] = __ldcg(gh + i); gh[i] = 0u; }
+                        named_sync(1, NC);
+                        const unsigned bsel = find_kth_bin_team(sh, a.hist_k, tid, NC, 1, sh + kHistBins);
+                        if (tid == 0) { a.ts.sel_bin[img] = bsel; a.ts.ticket[img] = 0u; }
+                    }
+                    named_sync(1, NC);                         // the FFT buffers go back to the next tile
+                }
+            }
+        }
         fence_proxy_async();                                   // generic-proxy writes of BUF[b] -> visible to the TMA store
         named_sync(1, NC);                                     // (also: FFT buffers free for the next tile)
         if (tid == 0) mbar_arrive(bar_ready0 + 8 * b);
+    }
+}
+
+// ---- linear bulk copies (cp.async.bulk, no tensor map): global -> shared signals an mbarrier, shared -> global joins a bulk group
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// mbarriers (8 bytes each, at OFF_BAR): fullA, freeA, fullB (inverse: originals landed) / drainedB (forward: the store has read B), readyB
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __grid_constant__ RowPipeArgs a) {
+    extern __shared__ __align__(1024) unsigned char pipe_smem[];
+    constexpr int NC = K::NC;
+    const int tid = threadIdx.x;
+    const unsigned sbase = smem_u32(pipe_smem);
+    const unsigned bar_fullA = sbase + K::OFF_BAR, bar_freeA = bar_fullA + 8, bar_inB = bar_fullA + 16, bar_readyB = bar_fullA + 24;
+    if (tid == 0) {
+        mbar_init(bar_fullA, 1);      // producer's expect_tx arrival + the bytes of the copy
+        mbar_init(bar_freeA, NC);     // every compute thread has consumed A
+        mbar_init(bar_inB, 1);        // forward: producer arrives when the store has read B; inverse: expect_tx of the originals
+        mbar_init(bar_readyB, NC);    // every compute thread has written (and fenced) its part of B
+        fence_mbar_init();
+    }
+    if (!a.pdl_late) pdl_trigger();
+    __syncthreads();
+    pdl_wait();
+
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
+    const size_t frame_px = (size_t)a.w * a.h;
+
+    if (tid >= NC) {
+        // ===================== producer warp =====================
+        if (tid == NC) {
+            auto pix_of = [&](int j, const unsigned char* base) {
+                const int tile = first + j * step, img = tile / a.tiles_per_image;
+                return base + 3 * (img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N);
+            };
+            auto coef_of = [&](int j) {
+                const int tile = first + j * step, img = tile / a.tiles_per_image;
+                return a.plane + img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N;
+            };
+            auto load_a = [&](int j) {
+                mbar_expect_tx(bar_fullA, K::A_BYTES);
+                if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, coef_of(j), K::A_BYTES, bar_fullA);
+                else bulk_load(sbase + K::OFF_A, pix_of(j, a.pix), K::A_BYTES, bar_fullA);
+            };
+            auto load_b = [&](int j) {   // inverse only: the original pixels of the tile
+                mbar_expect_tx(bar_inB, K::B_BYTES);
+                bulk_load(sbase + K::OFF_B, pix_of(j, a.pix), K::B_BYTES, bar_inB);
+            };
+            if (nt > 0) {
+                load_a(0);
+                if constexpr (K::INVERSE) load_b(0);
+            }
+            for (int j = 0; j < nt; ++j) {
+                if (j + 1 < nt) {
+                    mbar_wait(bar_freeA, j & 1);               // tile j has left A
+                    load_a(j + 1);
+                }
+                mbar_wait(bar_readyB, j & 1);                  // results of tile j are in B (writers fenced)
+                if constexpr (K::INVERSE) bulk_store((void*)pix_of(j, a.out), sbase + K::OFF_B, K::B_BYTES);
+                else bulk_store(coef_of(j), sbase + K::OFF_B, K::B_BYTES);
+                tma_commit();
+                if (j + 1 < nt) {
+                    tma_wait_read0();                          // the store has read B
+                    if constexpr (K::INVERSE) load_b(j + 1);
+                    else mbar_arrive(bar_inB);
+                }
+            }
+            tma_wait_all0();                                   // all stores complete before the CTA exits
+        }
+        return;
+    }
+
+    // ===================== compute teams =====================
+    typename K::Thread th;
+    const int team = tid / K::T;
+    cplx* fft = (cplx*)(pipe_smem + K::OFF_FFT);
+    for (int j = 0; j < nt; ++j) {
+        mbar_wait(bar_fullA, j & 1);                           // tile j has landed in A
+        static_for<K::NPH>([&](auto ph) {
+            constexpr int p = decltype(ph)::value;
+            if constexpr (p == K::NPH - 1) {
+                if (a.pdl_late && j + 1 == nt) pdl_trigger();
+                if constexpr (K::INVERSE) mbar_wait(bar_inB, j & 1);           // the originals of tile j have landed in B
+                else { if (j > 0) mbar_wait(bar_inB, (j - 1) & 1); }            // the store of tile j-1 has read B
+            }
+            K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, tid, th);
+            if constexpr (p == 0) mbar_arrive(bar_freeA);                      // (this thread's) reads of A are done
+            if constexpr (p + 1 < K::NPH) named_sync(1 + team, K::T);
+        });
+        fence_proxy_async();                                   // generic-proxy writes of B -> visible to the bulk store
+        mbar_arrive(bar_readyB);
+        named_sync(1 + team, K::T);                            // the team has read its FFT buffer: the next tile may overwrite it
     }
 }
 #endif

@@ -19,6 +19,13 @@ __device__ __forceinline__ float insert_fn(int method, float alpha, float orig, 
     return __fmul_rn(orig, expf(__fmul_rn(alpha, w)));
 }
 
+// extract functions, /root/reference/src/algorithm.rs:566-593 (separately rounded operations, as the reference)
+__device__ __forceinline__ float extract_fn(int method, float alpha, float b, float d) {
+    if (method == 1) return __fdiv_rn(__fsub_rn(d, b), alpha);
+    if (method == 2) return __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
+    return __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
+}
+
 // marks: [batch][n_marks][mark_stride] f32, lens: [n_marks] (NULL = all k)
 __global__ void embed_scatter_kernel(float* __restrict__ planes, long long plane_stride,
                                      const unsigned* __restrict__ idx, long long idx_stride, unsigned k,
@@ -61,11 +68,7 @@ __global__ void extract_gather_kernel(const float* __restrict__ base, const floa
     if (p == 0xFFFFFFFFu) { out[(long long)img * out_stride + i] = 0.f; return; }   // ordering failed (reported): defined output
     const float b = base[(long long)img * plane_stride + p];
     const float d = derived[(long long)img * plane_stride + p];
-    float r;
-    if (method == 1) r = __fdiv_rn(__fsub_rn(d, b), alpha);
-    else if (method == 2) r = __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
-    else r = __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
-    out[(long long)img * out_stride + i] = r;
+    out[(long long)img * out_stride + i] = extract_fn(method, alpha, b, d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -117,10 +120,7 @@ __global__ void extract_gather_shard_kernel(const float* __restrict__ base, cons
     unsigned long long q;
     float r = 0.f;
     if (shard_local(L, idx[i], &q)) {
-        const float b = base[q], d = derived[q];
-        if (method == 1) r = __fdiv_rn(__fsub_rn(d, b), alpha);
-        else if (method == 2) r = __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
-        else r = __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
+        r = extract_fn(method, alpha, base[q], derived[q]);
     }
     out[i] = r;
 }
@@ -288,20 +288,21 @@ similarity_bank_warp_kernel(const float* __restrict__ bank, size_t n_marks, unsi
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if ((((size_t)row) & 15) == 0) {
             const float4* r4 = (const float4*)row;
-            unsigned j = lane;
-            for (; j + 7 * 32 < n4; j += 8 * 32) {       // 8 independent 16-byte loads per lane in flight
+            // blocks of 8 x 32 float4: every lane issues its 8 (predicated) 16-byte loads before the first use, so a
+            // row costs the warp ONE memory latency whatever n is (n = 1000: 250 float4, lanes 26..31 idle in the last slot)
+            for (unsigned base = 0; base < n4; base += 8 * 32) {
                 float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = ld_stream4(r4 + j + 32 * u);
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned j = base + 32 * u + lane;
+                    v[u] = j < n4 ? ld_stream4(r4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const float4 x = ex4[j + 32 * u];
+                    const unsigned j = base + 32 * u + lane;
+                    const float4 x = j < n4 ? ex4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
                     a0 = fmaf(x.x, v[u].x, a0); a1 = fmaf(x.y, v[u].y, a1); a2 = fmaf(x.z, v[u].z, a2); a3 = fmaf(x.w, v[u].w, a3);
                 }
-            }
-            for (; j < n4; j += 32) {
-                const float4 v = ld_stream4(r4 + j), x = ex4[j];
-                a0 = fmaf(x.x, v.x, a0); a1 = fmaf(x.y, v.y, a1); a2 = fmaf(x.z, v.z, a2); a3 = fmaf(x.w, v.w, a3);
             }
             for (unsigned t = (n4 << 2) + lane; t < n; t += 32) a0 = fmaf(ex[t], __ldg(row + t), a0);
         } else {
@@ -314,62 +315,10 @@ similarity_bank_warp_kernel(const float* __restrict__ bank, size_t n_marks, unsi
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fused extraction + 1:1 score of the batch pipelines: one CTA per frame gathers the n coefficient pairs, applies the
-// extraction function (bit-faithful, as extract_gather_kernel), stores the vector and -- when marks are given --
-// reduces sum(e*m) and sum(e*e) in a fixed-shape tree (per-thread strided partial sums, xor-shuffle tree per warp,
-// warps in order): deterministic, within a few ulp of the sequential loop of src/algorithm.rs:696-714.
-// An index list that starts with 0xFFFFFFFF marks a frame whose ordering failed (candidate overflow): the vector is
-// zero-filled and the score is NaN instead of reading coefficients at arbitrary places.
-// ------------------------------------------------------------------------------------------------
-constexpr int kGatherSimThreads = 1024;
-constexpr unsigned kBadIndex = 0xFFFFFFFFu;
+constexpr unsigned kBadIndex = 0xFFFFFFFFu;   // index list entry of a frame whose ordering failed (candidate overflow)
 
-__global__ void __launch_bounds__(kGatherSimThreads)
-extract_gather_sim_kernel(const float* __restrict__ base, const float* __restrict__ derived, long long plane_stride,
-                          const unsigned* __restrict__ idx, long long idx_stride, unsigned n, int method, float alpha,
-                          float* __restrict__ out, long long out_stride, const float* __restrict__ marks, long long mark_stride,
-                          float* __restrict__ sim) {
-    pdl_enter();
-    __shared__ float red[2][kGatherSimThreads / 32];
-    const unsigned img = blockIdx.x;
-    const unsigned* ix = idx + (long long)img * idx_stride;
-    const float* b0 = base + (long long)img * plane_stride;
-    const float* d0 = derived + (long long)img * plane_stride;
-    const bool bad = ix[0] == kBadIndex;
-    float num = 0.f, den = 0.f;
-    for (unsigned i = threadIdx.x; i < n; i += kGatherSimThreads) {
-        float r = 0.f;
-        if (!bad) {
-            const unsigned p = ix[i];
-            const float b = b0[p], d = d0[p];
-            if (method == 1) r = __fdiv_rn(__fsub_rn(d, b), alpha);
-            else if (method == 2) r = __fdiv_rn(__fsub_rn(d, b), __fmul_rn(b, alpha));
-            else r = __fdiv_rn(logf(__fdiv_rn(d, b)), alpha);
-        }
-        out[(long long)img * out_stride + i] = r;
-        if (marks) {
-            num = fmaf(r, __ldg(marks + (long long)img * mark_stride + i), num);
-            den = fmaf(r, r, den);
-        }
-    }
-    if (!sim) return;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        num += __shfl_xor_sync(0xFFFFFFFFu, num, d);
-        den += __shfl_xor_sync(0xFFFFFFFFu, den, d);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[0][warp] = num; red[1][warp] = den; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float a = 0.f, q = 0.f;
-        for (int wv = 0; wv < kGatherSimThreads / 32; ++wv) { a += red[0][wv]; q += red[1][wv]; }
-        sim[img] = bad ? __int_as_float(0x7FC00000) : __fdiv_rn(a, __fsqrt_rn(q));
-    }
-}
-
-// 1:1 form: extracted vector i against mark i (the fused extract pipeline).
+// 1:1 form: extracted vector i against mark i, sequential order (the fused extract pipeline under SSW_SIM_EXACT=1;
+// by default the score is reduced by the last CTA of topk_rank, select_kernels.cuh).
 constexpr int kPairsPerCta = 2;   // two warps per pair: one walks the numerator chain, one the denominator chain
 
 __global__ void __launch_bounds__(kPairsPerCta * 64)

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "pdl.cuh"
+#include "mark_kernels.cuh"
 
 namespace ssw {
 
@@ -104,6 +105,40 @@ __device__ __forceinline__ unsigned find_kth_bin(const unsigned* sh, unsigned k)
     }
     __syncthreads();
     return s_bin;
+}
+
+// The same for a subset of a CTA (threads 0..nthreads-1, whole warps, synchronising on named barrier `bar_id`) and
+// any thread count: thread t owns the run of bins [t*per, t*per + per), per = ceil(4096 / nthreads).  `scratch`: 33 words
+// of shared memory.  Used by the forward column pipeline, whose compute warps share the CTA with a producer warp.
+__device__ __forceinline__ unsigned find_kth_bin_team(const unsigned* sh, unsigned k, int tid, int nthreads, int bar_id, unsigned* scratch) {
+    const int per = (kHistBins + nthreads - 1) / nthreads;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int lo = min(tid * per, kHistBins), hi = min(lo + per, kHistBins);
+    unsigned mine = 0;
+    for (int j = lo; j < hi; ++j) mine += sh[j];
+    unsigned incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_down_sync(0xFFFFFFFFu, incl, d);
+        if (lane + d < 32) incl += o;
+    }
+    if (lane == 0) scratch[warp] = incl;
+    if (tid == 0) scratch[32] = 0u;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    unsigned above_warps = 0;
+    for (int u = warp + 1; u < nwarps; ++u) above_warps += scratch[u];
+    const unsigned suffix = above_warps + incl, above = suffix - mine;
+    if (above < k && suffix >= k) {
+        unsigned a = above;
+        int b = hi - 1;
+        for (; b > lo; --b) {
+            if (a + sh[b] >= k) break;
+            a += sh[b];
+        }
+        scratch[32] = (unsigned)b;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    return scratch[32];
 }
 
 // ---- 1. histogram + threshold bin ---------------------------------------------------------------
@@ -262,10 +297,17 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
     pdl_enter();
     __shared__ unsigned off[65];
     if (threadIdx.x == 0) {
-        unsigned run = 0;
-        for (unsigned l = 0; l < n_lists; ++l) { off[l] = run; run += min(counts[l], list_cap); }
+        unsigned run = 0, claimed = 0;
+        bool lost = false;
+        for (unsigned l = 0; l < n_lists; ++l) {
+            off[l] = run; run += min(counts[l], list_cap);
+            claimed += counts[l];                       // what the ranks found, not what their lists could hold
+            lost = lost || counts[l] > list_cap;
+        }
         off[n_lists] = run;
-        ts.cand_count[0] = run;  // > kTopkCap is reported as overflow by topk_rank
+        // a list that overflowed on its rank dropped candidates in arbitrary order: the merged order would be wrong even
+        // if the surviving entries fit -> report a count above the capacity, which topk_rank flags as overflow
+        ts.cand_count[0] = (lost && claimed <= (unsigned)kTopkCap) ? (unsigned)kTopkCap + 1u : max(claimed, run);
     }
     __syncthreads();
     for (unsigned l = 0; l < n_lists; ++l) {
@@ -275,26 +317,58 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
     }
 }
 
-// ---- 3. order the candidates, emit the first k indices ------------------------------------------
+// ---- 3. order the candidates, emit the first k indices -- and consume them -----------------------
 // The composite keys are unique, so the position of a candidate in the descending order is simply the number
 // of candidates with a larger key.  With ~k + one bin of candidates (1049 for k = 1000 on the 4K frame) the
 // n^2 comparisons (1.1 M) spread over kRankCtas CTAs take ~1 us -- far less than a single-CTA bitonic network,
 // whose 66 dependent exchange steps (shuffles, shared-memory round trips, barriers) cost 12-14 us.
 // CTA b ranks candidates [64 b, 64 b + 64) (+ strides of 64 * gridDim.x); 4 thread groups split the comparison
-// range.  The last CTA to finish (ticket) reports overflow and clears the per-image counters for the next call.
+// range.  The thread that learns "candidate p has rank r < k" is also the one that knows everything the next step
+// of the fused pipelines needs, so it performs it in place (TopkApply): the embedding of mark value r into
+// coefficient p (Writer::embed_watermark, /root/reference/src/algorithm.rs:394-398) or the extraction of value r
+// from the base / derived coefficient pair (:556-561).  The last CTA to finish (ticket) reports overflow, clears
+// the per-image scratch for the next call and, for the extraction, reduces the 1:1 similarity score (:696-714) in a
+// fixed-shape tree (deterministic; within a few ulp of the sequential loop, the contract is 1e-3 relative).
+// A frame whose candidate list overflowed (or came up short) is NOT consumed: its index list is filled with
+// kBadIndex, its coefficients stay untouched (the inverse transform then returns the unmarked frame), its extracted
+// vector is zero and its score NaN -- and the sticky overflow counter tells the host (ssw_ctx_last_topk_fallbacks).
 constexpr int kRankThreads = 256, kRankCtas = 32;
 
+struct TopkApply {
+    int mode;                  // 0: indices only; 1: embed (scatter); 2: extract (gather [+ similarity])
+    int method; float alpha;   // insertion / extraction option 1..3
+    float* planes;             // mode 1: coefficient planes, modified in place; mode 2: base planes (read)
+    const float* derived;      // mode 2
+    long long plane_stride;
+    const float* marks;        // mode 1: [img][mark_stride]; mode 2: optional, for the score
+    long long mark_stride;
+    float* out; long long out_stride;   // mode 2: extracted vectors
+    float* sim;                // mode 2: optional scores [img]
+};
+
 __global__ void __launch_bounds__(kRankThreads)
-topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride) {
+topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride, TopkApply ap) {
     pdl_enter();
     extern __shared__ unsigned long long keys[];  // up to kTopkCap candidates
     __shared__ unsigned rank[64];
+    __shared__ unsigned s_last;
+    __shared__ float red[2][kRankThreads / 32];
     const unsigned img = blockIdx.y, tid = threadIdx.x;
     const unsigned total = __ldcg(ts.cand_count + img);
     const unsigned cnt = total < (unsigned)kTopkCap ? total : (unsigned)kTopkCap;
+    const bool bad = total > (unsigned)kTopkCap || cnt < k;
     const unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
     unsigned* out = idx_out + (long long)img * idx_stride;
-    if (blockIdx.x * 64u < cnt) {
+    float* plane = ap.planes ? ap.planes + (long long)img * ap.plane_stride : nullptr;
+    const float* dplane = ap.derived ? ap.derived + (long long)img * ap.plane_stride : nullptr;
+    const float* mk = ap.marks ? ap.marks + (long long)img * ap.mark_stride : nullptr;
+    float* ext = ap.out ? ap.out + (long long)img * ap.out_stride : nullptr;
+    if (bad) {
+        for (unsigned r = blockIdx.x * kRankThreads + tid; r < k; r += gridDim.x * kRankThreads) {
+            out[r] = kBadIndex;
+            if (ap.mode == 2) ext[r] = 0.f;
+        }
+    } else if (blockIdx.x * 64u < cnt) {
         for (unsigned j = tid; j < cnt; j += kRankThreads) keys[j] = __ldcg(cand + j);
         const unsigned slot = tid & 63u, part = tid >> 6;
         const unsigned j0 = (unsigned)(((unsigned long long)cnt * part) >> 2), j1 = (unsigned)(((unsigned long long)cnt * (part + 1)) >> 2);
@@ -310,19 +384,45 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
                 atomicAdd(&rank[slot], above);
             }
             __syncthreads();
-            if (tid < 64u && i < cnt && rank[tid] < k) out[rank[tid]] = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
+            if (tid < 64u && i < cnt && rank[tid] < k) {
+                const unsigned r = rank[tid], p = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
+                out[r] = p;
+                if (ap.mode == 1) plane[p] = insert_fn(ap.method, ap.alpha, plane[p], __ldg(mk + r));
+                else if (ap.mode == 2) ext[r] = extract_fn(ap.method, ap.alpha, plane[p], dplane[p]);
+            }
             __syncthreads();
         }
     }
-    if (blockIdx.x == 0)   // fewer candidates than ranks asked for (reported as overflow): defined output
-        for (unsigned r = cnt + tid; r < k; r += kRankThreads) out[r] = 0u;
+    __threadfence();   // this thread's results are visible device-wide before the CTA takes its ticket
     __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(ts.ticket + img, 1u) == gridDim.x - 1) ? 1u : 0u;   // every CTA of the image has read the counters
+    __syncthreads();
+    if (!s_last) return;
     if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(ts.ticket + img, 1u) == gridDim.x - 1) {   // every CTA of the image has read the counters
-            if (total > (unsigned)kTopkCap || cnt < k) atomicAdd(ts.overflow, 1u);
-            ts.cand_count[img] = 0;
-            ts.ticket[img] = 0;
+        if (bad) atomicAdd(ts.overflow, 1u);
+        ts.cand_count[img] = 0;
+        ts.ticket[img] = 0;
+    }
+    if (ap.mode == 2 && ap.sim) {
+        __threadfence();   // the other CTAs' extracted values (their fence + ticket precede ours)
+        float num = 0.f, den = 0.f;
+        if (!bad)
+            for (unsigned i = tid; i < k; i += kRankThreads) {
+                const float e = __ldcg(ext + i);
+                num = fmaf(e, __ldg(mk + i), num);
+                den = fmaf(e, e, den);
+            }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            num += __shfl_xor_sync(0xFFFFFFFFu, num, d);
+            den += __shfl_xor_sync(0xFFFFFFFFu, den, d);
+        }
+        if ((tid & 31u) == 0u) { red[0][tid >> 5] = num; red[1][tid >> 5] = den; }
+        __syncthreads();
+        if (tid == 0) {
+            float a = 0.f, q = 0.f;
+            for (int wv = 0; wv < kRankThreads / 32; ++wv) { a += red[0][wv]; q += red[1][wv]; }
+            ap.sim[img] = bad ? __int_as_float(0x7FC00000) : __fdiv_rn(a, __fsqrt_rn(q));
         }
     }
 }

@@ -80,6 +80,7 @@ struct ssw_ctx {
     int pf_tiles = 0;                      // SSW_PF_TILES: tiles per CTA of the prefetching kernels (0 = automatic)
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
+    int row_pipe = 1;                      // SSW_ROW_PIPE: 0 RowFwd / RowInv (one CTA per tile); 1 persistent bulk-copy pipelines (dct_pipe.cuh)
     int col_pipe = 1;                      // SSW_COL_PIPE: 0 ColPass (one CTA per tile); 1..3 persistent TMA pipelines (dct_pipe.cuh):
                                            // 1 = 8 columns, 4 teams; 2 = 8 columns, 2 teams x 2 rounds; 3 = 4 columns, 2 teams (2 CTAs / SM)
     void* encode_tiled = nullptr;          // cuTensorMapEncodeTiled (driver entry point, resolved once)
@@ -87,6 +88,10 @@ struct ssw_ctx {
         return std::tie(p, w, h, batch, g) < std::tie(o.p, o.w, o.h, o.batch, o.g); } };
     std::map<MapKey, std::pair<fast::TmaMap, fast::TmaMap>> tma_maps;   // plane -> (sample-side 4-D map, coefficient-side 3-D map)
     struct { bool active = false; int seg_shift = -1, chunk_shift = 0, ranks = 1, lines = 0; } seg;  // ssw_lines_forward_seg_dev
+    // fused pipelines: ask the forward column pipeline for the low-frequency-block histogram of the ordering that
+    // follows (want), learn whether a pipeline produced it (done) -- see run_topk_fast
+    struct { bool want = false, done = false; unsigned k = 0; int ordering = 0; } col_hist;
+    bool sim_exact = false;                // SSW_SIM_EXACT=1: scores in the reference's sequential order (bit-identical)
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -201,6 +206,8 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_TOPK_FULL_HIST")) c->topk_full_hist = atoi(s) != 0;
     if (const char* s = getenv("SSW_FORCE_LINE1")) c->force_line1 = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_PIPE")) c->col_pipe = atoi(s);
+    if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
+    if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     *out = c.release();
     return SSW_OK;
 }
@@ -504,6 +511,62 @@ static bool aligned(const void* p, size_t n) { return (((size_t)p) & (n - 1)) ==
 template <class K, int M> struct WithMinB : K { static constexpr int MINB = M; };
 #endif
 
+// ---- persistent bulk-copy row pipelines (dct_pipe.cuh): RGB8 frames <-> coefficient planes -------------------------
+template <class K>
+static int launch_row_pipe(ssw_ctx* c, const char* name, const void* pix, float* plane, void* out, int w, int h, int batch,
+                           float scale0, float scalen) {
+    using P = typename K::P;
+    fast::RowPipeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.w = w; a.h = h; a.batch = batch; a.scale0 = scale0; a.scalen = scalen;
+    a.pix = (const unsigned char*)pix; a.plane = plane; a.out = (unsigned char*)out;
+    CKS(fast_tables<P>(c, &a.tw, &a.t4));
+    a.tiles_per_image = K::tiles_per_image(w, h);
+    const long long tiles = (long long)a.tiles_per_image * batch;
+    if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
+    a.total_tiles = (int)tiles;
+    a.pdl_late = c->pdl_mode != 0;
+    a.neg_zero = -0.0f;
+    auto kernel = fast::row_pipe_kernel<K>;
+    const void* key = (const void*)kernel;
+    auto it = c->smem_attr.find(key);
+    if (it == c->smem_attr.end()) {
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, K::THREADS, K::SMEM));
+        it = c->smem_attr.emplace(key, std::max(1, occ)).first;   // value: resident CTAs per SM
+    }
+    const long long slots = (long long)it->second * c->sm_count;
+    const unsigned grid = (unsigned)std::min<long long>(tiles, slots);
+    {
+        KScope ks(c, name);
+        launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a);
+    }
+    CK(cudaGetLastError());
+    return SSW_OK;
+}
+
+// *done = true when a pipeline ran.  inverse: d_pix = the original frames, d_out = the destination frames.
+static int pipe_row(ssw_ctx* c, bool inverse, const void* d_pix, float* d_plane, void* d_out, int w, int h, int batch,
+                    float scale0, float scalen, bool* done) {
+    *done = false;
+    if (c->row_pipe <= 0 || c->seg.active) return SSW_OK;
+    // bulk copies need 16-byte aligned tiles on both sides: aligned bases and whole 16-byte frames
+    if (!aligned(d_pix, 16) || !aligned(d_plane, 16) || (inverse && !aligned(d_out, 16)) || (((size_t)w * h * 3) & 15)) return SSW_OK;
+    int rc = SSW_OK;
+    fast::with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        using Cfg = fast::RowPipeCfg<P>;
+        if constexpr (Cfg::OK) {
+            if (!Cfg::Fwd::supports(w, h)) return;
+            if (inverse) rc = launch_row_pipe<typename Cfg::Inv>(c, "inv_rows", d_pix, d_plane, d_out, w, h, batch, scale0, scalen);
+            else rc = launch_row_pipe<typename Cfg::Fwd>(c, "fwd_rows", d_pix, d_plane, nullptr, w, h, batch, scale0, scalen);
+            *done = true;
+        }
+    });
+    return rc;
+}
+
 // returns SSW_OK and sets *done when a fast kernel ran; *done = false -> caller uses the generic kernel
 static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int h, int batch, float* d_plane,
                         float scale0, float scalen, bool* done) {
@@ -511,6 +574,10 @@ static int fast_row_fwd(ssw_ctx* c, int src_type, const void* d_src, int w, int 
     if (!c->use_fast) return SSW_OK;
     if (!aligned(d_plane, 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
     int rc = SSW_OK;
+    if (src_type == PIX_RGB8 && !c->prefetch && !c->row_variant) {
+        CKS(pipe_row(c, false, d_src, d_plane, nullptr, w, h, batch, scale0, scalen, done));
+        if (*done) return SSW_OK;
+    }
 #ifdef SSW_TUNE
     if (w == 3840 && src_type == PIX_RGB8 && c->row_variant) {
         fast::FastArgs a = fast_args(w, h);
@@ -581,6 +648,8 @@ static int launch_col_variant(ssw_ctx* c, const fast::FastArgs& a, int w, int h,
     }
 }
 
+static OrderConsts make_order(int ordering, int w, int h);
+
 // ---- persistent TMA column pipelines (dct_pipe.cuh) ---------------------------------------------------------------
 // tensor maps of a coefficient plane [batch][h][w] f32 for tiles of 2*g columns:
 //   sample side      4-D (column, row parity, row pair, image)  -- even rows / odd rows as separate boxes (Makhoul split)
@@ -640,6 +709,15 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
     if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
     a.total_tiles = (int)tiles;
     a.pdl_late = c->pdl_mode != 0;
+    if (!K::INVERSE && c->col_hist.want && (unsigned)batch <= c->ts_batch) {
+        const bool small = c->col_hist.k <= (unsigned)kSmallMaxK;
+        a.ts = c->ts;
+        a.hist_k = c->col_hist.k;
+        a.hist_rows = std::min(h, small ? kSmallRows : kBlockRows);
+        a.hist_cols = std::min(w, small ? kSmallCols : kBlockCols);
+        a.oc = make_order(c->col_hist.ordering, w, h);
+        c->col_hist.done = true;
+    }
     const std::pair<fast::TmaMap, fast::TmaMap>* maps;
     CKS(tma_maps_for(c, d_plane, w, h, batch, K::G, K::RB_HALF, K::RB_FULL, &maps));
     auto kernel = fast::col_pipe_kernel<K>;
@@ -653,6 +731,11 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
     }
     const long long slots = (long long)it->second * c->sm_count;
     const unsigned grid = (unsigned)std::min<long long>(tiles, slots);
+    if (!K::INVERSE && a.ts.hist && batch == 1) {
+        // one frame: `rot` CTAs get one tile more than the others and finish last -- keep the histogram tiles off them
+        const long long rot = tiles % grid, nh = (a.hist_cols + 2 * K::G - 1) / (2 * K::G);
+        if (rot + nh <= grid) a.tile_rot = (int)rot;
+    }
     {
         KScope ks(c, name);
         launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a, maps->first, maps->second);
@@ -710,6 +793,10 @@ static int fast_row_inv(ssw_ctx* c, float* d_plane, int src_type, const void* d_
         if (!aligned(d_dst, dst_type == PIX_RGB8 ? 4 : 16) || !aligned(d_src, src_type == PIX_RGB8 ? 4 : 16)) return SSW_OK;
     }
     int rc = SSW_OK;
+    if (dst_type == PIX_RGB8 && src_type == PIX_RGB8) {
+        CKS(pipe_row(c, true, d_src, d_plane, d_dst, w, h, batch, scale, scale, done));
+        if (*done) return SSW_OK;
+    }
     *done = fast::with_plan(w, [&](auto p) {
         using P = decltype(p);
         constexpr int G = fast::RowG<P>::value;
@@ -906,16 +993,21 @@ static OrderConsts make_order(int ordering, int w, int h) {
 }
 
 // fast path: k + (one histogram bin of elements) must fit kTopkCap; no host synchronisation.
-// full_hist = false: selection bin from the low-frequency block (topk_block_bin), one pass over the plane;
+// full_hist = false: selection bin from the low-frequency block -- from the histogram the forward column pipeline left
+//                    in ts.hist (hist_ready, see ssw_ctx::col_hist) or from topk_block_bin -- one pass over the plane;
 // full_hist = true : selection bin from a histogram of the whole plane (two passes) -- the repair path.
+// ap: what the ranking kernel does with (rank, index) beyond storing the index list (embed / extract [+ score]).
 static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsigned batch, int ordering,
-                         unsigned k, unsigned* d_idx, long long idx_stride, bool full_hist) {
+                         unsigned k, unsigned* d_idx, long long idx_stride, bool full_hist, bool hist_ready = false,
+                         const TopkApply* ap = nullptr, cudaEvent_t join_before_apply = nullptr) {
     CKS(ensure_topk_scratch(c, batch));
     const unsigned n = (unsigned)((size_t)w * h);
     const OrderConsts oc = make_order(ordering, w, h);
     const long long stride = (long long)n;
     unsigned blocks = (unsigned)std::min<size_t>(((size_t)n / 4 + 511) / 512, (size_t)std::max(1u, (unsigned)(c->sm_count * 4) / std::min(batch, (unsigned)(c->sm_count * 4))));
     blocks = std::max(1u, blocks);
+    // hist_ready: the forward column pipeline has already left the selection bin of the low-frequency block in ts.sel_bin
+    if (full_hist && hist_ready) return fail(SSW_ERR_STATE, "selection bin requested from both the block and the full plane");
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
@@ -924,13 +1016,14 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         if (full_hist) {
             KScope ks(c, "topk_hist");
             launch_pdl(c, topk_hist_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, k, oc, ts);
-        } else {
+        } else if (!hist_ready) {
             KScope ks(c, "topk_block_bin");
             launch_pdl(c, topk_block_bin_kernel, dim3(nb), kBinThreads, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
         { KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts); }
         CK(cudaGetLastError());
     }
+    if (join_before_apply) CK(cudaStreamWaitEvent(c->stream, join_before_apply, 0));   // extract: the derived planes
     const void* key = (const void*)topk_rank_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
     if (c->smem_attr.find(key) == c->smem_attr.end()) {
@@ -940,9 +1033,19 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
-        ts.ticket += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap;
-        KScope ks(c, "topk_rank");
-        launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, nb), kRankThreads, smem, c->stream, ts, k, d_idx + (long long)b0 * idx_stride, idx_stride);
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap;
+        TopkApply a;
+        std::memset(&a, 0, sizeof(a));
+        if (ap) {
+            a = *ap;
+            if (a.planes) a.planes += (size_t)b0 * a.plane_stride;
+            if (a.derived) a.derived += (size_t)b0 * a.plane_stride;
+            if (a.marks) a.marks += (size_t)b0 * a.mark_stride;
+            if (a.out) a.out += (size_t)b0 * a.out_stride;
+            if (a.sim) a.sim += b0;
+        }
+        KScope ks(c, ap && ap->mode == 1 ? "topk_rank_embed" : (ap && ap->mode == 2 ? "topk_rank_extract" : "topk_rank"));
+        launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, nb), kRankThreads, smem, c->stream, ts, k, d_idx + (long long)b0 * idx_stride, idx_stride, a);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -1380,8 +1483,10 @@ struct ssw_bank {
     size_t n_marks, n;
 };
 
+// exact: scores in the reference's sequential f32 order (bit-identical to src/algorithm.rs:696-714) -- always for
+// Tester::similarity (one mark), on request (SSW_SIM_EXACT=1) for bank searches, which default to the HBM-speed kernel
 static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, size_t n, const float* d_ext,
-                             size_t n_ext, bool pair_mode, float* d_out) {
+                             size_t n_ext, bool pair_mode, float* d_out, bool exact = false) {
     if (n_marks == 0 || n_ext == 0) return SSW_OK;
     if (pair_mode) {
         if (n_marks > 0x7FFFFFFFull || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
@@ -1401,8 +1506,16 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
         KScope ks(c, "similarity_den");
         launch_pdl(c, similarity_den_kernel, (unsigned)((n_ext + 3) / 4), 128, 0, c->stream, d_ext, (unsigned)n, (long long)n, (unsigned)n_ext, d_den);
     }
-    {
+    if (!exact && !c->sim_exact && n <= (size_t)kWarpSimMaxN) {
+        // default: one warp per stored mark, 16-byte coalesced streaming reads, fixed-shape reduction (HBM speed)
+        const size_t ctas = (n_marks + kWarpSimThreads / 32 - 1) / (kWarpSimThreads / 32);
+        const unsigned gxw = (unsigned)std::max<size_t>(1, std::min<size_t>(ctas, (size_t)c->sm_count * 6));
         KScope ks(c, "similarity_bank");
+        launch_pdl(c, similarity_bank_warp_kernel, dim3(gxw, (unsigned)n_ext), kWarpSimThreads, 0, c->stream,
+            d_bank, n_marks, (unsigned)n, d_ext, (long long)n, d_den, d_out, (long long)n_marks);
+    } else {
+        // SSW_SIM_EXACT=1 (or very long marks): one thread per mark in the reference's sequential order, bit-identical
+        KScope ks(c, "similarity_bank_seq");
         launch_pdl(c, similarity_bank_kernel, dim3((unsigned)gx, (unsigned)n_ext), kSimMarks, 0, c->stream, 
             d_bank, n_marks, (unsigned)n, d_ext, (long long)n, d_den, d_out, (long long)n_marks);
     }
@@ -1420,7 +1533,7 @@ extern "C" int ssw_similarity(ssw_ctx* c, const float* extracted, const float* m
         CK(cudaMemcpyAsync(d, extracted, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(d + n, mark, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
-    CKS(launch_similarity(c, d + n, 1, n, d, 1, false, d + 2 * n));
+    CKS(launch_similarity(c, d + n, 1, n, d, 1, false, d + 2 * n, true));
     CK(cudaMemcpyAsync(out, d + 2 * n, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaFreeAsync(d, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1539,6 +1652,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
     const size_t k = std::min(n, np - 1);
     if (k > (size_t)kTopkCap / 2) return fail(SSW_ERR_UNSUPPORTED, "fused pipeline supports mark lengths up to 4096; use the Writer API");
     const unsigned cb = chunk_images(c, np, batch, 1);
+    CKS(ensure_topk_scratch(c, cb));
     float* d_planes = nullptr;
     unsigned* d_idx = nullptr;
     CK(cudaMallocAsync(&d_planes, (size_t)cb * np * sizeof(float), c->stream));
@@ -1547,15 +1661,20 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
     for (unsigned b0 = 0; b0 < batch && rc == SSW_OK; b0 += cb) {
         const unsigned nb = std::min(cb, batch - b0);
         const uint8_t* src = rgb + (size_t)b0 * np * 3;
+        // the forward column pipeline leaves the low-frequency-block histogram of every frame for the ordering
+        c->col_hist.want = k > 0 && !c->topk_full_hist; c->col_hist.done = false;
+        c->col_hist.k = (unsigned)k; c->col_hist.ordering = cfg->ordering;
         rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
+        const bool hist_ready = c->col_hist.done;
+        c->col_hist.want = false;
         if (rc == SSW_OK && k) {
-            rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k, c->topk_full_hist);
-            if (rc == SSW_OK) {
-                KScope ks(c, "embed_scatter");
-                launch_pdl(c, embed_scatter_kernel, dim3((unsigned)((k + 255) / 256), nb), 256, 0, c->stream, 
-                    d_planes, (long long)np, d_idx, (long long)k, (unsigned)k, marks + (size_t)b0 * n, (long long)n, 1,
-                    nullptr, cfg->method, cfg->alpha);
-            }
+            // ordering + embedding: the ranking kernel applies mark value r to the rank-r coefficient in place
+            TopkApply ap;
+            std::memset(&ap, 0, sizeof(ap));
+            ap.mode = 1; ap.method = cfg->method; ap.alpha = cfg->alpha;
+            ap.planes = d_planes; ap.plane_stride = (long long)np;
+            ap.marks = marks + (size_t)b0 * n; ap.mark_stride = (long long)n;
+            rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k, c->topk_full_hist, hist_ready, &ap);
         }
         if (rc == SSW_OK) rc = run_inverse(c, d_planes, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3);
     }
@@ -1578,6 +1697,7 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
     if (batch == 0 || n == 0) return SSW_OK;
     CKS(ctx_bind(c));
     const unsigned cb = chunk_images(c, np, batch, 2);
+    CKS(ensure_topk_scratch(c, cb));
     float* d_planes = nullptr;
     unsigned* d_idx = nullptr;
     CK(cudaMallocAsync(&d_planes, (size_t)cb * np * 2 * sizeof(float), c->stream));
@@ -1587,9 +1707,26 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         const unsigned nb = std::min(cb, batch - b0);
         float* pb = d_planes;
         float* pd = d_planes + (size_t)cb * np;
+        // ordering + extraction [+ 1:1 score]: the ranking kernel reads the rank-r coefficient pair and stores x*_r
+        TopkApply ap;
+        std::memset(&ap, 0, sizeof(ap));
+        ap.mode = 2; ap.method = cfg->method; ap.alpha = cfg->alpha;
+        ap.planes = pb; ap.derived = pd; ap.plane_stride = (long long)np;
+        ap.marks = marks ? marks + (size_t)b0 * n : nullptr; ap.mark_stride = (long long)n;
+        ap.out = extracted + (size_t)b0 * n; ap.out_stride = (long long)n;
+        ap.sim = (sim && !c->sim_exact) ? sim + b0 : nullptr;
+        auto base_forward = [&]() -> int {
+            c->col_hist.want = !c->topk_full_hist; c->col_hist.done = false;
+            c->col_hist.k = (unsigned)n; c->col_hist.ordering = cfg->ordering;
+            const int r = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
+            c->col_hist.want = false;
+            return r;
+        };
+        bool hist_ready = false;
         if (c->overlap_topk && !c->profiling) {   // per-kernel profiling times every kernel alone, on one stream
             // fork: the derived frame's forward transform runs on the side stream beside the base frame's forward
-            // transform and its (latency-bound) ordering; CTAs of the two transforms fill each other's partial waves
+            // transform and the candidate collection; CTAs of the two transforms fill each other's partial waves.
+            // The join sits before the ranking kernel, the first consumer of the derived planes.
             cudaStream_t main_stream = c->stream;
             CK(cudaEventRecord(c->ev_fork, main_stream));
             CK(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
@@ -1597,23 +1734,16 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
             rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
             c->stream = main_stream;
             CK(cudaEventRecord(c->ev_join, c->aux));
-            if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
-            if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
-            CK(cudaStreamWaitEvent(main_stream, c->ev_join, 0));   // join (also on error paths: keeps the streams ordered)
+            if (rc == SSW_OK) { rc = base_forward(); hist_ready = c->col_hist.done; }
+            if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist, hist_ready, &ap, c->ev_join);
+            else CK(cudaStreamWaitEvent(main_stream, c->ev_join, 0));   // error paths: keep the streams ordered
         } else {
-            rc = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
+            rc = base_forward(); hist_ready = c->col_hist.done;
             if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
-            if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist);
+            if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist, hist_ready, &ap);
         }
-        if (rc == SSW_OK) {
-            {
-                KScope ks(c, "extract_gather");
-                launch_pdl(c, extract_gather_kernel, dim3((unsigned)((n + 255) / 256), nb), 256, 0, c->stream, 
-                    pb, pd, (long long)np, d_idx, (long long)n, (unsigned)n, cfg->method, cfg->alpha,
-                    extracted + (size_t)b0 * n, (long long)n);
-            }
-            if (sim) rc = launch_similarity(c, marks + (size_t)b0 * n, nb, n, extracted + (size_t)b0 * n, nb, true, sim + b0);
-        }
+        if (rc == SSW_OK && sim && c->sim_exact)
+            rc = launch_similarity(c, marks + (size_t)b0 * n, nb, n, extracted + (size_t)b0 * n, nb, true, sim + b0);
     }
     cudaFreeAsync(d_planes, c->stream);
     cudaFreeAsync(d_idx, c->stream);
@@ -1985,7 +2115,8 @@ extern "C" int ssw_shard_topk_merge_dev(ssw_ctx* c, const uint64_t* lists_dev, c
         CK(cudaFuncSetAttribute(topk_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->smem_attr[key] = smem;
     }
-    { KScope ks(c, "topk_rank"); launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, 1), kRankThreads, smem, c->stream, ts, (unsigned)k, idx_dev, 0); }
+    { KScope ks(c, "topk_rank"); TopkApply none; std::memset(&none, 0, sizeof(none));
+      launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, 1), kRankThreads, smem, c->stream, ts, (unsigned)k, idx_dev, 0, none); }
     CK(cudaGetLastError());
     return SSW_OK;
 }

@@ -108,9 +108,57 @@ void emulate_col_pipe(PipeArgs a, float* plane, const cplx* tw, const cplx* t4) 
     }
 }
 
+// persistent bulk-copy row pipelines (dct_pipe.cuh): memcpy stands in for the linear bulk copies of a tile (2*TEAMS
+// adjacent rows); the phases run for all compute threads one after the other
+template <class K>
+void emulate_row_pipe(RowPipeArgs a) {
+    std::vector<unsigned char> A(K::A_BYTES + 16), B(K::B_BYTES + 16);
+    std::vector<cplx> fft((size_t)K::TEAMS * K::P::PITCH + 8);
+    std::vector<typename K::Thread> th(K::NC);
+    a.tiles_per_image = K::tiles_per_image(a.w, a.h);
+    a.total_tiles = a.tiles_per_image * a.batch;
+    const size_t frame_px = (size_t)a.w * a.h;
+    for (int tile = 0; tile < a.total_tiles; ++tile) {
+        const int img = tile / a.tiles_per_image;
+        const size_t px0 = img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N;
+        if (K::INVERSE) {
+            std::memcpy(A.data(), a.plane + px0, K::A_BYTES);
+            std::memcpy(B.data(), a.pix + 3 * px0, K::B_BYTES);
+        } else {
+            std::memcpy(A.data(), a.pix + 3 * px0, K::A_BYTES);
+        }
+        static_for<K::NPH>([&](auto ph) {
+            constexpr int p = decltype(ph)::value;
+            for (int c = 0; c < K::NC; ++c) K::template phase<p>(a, A.data(), fft.data(), B.data(), c, th[c]);
+        });
+        if (K::INVERSE) std::memcpy(a.out + 3 * px0, B.data(), K::B_BYTES);
+        else std::memcpy(a.plane + px0, B.data(), K::B_BYTES);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// row pipelines: forward (pix -> plane) or inverse (plane + original pix -> out); -2 when the length has no pipeline
+int emul_row_pipe(int inverse, const unsigned char* pix, int w, int h, int batch, float* plane, unsigned char* out, float scale0, float scalen) {
+    bool ran = false;
+    with_plan(w, [&](auto p) {
+        using P = decltype(p);
+        using Cfg = RowPipeCfg<P>;
+        if constexpr (Cfg::OK) {
+            if (!Cfg::Fwd::supports(w, h)) return;
+            Tables<P> tb;
+            RowPipeArgs a;
+            std::memset(&a, 0, sizeof(a));
+            a.w = w; a.h = h; a.batch = batch; a.pix = pix; a.plane = plane; a.out = out; a.scale0 = scale0; a.scalen = scalen;
+            a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+            if (inverse) emulate_row_pipe<typename Cfg::Inv>(a); else emulate_row_pipe<typename Cfg::Fwd>(a);
+            ran = true;
+        }
+    });
+    return ran ? 0 : -2;
+}
 
 // variant: 1 = 4 pairs x 4 teams, 2 = 4 pairs x 2 teams (2 rounds), 3 = 2 pairs x 2 teams
 int emul_col_pipe(int variant, int inverse, int w, int h, int batch, float* plane, float scale0, float scalen) {

@@ -225,3 +225,21 @@ def test_col_pipe_matches_col_pass(emul, n, variant, inverse):
     assert emul.emul_col_pipe(variant, inverse, w, n, 2, ptr(got), f32(1.0 if inverse else 0.7), f32(1.0 if inverse else 1.3)) == 0
     assert np.abs(ref).max() > 1.0
     assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize('n,h', [(3840, 4), (1920, 8), (1080, 4), (2160, 2), (640, 8), (1280, 4), (720, 4), (2560, 2), (1440, 4)])
+def test_row_pipe_matches_row_kernels(emul, so, n, h):
+    """persistent bulk-copy row pipelines (csrc/dct_pipe.cuh RowPipe), phases run on the CPU with memcpy standing in for the
+    bulk copies: coefficient planes and RGB8 output must be bit-identical to the one-CTA-per-tile row kernels"""
+    rgb = np.concatenate([so.synth_frame(n, h, seed=n, img=1), so.synth_frame(n, h, seed=n + 1, img=2)])   # batch of 2 frames
+    a, b = np.zeros((2 * h, n), np.float32), np.zeros((2 * h, n), np.float32)
+    assert emul.emul_fast_row_fwd(0, ptr(rgb), n, h, 2, ptr(a), f32(0.7), f32(1.3)) == 0
+    assert emul.emul_row_pipe(0, ptr(rgb), n, h, 2, ptr(b), None, f32(0.7), f32(1.3)) == 0
+    assert np.abs(a).max() > 1.0 and np.array_equal(a, b)
+    rng = np.random.default_rng(n)
+    coef = ((rng.random((2 * h, n)).astype(np.float32) - 0.5) * 2.0)
+    coef[:, 0] += 80.0
+    o1, o2 = np.zeros_like(rgb), np.zeros_like(rgb)
+    assert emul.emul_fast_row_inv(0, 0, ptr(coef.copy()), ptr(rgb), n, h, 2, ptr(o1), f32(2.0 / n)) == 0
+    assert emul.emul_row_pipe(1, ptr(rgb), n, h, 2, ptr(coef.copy()), ptr(o2), f32(2.0 / n), f32(2.0 / n)) == 0
+    assert len(np.unique(o1)) > 50 and np.array_equal(o1, o2)
