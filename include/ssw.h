@@ -173,6 +173,17 @@ int ssw_embed_batch_rgb8(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, 
 int ssw_extract_batch_rgb8(ssw_ctx* ctx, const uint8_t* base_rgb_host, const uint8_t* derived_rgb_host,
                            uint32_t width, uint32_t height, uint32_t batch, const ssw_config* cfg,
                            size_t n, float* extracted_host, const float* marks_host, float* sim_host);
+/* asynchronous forms of the host-buffer calls: enqueue and return; results are valid after ssw_ctx_synchronize().
+ * Consecutive calls overlap (upload of call i+1 beside the kernels and the download of call i: PCIe is full duplex).
+ * Host buffers may be reused between calls without synchronising: a copy touching a host range with an earlier copy
+ * still in flight is ordered behind it (embed -> extract on the same buffers works).  The caller must not touch the
+ * buffers itself before ssw_ctx_synchronize().  Overflowing frames are handled as by the _dev entry points. */
+int ssw_embed_batch_rgb8_async(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t width, uint32_t height,
+                               uint32_t batch, const ssw_config* cfg, const float* marks_host, size_t n,
+                               uint8_t* out_rgb_host);
+int ssw_extract_batch_rgb8_async(ssw_ctx* ctx, const uint8_t* base_rgb_host, const uint8_t* derived_rgb_host,
+                                 uint32_t width, uint32_t height, uint32_t batch, const ssw_config* cfg,
+                                 size_t n, float* extracted_host, const float* marks_host, float* sim_host);
 /* Number of frames of the fused calls since the last query whose ordered top-k could not be served by the
  * candidate list (degenerate, noise-like spectrum: more than SSW_TOPK_CAP near-equal keys).  Synchronises the
  * stream.  What the calls did with such frames:
@@ -183,6 +194,10 @@ int ssw_extract_batch_rgb8(ssw_ctx* ctx, const uint8_t* base_rgb_host, const uin
  *   host-buffer entry points: re-run the whole batch once with the full-plane histogram; if frames still
  *     overflow they return SSW_ERR_UNSUPPORTED (outputs of those frames as above). */
 int ssw_ctx_last_topk_fallbacks(ssw_ctx* ctx);
+
+/* device self-test: the packed f32 -> RGB8 output conversion of the inverse row passes against
+ * round(clamp(v, 0, 1) * 255) (image::into_rgb8, tests/single_simple.rs:28) over all 2^32 float bit patterns */
+int ssw_selftest_pack_u8(ssw_ctx* ctx, uint64_t* mismatches);
 
 /* ---- synthetic frames for the benchmark (SURVEY.md section 8(d) generator, integer only) */
 int ssw_synth_frame_rgb8_dev(ssw_ctx* ctx, uint32_t width, uint32_t height, uint64_t seed,
@@ -246,6 +261,34 @@ int ssw_shard_embed_dev(ssw_ctx* ctx, float* plane_dev, const ssw_shard* sh, con
                         const ssw_config* cfg);
 int ssw_shard_extract_dev(ssw_ctx* ctx, const float* base_plane_dev, const float* derived_plane_dev, const ssw_shard* sh,
                           const uint32_t* idx_dev, size_t n, const ssw_config* cfg, float* out_dev);
+
+/* ---- the same behind one object per rank: orchestration in the library, exchange through peer-mapped memory.
+ *      One process per GPU of one node.  ssw_sharded_create maps the coefficient planes of all ranks into each
+ *      other (CUDA IPC over NVLink / NVSwitch); the block transposes between the two passes of the transform STORE
+ *      their tiles straight into the owner's plane, slice by slice beside the line kernels of the next slice -- there is
+ *      no all-to-all collective.  NCCL (resolved with dlopen at the first use; no link-time dependency) carries the IPC
+ *      handles, the barrier that closes an exchange and the few hundred bytes of the distributed top-k.
+ *      Bootstrap: rank 0 calls ssw_sharded_unique_id and hands the 128 bytes to the other ranks by any means (the
+ *      host application's own channel: MPI, a socket, torch.distributed in the tests), then every rank calls
+ *      ssw_sharded_create (collective).  embed / extract are collective calls, stream-ordered on the context's stream,
+ *      without host synchronisation.  Mirrors Writer::new(img,cfg).mark(&[mark]).into_rgb8() and Reader::base +
+ *      Reader::derived + extract (src/algorithm.rs:295-379, 462-562) for frames of up to 2^32-2 pixels. */
+typedef struct ssw_sharded ssw_sharded;
+#define SSW_SHARDED_ID_BYTES 128
+int ssw_sharded_unique_id(void* id_out /* SSW_SHARDED_ID_BYTES */);
+int ssw_sharded_create(ssw_ctx* ctx, const void* id, int rank, int world, uint32_t width, uint32_t height, ssw_sharded** out);
+int ssw_sharded_destroy(ssw_sharded* s);
+/* rows_dev / out_rows_dev: this rank's rows [rank*H/G, (rank+1)*H/G) as [H/G][W][3] u8; mark_dev: n floats (all ranks) */
+int ssw_sharded_embed_rgb8_dev(ssw_sharded* s, const uint8_t* rows_dev, const ssw_config* cfg, const float* mark_dev, size_t n,
+                               uint8_t* out_rows_dev);
+/* extracted_dev: n floats, the whole vector on every rank */
+int ssw_sharded_extract_rgb8_dev(ssw_sharded* s, const uint8_t* base_rows_dev, const uint8_t* derived_rows_dev,
+                                 const ssw_config* cfg, size_t n, float* extracted_dev);
+/* first n ordered indices (flat r*W + c) of the last embed / extract; this rank's coefficient columns of the base (0) /
+ * derived (1) frame, transposed [W/G][H]; the sticky candidate-overflow flag (read and clear).  All three synchronise. */
+int ssw_sharded_indices(ssw_sharded* s, uint32_t* out_host, size_t n);
+int ssw_sharded_coefficients(ssw_sharded* s, int which, float* out_host);
+int ssw_sharded_overflow(ssw_sharded* s, int* overflowed);
 
 #ifdef __cplusplus
 }

@@ -99,7 +99,10 @@ SIGNATURES = {
     'ssw_extract_batch_rgb8_dev': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _cfg, c_size_t, _p, _p, _p]),
     'ssw_embed_batch_rgb8': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, _cfg, _p, c_size_t, _p]),
     'ssw_extract_batch_rgb8': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _cfg, c_size_t, _p, _p, _p]),
+    'ssw_embed_batch_rgb8_async': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, _cfg, _p, c_size_t, _p]),
+    'ssw_extract_batch_rgb8_async': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _cfg, c_size_t, _p, _p, _p]),
     'ssw_ctx_last_topk_fallbacks': (c_int, [_p]),
+    'ssw_selftest_pack_u8': (c_int, [_p, POINTER(c_uint64)]),
     'ssw_synth_frame_rgb8_dev': (c_int, [_p, c_uint32, c_uint32, c_uint64, c_uint32, c_uint32, _p]),
     'ssw_synth_rows_rgb8_dev': (c_int, [_p, c_uint32, c_uint64, c_uint32, c_uint32, c_uint32, _p]),
     'ssw_stage_forward_rgb8_dev': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, _p]),
@@ -116,6 +119,14 @@ SIGNATURES = {
     'ssw_shard_topk_merge_dev': (c_int, [_p, _p, _p, c_uint32, c_size_t, _p, _p]),
     'ssw_shard_embed_dev': (c_int, [_p, _p, POINTER(ssw_shard), _p, c_size_t, _p, c_size_t, c_size_t, _p, _cfg]),
     'ssw_shard_extract_dev': (c_int, [_p, _p, _p, POINTER(ssw_shard), _p, c_size_t, _cfg, _p]),
+    'ssw_sharded_unique_id': (c_int, [_p]),
+    'ssw_sharded_create': (c_int, [_p, _p, c_int, c_int, c_uint32, c_uint32, _pp]),
+    'ssw_sharded_destroy': (c_int, [_p]),
+    'ssw_sharded_embed_rgb8_dev': (c_int, [_p, _p, _cfg, _p, c_size_t, _p]),
+    'ssw_sharded_extract_rgb8_dev': (c_int, [_p, _p, _p, _cfg, c_size_t, _p]),
+    'ssw_sharded_indices': (c_int, [_p, _p, c_size_t]),
+    'ssw_sharded_coefficients': (c_int, [_p, c_int, _p]),
+    'ssw_sharded_overflow': (c_int, [_p, POINTER(c_int)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

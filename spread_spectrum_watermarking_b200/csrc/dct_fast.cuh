@@ -407,15 +407,31 @@ SSW_HD void unpack4_unit2(const unsigned* wa, const unsigned* wb, float2* c) {
     c[10] = unit_of2(byte_to_float2<2>(wa[2], wb[2])); c[11] = unit_of2(byte_to_float2<3>(wa[2], wb[2]));
 }
 // four (A,B) pairs of unit values -> one RGB8 word per row
+#ifndef SSW_PACK_F2I
+#define SSW_PACK_F2I 1
+#endif
+// float -> u8, truncating, saturating to [0, 255], NaN -> 0 (cvt.rzi.u8.f32 clamps by definition; SASS: F2IP.U8.F32.TRUNC)
+SSW_HD unsigned sat_u8_rz(float t) { unsigned r; asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(t)); return r; }
 SSW_HD void pack_u8x4x2(const float2* o, float nz, unsigned& wa, unsigned& wb) {
     unsigned ma[4], mb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#if SSW_PACK_F2I
+        // round(clamp(v, 0, 1) * 255), ties away from zero, == sat_u8(trunc(RZ(rn(255 v) + 0.5))) for EVERY float v: inside
+        // [0, 1] the forms coincide (see unit_to_u8_fast), below 0 / above 1 / NaN the saturating conversion gives the 0 /
+        // 255 / 0 of the clamp (rn(255 v) is monotone, so v < 0 cannot reach 0.5 and v > 1 cannot fall below 255).  The
+        // clamp (4 FMNMX per pair) and the second magic add leave the FP32 / ALU pipes, which bound the inverse row pass;
+        // the conversion unit is otherwise idle there.  Checked against unit_to_u8(clamp01(v)) over all 2^32 bit patterns
+        // on the device (ssw_selftest_pack_u8, tests/test_gpu_parity.py).
+        const float2 t = __fadd2_rz(prod2(255.0f, o[i], nz), make_float2(0.5f, 0.5f));
+        ma[i] = sat_u8_rz(t.x); mb[i] = sat_u8_rz(t.y);
+#else
         const float2 c = make_float2(fminf(fmaxf(o[i].x, 0.0f), 1.0f), fminf(fmaxf(o[i].y, 0.0f), 1.0f));   // NaN -> 0
         // the product must be rounded to f32 BEFORE the +0.5 (round half away from zero of the f32 value): prod2, not
         // FMUL2 -- ptxas would contract FMUL2 + FADD2.RZ into one FFMA2.RZ
         const float2 m = __fadd2_rz(__fadd2_rz(prod2(255.0f, c, nz), make_float2(0.5f, 0.5f)), make_float2(8388608.0f, 8388608.0f));
         ma[i] = __float_as_uint(m.x); mb[i] = __float_as_uint(m.y);
+#endif
     }
     wa = __byte_perm(__byte_perm(ma[0], ma[1], 0x0040u), __byte_perm(ma[2], ma[3], 0x0040u), 0x5410u);
     wb = __byte_perm(__byte_perm(mb[0], mb[1], 0x0040u), __byte_perm(mb[2], mb[3], 0x0040u), 0x5410u);

@@ -208,15 +208,17 @@ struct ColPipe {
 //   * one CTA per SM slot looping over its tiles; tile = TEAMS row pairs = 2*TEAMS adjacent rows, which are CONTIGUOUS
 //     in memory on both sides, so every transfer is one linear bulk copy (cp.async.bulk, no tensor map);
 //   * a PRODUCER warp (one elected thread) moves the tiles, signalled by mbarriers:
-//       forward : A <- RGB8 rows of tile j+1 as soon as the conversion phase of tile j has consumed A;
-//                 B -> coefficient rows of tile j once the post pass has filled B;
+//       forward : A <- RGB8 rows of tile j+1 as soon as the conversion phase of tile j has consumed A; the post pass
+//                 stores its coefficient rows straight to the plane (coalesced 128-byte warp stores -- staging them
+//                 for a bulk store costs the same number of store instructions and 8N bytes of shared memory per
+//                 team, i.e. a third resident CTA per SM);
 //       inverse : A <- coefficient rows (consumed by the pre pass); B <- original RGB8 rows, converted IN PLACE to the
 //                 output RGB8 rows by the last phase and stored from there; the next tile's originals follow the store;
 //   * COMPUTE teams of P::T threads own one row pair each; they never touch global memory except for twiddles, wait only
 //     on mbarriers (tile landed / buffer drained) and on their own team's named barrier between FFT stages, so the
 //     teams of a CTA drift apart and the conversion, FFT and post phases of different row pairs overlap on the SM.
-// Shared memory per CTA: A + B + TEAMS FFT buffers (22*N bytes per team: 84.5 KB for one 3840-point row pair -> two
-// CTAs per SM).
+// Shared memory per CTA: forward A + FFT buffers (14*N bytes per team: 54 KB for one 3840-point row pair -> three CTAs
+// per SM), inverse A + B + FFT buffers (22*N bytes per team -> two CTAs per SM).
 // =====================================================================================================================
 struct RowPipeArgs {
     int w, h, batch;
@@ -241,7 +243,7 @@ struct RowPipe {
     static constexpr int PIX_BYTES = ROWS * PIX_ROW, COEF_BYTES = ROWS * COEF_ROW;
     static_assert(PIX_BYTES % 16 == 0 && COEF_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
     static constexpr int A_BYTES = INVERSE_ ? COEF_BYTES : PIX_BYTES;    // input side
-    static constexpr int B_BYTES = INVERSE_ ? PIX_BYTES : COEF_BYTES;    // output side
+    static constexpr int B_BYTES = INVERSE_ ? PIX_BYTES : 0;             // inverse: originals in, output bytes out (in place)
     static constexpr int al128(int b) { return (b + 127) / 128 * 128; }
     static constexpr int OFF_A = 0, OFF_B = al128(A_BYTES), OFF_FFT = OFF_B + al128(B_BYTES);
     static constexpr int FFT_BYTES = TEAMS_ * P_::PITCH * (int)sizeof(cplx);
@@ -253,9 +255,9 @@ struct RowPipe {
     static bool supports(int w, int h) { return w == N && h > 0 && h % ROWS == 0; }
     static int tiles_per_image(int w, int h) { (void)w; return h / ROWS; }
 
-    // c: compute thread id (team g = c / T owns rows 2g, 2g+1 of the tile)
+    // c: compute thread id (team g = c / T owns rows 2g, 2g+1 of the tile); gout: the tile's coefficient rows in the plane (forward)
     template <int PH>
-    static SSW_HD void phase(const RowPipeArgs& a, unsigned char* bufA, cplx* fft, unsigned char* bufB, int c, Thread& th) {
+    static SSW_HD void phase(const RowPipeArgs& a, unsigned char* bufA, cplx* fft, unsigned char* bufB, float* gout, int c, Thread& th) {
         const int g = c / T, t = c - g * T;
         cplx* s = fft + g * P::PITCH;
         if constexpr (PH > 0 && PH < NPH - 1) {
@@ -275,8 +277,8 @@ struct RowPipe {
                 }
             }
         } else if constexpr (!INVERSE) {
-            // DCT-II post pass -> coefficient rows in B (RowFwd last phase, shared-memory destination)
-            float* oa = (float*)(bufB + (2 * g) * COEF_ROW);
+            // DCT-II post pass -> coefficient rows of the plane (RowFwd last phase)
+            float* oa = gout + (size_t)(2 * g) * N;
             float* ob = oa + N;
 #pragma unroll 4
             for (int k = t; k <= N / 2; k += T) {
@@ -332,11 +334,12 @@ struct RowPipe {
 // default shape of the row pipelines of a plan: ~256 compute threads per CTA, two CTAs per SM when they fit
 template <class P> struct RowPipeCfg {
     static constexpr int TEAMS = P::T >= 192 ? 1 : (P::T >= 96 ? 2 : 4);
-    static constexpr int MINB = RowPipe<P, TEAMS, false, 2>::FITS ? 2 : 1;
-    static constexpr bool OK = !P::PAD && RowPipe<P, TEAMS, false, MINB>::FITS && RowPipe<P, TEAMS, true, MINB>::FITS &&
+    static constexpr int MINB_I = RowPipe<P, TEAMS, true, 2>::FITS ? 2 : 1;
+    static constexpr int MINB_F = (RowPipe<P, TEAMS, false, 3>::FITS && 3 * (TEAMS * P::T + 32) * 72 <= 65536) ? 3 : MINB_I;
+    static constexpr bool OK = !P::PAD && RowPipe<P, TEAMS, false, MINB_F>::FITS && RowPipe<P, TEAMS, true, MINB_I>::FITS &&
                                (TEAMS * P::T + 32) <= 1024;
-    using Fwd = RowPipe<P, TEAMS, false, MINB>;
-    using Inv = RowPipe<P, TEAMS, true, MINB>;
+    using Fwd = RowPipe<P, TEAMS, false, MINB_F>;
+    using Inv = RowPipe<P, TEAMS, true, MINB_I>;
 };
 
 #if defined(__CUDACC__)
@@ -357,9 +360,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     for (unsigned spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspended (no issue slots) until the phase completes or the hint (ns) expires
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
         if (!done && spin > (1u << 22)) __trap();
     }
 }
@@ -543,19 +546,19 @@ __device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned byt
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-// mbarriers (8 bytes each, at OFF_BAR): fullA, freeA, fullB (inverse: originals landed) / drainedB (forward: the store has read B), readyB
+// mbarriers (8 bytes each, at OFF_BAR): fullA, freeA; inverse also fullB (originals landed) and readyB (output bytes written)
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __grid_constant__ RowPipeArgs a) {
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int NC = K::NC;
     const int tid = threadIdx.x;
     const unsigned sbase = smem_u32(pipe_smem);
-    const unsigned bar_fullA = sbase + K::OFF_BAR, bar_freeA = bar_fullA + 8, bar_inB = bar_fullA + 16, bar_readyB = bar_fullA + 24;
+    const unsigned bar_fullA = sbase + K::OFF_BAR, bar_freeA = bar_fullA + 8, bar_fullB = bar_fullA + 16, bar_readyB = bar_fullA + 24;
     if (tid == 0) {
         mbar_init(bar_fullA, 1);      // producer's expect_tx arrival + the bytes of the copy
         mbar_init(bar_freeA, NC);     // every compute thread has consumed A
-        mbar_init(bar_inB, 1);        // forward: producer arrives when the store has read B; inverse: expect_tx of the originals
-        mbar_init(bar_readyB, NC);    // every compute thread has written (and fenced) its part of B
+        mbar_init(bar_fullB, 1);      // inverse: expect_tx of the originals
+        mbar_init(bar_readyB, NC);    // inverse: every compute thread has written (and fenced) its part of B
         fence_mbar_init();
     }
     if (!a.pdl_late) pdl_trigger();
@@ -565,26 +568,22 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
     const int first = blockIdx.x, step = gridDim.x;
     const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
     const size_t frame_px = (size_t)a.w * a.h;
+    auto px_of = [&](int j) {   // first pixel of tile j of this CTA, counted over the whole batch
+        const int tile = first + j * step, img = tile / a.tiles_per_image;
+        return img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N;
+    };
 
     if (tid >= NC) {
         // ===================== producer warp =====================
         if (tid == NC) {
-            auto pix_of = [&](int j, const unsigned char* base) {
-                const int tile = first + j * step, img = tile / a.tiles_per_image;
-                return base + 3 * (img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N);
-            };
-            auto coef_of = [&](int j) {
-                const int tile = first + j * step, img = tile / a.tiles_per_image;
-                return a.plane + img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N;
-            };
             auto load_a = [&](int j) {
                 mbar_expect_tx(bar_fullA, K::A_BYTES);
-                if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, coef_of(j), K::A_BYTES, bar_fullA);
-                else bulk_load(sbase + K::OFF_A, pix_of(j, a.pix), K::A_BYTES, bar_fullA);
+                if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, a.plane + px_of(j), K::A_BYTES, bar_fullA);
+                else bulk_load(sbase + K::OFF_A, a.pix + 3 * px_of(j), K::A_BYTES, bar_fullA);
             };
             auto load_b = [&](int j) {   // inverse only: the original pixels of the tile
-                mbar_expect_tx(bar_inB, K::B_BYTES);
-                bulk_load(sbase + K::OFF_B, pix_of(j, a.pix), K::B_BYTES, bar_inB);
+                mbar_expect_tx(bar_fullB, K::B_BYTES);
+                bulk_load(sbase + K::OFF_B, a.pix + 3 * px_of(j), K::B_BYTES, bar_fullB);
             };
             if (nt > 0) {
                 load_a(0);
@@ -595,17 +594,17 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
                     mbar_wait(bar_freeA, j & 1);               // tile j has left A
                     load_a(j + 1);
                 }
-                mbar_wait(bar_readyB, j & 1);                  // results of tile j are in B (writers fenced)
-                if constexpr (K::INVERSE) bulk_store((void*)pix_of(j, a.out), sbase + K::OFF_B, K::B_BYTES);
-                else bulk_store(coef_of(j), sbase + K::OFF_B, K::B_BYTES);
-                tma_commit();
-                if (j + 1 < nt) {
-                    tma_wait_read0();                          // the store has read B
-                    if constexpr (K::INVERSE) load_b(j + 1);
-                    else mbar_arrive(bar_inB);
+                if constexpr (K::INVERSE) {
+                    mbar_wait(bar_readyB, j & 1);              // output bytes of tile j are in B (writers fenced)
+                    bulk_store(a.out + 3 * px_of(j), sbase + K::OFF_B, K::B_BYTES);
+                    tma_commit();
+                    if (j + 1 < nt) {
+                        tma_wait_read0();                      // the store has read B
+                        load_b(j + 1);
+                    }
                 }
             }
-            tma_wait_all0();                                   // all stores complete before the CTA exits
+            if constexpr (K::INVERSE) tma_wait_all0();         // all stores complete before the CTA exits
         }
         return;
     }
@@ -615,20 +614,22 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
     const int team = tid / K::T;
     cplx* fft = (cplx*)(pipe_smem + K::OFF_FFT);
     for (int j = 0; j < nt; ++j) {
+        float* gout = K::INVERSE ? nullptr : a.plane + px_of(j);
         mbar_wait(bar_fullA, j & 1);                           // tile j has landed in A
         static_for<K::NPH>([&](auto ph) {
             constexpr int p = decltype(ph)::value;
             if constexpr (p == K::NPH - 1) {
                 if (a.pdl_late && j + 1 == nt) pdl_trigger();
-                if constexpr (K::INVERSE) mbar_wait(bar_inB, j & 1);           // the originals of tile j have landed in B
-                else { if (j > 0) mbar_wait(bar_inB, (j - 1) & 1); }            // the store of tile j-1 has read B
+                if constexpr (K::INVERSE) mbar_wait(bar_fullB, j & 1);         // the originals of tile j have landed in B
             }
-            K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, tid, th);
+            K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, gout, tid, th);
             if constexpr (p == 0) mbar_arrive(bar_freeA);                      // (this thread's) reads of A are done
             if constexpr (p + 1 < K::NPH) named_sync(1 + team, K::T);
         });
-        fence_proxy_async();                                   // generic-proxy writes of B -> visible to the bulk store
-        mbar_arrive(bar_readyB);
+        if constexpr (K::INVERSE) {
+            fence_proxy_async();                               // generic-proxy writes of B -> visible to the bulk store
+            mbar_arrive(bar_readyB);
+        }
         named_sync(1 + team, K::T);                            // the team has read its FFT buffer: the next tile may overwrite it
     }
 }

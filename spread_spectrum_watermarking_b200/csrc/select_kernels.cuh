@@ -293,7 +293,7 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
 // ---- 2'. distributed merge: concatenate the candidate lists gathered from all ranks --------------
 __global__ void __launch_bounds__(256)
 topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned* __restrict__ counts, unsigned n_lists,
-                   unsigned list_cap, TopkScratch ts) {
+                   unsigned list_cap, unsigned list_pitch, TopkScratch ts) {
     pdl_enter();
     __shared__ unsigned off[65];
     if (threadIdx.x == 0) {
@@ -313,7 +313,7 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
     for (unsigned l = 0; l < n_lists; ++l) {
         const unsigned c = min(counts[l], list_cap);
         for (unsigned i = threadIdx.x; i < c; i += blockDim.x)
-            if (off[l] + i < (unsigned)kTopkCap) ts.cand[off[l] + i] = lists[(size_t)l * list_cap + i];
+            if (off[l] + i < (unsigned)kTopkCap) ts.cand[off[l] + i] = lists[(size_t)l * list_pitch + i];
     }
 }
 

@@ -91,7 +91,19 @@ struct ssw_ctx {
     // fused pipelines: ask the forward column pipeline for the low-frequency-block histogram of the ordering that
     // follows (want), learn whether a pipeline produced it (done) -- see run_topk_fast
     struct { bool want = false, done = false; unsigned k = 0; int ordering = 0; } col_hist;
+    bool col_hist_on = true;               // SSW_COL_HIST=0: selection bin from the topk_block_bin kernel even where a column pipeline runs
     bool sim_exact = false;                // SSW_SIM_EXACT=1: scores in the reference's sequential order (bit-identical)
+    // asynchronous host-buffer entry points: two persistent sets of device staging buffers used alternately (the copies
+    // of call i+1 run beside the kernels and the download of call i), events that mark a set free again, and the host
+    // ranges with copies still in flight (a later copy that touches one of them is ordered behind it)
+    struct Staging { uint8_t* in = nullptr; size_t in_cap = 0; uint8_t* out = nullptr; size_t out_cap = 0;
+                     float* f32 = nullptr; size_t f32_cap = 0; cudaEvent_t done = nullptr; bool used = false; };
+    Staging stage[2];
+    unsigned stage_next = 0;
+    struct HostRange { const char* p; size_t n; cudaEvent_t ev; };
+    std::vector<HostRange> pending_d2h, pending_h2d;
+    std::vector<cudaEvent_t> range_events;
+    size_t range_next = 0;
     TopkScratch ts{};
     unsigned ts_batch = 0;
     GeneralSelect general;
@@ -208,6 +220,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_COL_PIPE")) c->col_pipe = atoi(s);
     if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
+    if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
     *out = c.release();
     return SSW_OK;
 }
@@ -235,6 +248,11 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
     if (c->copy_out) { cudaStreamSynchronize(c->copy_out); cudaStreamDestroy(c->copy_out); }
     for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->range_events) cudaEventDestroy(e);
+    for (auto& st : c->stage) {
+        cudaFree(st.in); cudaFree(st.out); cudaFree(st.f32);
+        if (st.done) cudaEventDestroy(st.done);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -247,6 +265,12 @@ extern "C" int ssw_ctx_synchronize(ssw_ctx* c) {
     if (!c) return fail(SSW_ERR_INVALID, "ctx is NULL");
     CKS(ctx_bind(c));
     CK(cudaStreamSynchronize(c->stream));
+    // the asynchronous host-buffer entry points finish on the copy streams
+    if (c->copy_in) CK(cudaStreamSynchronize(c->copy_in));
+    if (c->copy_out) CK(cudaStreamSynchronize(c->copy_out));
+    if (c->aux) CK(cudaStreamSynchronize(c->aux));
+    c->pending_d2h.clear();
+    c->pending_h2d.clear();
     return SSW_OK;
 }
 extern "C" void* ssw_ctx_stream(ssw_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -1662,7 +1686,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
         const unsigned nb = std::min(cb, batch - b0);
         const uint8_t* src = rgb + (size_t)b0 * np * 3;
         // the forward column pipeline leaves the low-frequency-block histogram of every frame for the ordering
-        c->col_hist.want = k > 0 && !c->topk_full_hist; c->col_hist.done = false;
+        c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on; c->col_hist.done = false;
         c->col_hist.k = (unsigned)k; c->col_hist.ordering = cfg->ordering;
         rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
         const bool hist_ready = c->col_hist.done;
@@ -1716,7 +1740,7 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         ap.out = extracted + (size_t)b0 * n; ap.out_stride = (long long)n;
         ap.sim = (sim && !c->sim_exact) ? sim + b0 : nullptr;
         auto base_forward = [&]() -> int {
-            c->col_hist.want = !c->topk_full_hist; c->col_hist.done = false;
+            c->col_hist.want = !c->topk_full_hist && c->col_hist_on; c->col_hist.done = false;
             c->col_hist.k = (unsigned)n; c->col_hist.ordering = cfg->ordering;
             const int r = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
             c->col_hist.want = false;
@@ -1888,6 +1912,176 @@ extern "C" int ssw_extract_batch_rgb8(ssw_ctx* c, const uint8_t* base_rgb, const
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// asynchronous host-buffer entry points: enqueue and return; results are valid after ssw_ctx_synchronize.
+// Consecutive calls overlap -- the upload of call i+1 runs on the copy-in stream beside the kernels (context stream)
+// and the download (copy-out stream) of call i; PCIe is full duplex, so a stream of frames moves at the line rate of
+// the busier direction instead of the sum of both.  Host buffers may be reused freely between
+// calls: a copy that touches a host range with an earlier copy still in flight is ordered behind that copy (the
+// watermarked frames of an embed call can be handed to an extract call without a synchronize in between).
+// Like the _dev entry points they do not repair a top-k candidate overflow (no host synchronisation): such frames come
+// back unmarked / with a zero vector and are reported by ssw_ctx_last_topk_fallbacks.
+// ------------------------------------------------------------------------------------------------
+static bool ranges_overlap(const void* a, size_t na, const char* b, size_t nb) {
+    const char* pa = (const char*)a;
+    return na && nb && pa < b + nb && b < pa + na;
+}
+
+static int range_event(ssw_ctx* c, cudaEvent_t* ev) {
+    constexpr size_t kRing = 32;
+    if (c->range_events.size() < kRing) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->range_events.push_back(e);
+        *ev = e;
+        return SSW_OK;
+    }
+    cudaEvent_t e = c->range_events[c->range_next++ % kRing];
+    CK(cudaEventSynchronize(e));   // 16 calls old: long complete; its ranges leave the pending lists
+    auto drop = [&](std::vector<ssw_ctx::HostRange>& v) {
+        v.erase(std::remove_if(v.begin(), v.end(), [&](const ssw_ctx::HostRange& r) { return r.ev == e; }), v.end());
+    };
+    drop(c->pending_d2h); drop(c->pending_h2d);
+    *ev = e;
+    return SSW_OK;
+}
+
+// the next staging set, large enough, with every stream that will touch it ordered behind its previous user
+static int acquire_stage(ssw_ctx* c, size_t in_bytes, size_t out_bytes, size_t n_f32, ssw_ctx::Staging** out) {
+    ssw_ctx::Staging& st = c->stage[c->stage_next++ & 1];
+    if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    if (st.in_cap < in_bytes || st.out_cap < out_bytes || st.f32_cap < n_f32) {
+        CKS(ssw_ctx_synchronize(c));   // growth is rare (first calls): everything drains, then the set is reallocated
+        if (st.in_cap < in_bytes) { cudaFree(st.in); st.in = nullptr; st.in_cap = 0; CK(cudaMalloc(&st.in, in_bytes)); st.in_cap = in_bytes; }
+        if (st.out_cap < out_bytes) { cudaFree(st.out); st.out = nullptr; st.out_cap = 0; CK(cudaMalloc(&st.out, out_bytes)); st.out_cap = out_bytes; }
+        if (st.f32_cap < n_f32) { cudaFree(st.f32); st.f32 = nullptr; st.f32_cap = 0; CK(cudaMalloc(&st.f32, n_f32 * sizeof(float))); st.f32_cap = n_f32; }
+        st.used = false;
+    }
+    if (st.used) {
+        CK(cudaStreamWaitEvent(c->copy_in, st.done, 0));
+        CK(cudaStreamWaitEvent(c->stream, st.done, 0));
+    }
+    st.used = true;
+    *out = &st;
+    return SSW_OK;
+}
+
+// order `stream` behind every pending copy of the other direction that touches [p, p+n)
+static int wait_host_range(ssw_ctx* c, cudaStream_t stream, const std::vector<ssw_ctx::HostRange>& pending, const void* p, size_t n) {
+    for (const auto& r : pending)
+        if (ranges_overlap(p, n, r.p, r.n)) CK(cudaStreamWaitEvent(stream, r.ev, 0));
+    return SSW_OK;
+}
+
+extern "C" int ssw_embed_batch_rgb8_async(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t batch,
+                                          const ssw_config* cfg, const float* marks, size_t n, uint8_t* out_rgb) {
+    if (!c || !rgb || !out_rgb || (n && !marks)) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    CKS(check_dims(w, h));
+    if (batch == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch;
+    ssw_ctx::Staging* st;
+    CKS(acquire_stage(c, bytes, bytes, std::max<size_t>(n * batch, 1), &st));
+    cudaEvent_t ev_up, ev_down;
+    CKS(range_event(c, &ev_up));
+    CKS(range_event(c, &ev_down));
+    // uploads wait for downloads still writing their source ranges; downloads for uploads still reading their target
+    CKS(wait_host_range(c, c->copy_in, c->pending_d2h, rgb, bytes));
+    CKS(wait_host_range(c, c->copy_in, c->pending_d2h, marks, n * batch * sizeof(float)));
+    CKS(wait_host_range(c, c->copy_out, c->pending_h2d, out_rgb, bytes));
+    CKS(wait_host_range(c, c->copy_out, c->pending_d2h, out_rgb, bytes));
+    if (n) CK(cudaMemcpyAsync(st->f32, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->copy_in));
+    const uint32_t cb = pipe_chunk_frames(fbytes, batch);
+    const uint32_t nchunks = (batch + cb - 1) / cb;
+    int rc = SSW_OK;
+    for (uint32_t ci = 0; ci < nchunks && rc == SSW_OK; ++ci) {
+        const uint32_t f0 = ci * cb, nf = std::min(cb, batch - f0);
+        cudaEvent_t e_in, e_cmp;
+        CKS(pipe_event(c, 1 + 2 * (size_t)ci, &e_in));
+        CKS(pipe_event(c, 2 + 2 * (size_t)ci, &e_cmp));
+        CK(cudaMemcpyAsync(st->in + f0 * fbytes, rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+        CK(cudaEventRecord(e_in, c->copy_in));
+        CK(cudaStreamWaitEvent(c->stream, e_in, 0));
+        rc = ssw_embed_batch_rgb8_dev(c, st->in + f0 * fbytes, w, h, nf, cfg, st->f32 + (size_t)f0 * n, n, st->out + f0 * fbytes);
+        if (rc != SSW_OK) break;
+        CK(cudaEventRecord(e_cmp, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_out, e_cmp, 0));
+        CK(cudaMemcpyAsync(out_rgb + f0 * fbytes, st->out + f0 * fbytes, nf * fbytes, cudaMemcpyDeviceToHost, c->copy_out));
+    }
+    CK(cudaEventRecord(ev_up, c->copy_in));
+    CK(cudaEventRecord(ev_down, c->copy_out));
+    CK(cudaEventRecord(st->done, c->copy_out));
+    c->pending_h2d.push_back({(const char*)rgb, bytes, ev_up});
+    if (n) c->pending_h2d.push_back({(const char*)marks, n * batch * sizeof(float), ev_up});
+    c->pending_d2h.push_back({(const char*)out_rgb, bytes, ev_down});
+    return rc;
+}
+
+extern "C" int ssw_extract_batch_rgb8_async(ssw_ctx* c, const uint8_t* base_rgb, const uint8_t* derived_rgb, uint32_t w,
+                                            uint32_t h, uint32_t batch, const ssw_config* cfg, size_t n, float* extracted,
+                                            const float* marks, float* sim) {
+    if (!c || !base_rgb || !derived_rgb || !extracted) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(check_cfg(cfg));
+    CKS(check_dims(w, h));
+    if (sim && !marks) return fail(SSW_ERR_INVALID, "similarity requested without marks");
+    if (batch == 0 || n == 0) return SSW_OK;
+    CKS(ctx_bind(c));
+    const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch, vbytes = n * batch * sizeof(float);
+    ssw_ctx::Staging* st;
+    // out: extracted vectors followed by the scores; f32: the marks
+    CKS(acquire_stage(c, 2 * bytes, vbytes + batch * sizeof(float), n * batch, &st));
+    uint8_t *d_b = st->in, *d_d = st->in + bytes;
+    float* d_ext = (float*)st->out;
+    float* d_sim = sim ? d_ext + n * batch : nullptr;
+    cudaEvent_t ev_up, ev_down;
+    CKS(range_event(c, &ev_up));
+    CKS(range_event(c, &ev_down));
+    CKS(wait_host_range(c, c->copy_in, c->pending_d2h, base_rgb, bytes));
+    if (marks) CKS(wait_host_range(c, c->copy_in, c->pending_d2h, marks, vbytes));
+    for (const void* q : {(const void*)extracted, (const void*)sim}) {
+        if (!q) continue;
+        const size_t qn = q == (const void*)extracted ? vbytes : batch * sizeof(float);
+        CKS(wait_host_range(c, c->copy_out, c->pending_h2d, q, qn));
+        CKS(wait_host_range(c, c->copy_out, c->pending_d2h, q, qn));
+    }
+    if (marks) CK(cudaMemcpyAsync(st->f32, marks, vbytes, cudaMemcpyHostToDevice, c->copy_in));
+    const uint32_t cb = pipe_chunk_frames(2 * fbytes, batch);
+    const uint32_t nchunks = (batch + cb - 1) / cb;
+    int rc = SSW_OK;
+    for (uint32_t ci = 0; ci < nchunks && rc == SSW_OK; ++ci) {
+        const uint32_t f0 = ci * cb, nf = std::min(cb, batch - f0);
+        cudaEvent_t e_in;
+        CKS(pipe_event(c, 1 + (size_t)ci, &e_in));
+        CK(cudaMemcpyAsync(d_b + f0 * fbytes, base_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+        // the derived frames are typically the output of an embed call whose download is still in flight: the base
+        // frames above go up beside that download, the derived frames behind it
+        if (ci == 0) CKS(wait_host_range(c, c->copy_in, c->pending_d2h, derived_rgb, bytes));
+        CK(cudaMemcpyAsync(d_d + f0 * fbytes, derived_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+        CK(cudaEventRecord(e_in, c->copy_in));
+        CK(cudaStreamWaitEvent(c->stream, e_in, 0));
+        rc = ssw_extract_batch_rgb8_dev(c, d_b + f0 * fbytes, d_d + f0 * fbytes, w, h, nf, cfg, n, d_ext + (size_t)f0 * n,
+                                        marks ? st->f32 + (size_t)f0 * n : nullptr, d_sim ? d_sim + f0 : nullptr);
+    }
+    if (rc == SSW_OK) {
+        cudaEvent_t e_cmp;
+        CKS(pipe_event(c, 0, &e_cmp));
+        CK(cudaEventRecord(e_cmp, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_out, e_cmp, 0));
+        CK(cudaMemcpyAsync(extracted, d_ext, vbytes, cudaMemcpyDeviceToHost, c->copy_out));
+        if (d_sim) CK(cudaMemcpyAsync(sim, d_sim, batch * sizeof(float), cudaMemcpyDeviceToHost, c->copy_out));
+    }
+    CK(cudaEventRecord(ev_up, c->copy_in));
+    CK(cudaEventRecord(ev_down, c->copy_out));
+    CK(cudaEventRecord(st->done, c->copy_out));
+    c->pending_h2d.push_back({(const char*)base_rgb, bytes, ev_up});
+    c->pending_h2d.push_back({(const char*)derived_rgb, bytes, ev_up});
+    if (marks) c->pending_h2d.push_back({(const char*)marks, vbytes, ev_up});
+    c->pending_d2h.push_back({(const char*)extracted, vbytes, ev_down});
+    if (sim) c->pending_d2h.push_back({(const char*)sim, batch * sizeof(float), ev_down});
+    return rc;
+}
+
 extern "C" int ssw_ctx_last_topk_fallbacks(ssw_ctx* c) {
     if (!c) return 0;
     if (ctx_bind(c) != SSW_OK) return -1;
@@ -1896,6 +2090,46 @@ extern "C" int ssw_ctx_last_topk_fallbacks(ssw_ctx* c) {
     const int r = c->last_fallbacks + (int)ov;
     c->last_fallbacks = 0;
     return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device self-test of the packed RGB8 output conversion (pack_u8x4x2, dct_fast.cuh) against the reference-faithful
+// round(clamp(v, 0, 1) * 255) (color.cuh) over ALL 2^32 float bit patterns; returns the number of mismatching values
+// ------------------------------------------------------------------------------------------------
+__global__ void selftest_pack_u8_kernel(unsigned long long* bad, float nz) {
+#if defined(__CUDA_ARCH__)   // the packed helpers exist in the device pass only
+    unsigned long long local = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 8ull;
+    for (unsigned long long b = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 8ull; b < (1ull << 32); b += stride) {
+        float2 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_float2(__uint_as_float((unsigned)(b + 2 * i)), __uint_as_float((unsigned)(b + 2 * i + 1)));
+        unsigned wa, wb;
+        fast::pack_u8x4x2(o, nz, wa, wb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            local += ((wa >> (8 * i)) & 255u) != unit_to_u8(clamp01(o[i].x));
+            local += ((wb >> (8 * i)) & 255u) != unit_to_u8(clamp01(o[i].y));
+        }
+    }
+    if (local) atomicAdd(bad, local);
+#endif
+}
+
+extern "C" int ssw_selftest_pack_u8(ssw_ctx* c, uint64_t* mismatches) {
+    if (!c || !mismatches) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(c));
+    unsigned long long* d = nullptr;
+    CK(cudaMallocAsync(&d, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
+    { KScope ks(c, "selftest_pack_u8"); selftest_pack_u8_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d, -0.0f); }
+    CK(cudaGetLastError());
+    unsigned long long hv = 0;
+    CK(cudaMemcpyAsync(&hv, d, sizeof(hv), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaFreeAsync(d, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *mismatches = hv;
+    return SSW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2107,7 +2341,7 @@ extern "C" int ssw_shard_topk_merge_dev(ssw_ctx* c, const uint64_t* lists_dev, c
     CK(cudaMemsetAsync(overflow_dev, 0, sizeof(uint32_t), c->stream));
     {
         KScope ks(c, "topk_concat");
-        launch_pdl(c, topk_concat_kernel, 1, 256, 0, c->stream, (const unsigned long long*)lists_dev, counts_dev, n_lists, (unsigned)kTopkCap, ts);
+        launch_pdl(c, topk_concat_kernel, 1, 256, 0, c->stream, (const unsigned long long*)lists_dev, counts_dev, n_lists, (unsigned)kTopkCap, (unsigned)kTopkCap, ts);
     }
     const void* key = (const void*)topk_rank_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
@@ -2163,3 +2397,5 @@ extern "C" int ssw_shard_extract_dev(ssw_ctx* c, const float* base_plane, const 
     CK(cudaGetLastError());
     return SSW_OK;
 }
+
+#include "sharded_api.cuh"

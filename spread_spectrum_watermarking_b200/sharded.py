@@ -212,6 +212,64 @@ class CudaOps:
         return torch.as_tensor(array, dtype=dtype).to(self.device)
 
 
+class Sharded:
+    """`ssw_sharded_*` (include/ssw.h): the whole sharded path behind the C ABI -- orchestration in libssw, the exchange
+    between the two passes of the transform through peer-mapped memory (no all-to-all collective), NCCL (inside the
+    library) only for the bootstrap, the barriers and the few hundred bytes of the distributed top-k.  This class is the
+    thin binding the tests and bench.py use; the only thing it adds is the hand-over of rank 0's NCCL id to the other
+    ranks (here: one torch.distributed broadcast -- a Rust host would use its own channel)."""
+
+    def __init__(self, ctx, width, height, rank=0, world=1, group=None):
+        self.ctx, self.width, self.height, self.rank, self.world = ctx, int(width), int(height), int(rank), int(world)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if world > 1:
+            if rank == 0:
+                check(lib.ssw_sharded_unique_id(ident.data_ptr()))
+            dev = ident.cuda() if dist.get_backend(group) == 'nccl' else ident
+            dist.broadcast(dev, 0, group=group)
+            ident = dev.cpu()
+        h = ctypes.c_void_p()
+        check(lib.ssw_sharded_create(ctx.handle, ident.data_ptr(), self.rank, self.world, self.width, self.height, ctypes.byref(h)))
+        self.handle = h
+        self.hb, self.wb = self.height // self.world, self.width // self.world
+
+    def embed_rgb8(self, rows, cfg, mark_dev, out=None):
+        """rows: [H/G][W][3] uint8 CUDA tensor (this rank's rows); mark_dev: float32 CUDA tensor; stream-ordered on the
+        context's stream, no host synchronisation"""
+        out = torch.empty_like(rows) if out is None else out
+        check(lib.ssw_sharded_embed_rgb8_dev(self.handle, rows.data_ptr(), ctypes.byref(cfg), mark_dev.data_ptr(), mark_dev.numel(),
+                                             out.data_ptr()))
+        return out
+
+    def extract(self, base_rows, derived_rows, cfg, n, out=None):
+        out = torch.empty((n,), dtype=torch.float32, device=base_rows.device) if out is None else out
+        check(lib.ssw_sharded_extract_rgb8_dev(self.handle, base_rows.data_ptr(), derived_rows.data_ptr(), ctypes.byref(cfg), n,
+                                               out.data_ptr()))
+        return out
+
+    def indices(self, n):
+        import numpy as np
+        idx = np.empty(n, np.uint32)
+        check(lib.ssw_sharded_indices(self.handle, idx.ctypes.data, n))
+        return idx
+
+    def coefficients(self, which=0):
+        import numpy as np
+        c = np.empty((self.wb, self.height), np.float32)
+        check(lib.ssw_sharded_coefficients(self.handle, which, c.ctypes.data))
+        return c
+
+    def overflow(self):
+        v = ctypes.c_int(0)
+        check(lib.ssw_sharded_overflow(self.handle, ctypes.byref(v)))
+        return bool(v.value)
+
+    def close(self):
+        if self.handle:
+            check(lib.ssw_sharded_destroy(self.handle))
+            self.handle = None
+
+
 class ShardedFrame:
     """forward-transformed frame: this rank's coefficient columns, transposed ([wb][H] f32)"""
 

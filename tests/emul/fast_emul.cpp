@@ -129,10 +129,9 @@ void emulate_row_pipe(RowPipeArgs a) {
         }
         static_for<K::NPH>([&](auto ph) {
             constexpr int p = decltype(ph)::value;
-            for (int c = 0; c < K::NC; ++c) K::template phase<p>(a, A.data(), fft.data(), B.data(), c, th[c]);
+            for (int c = 0; c < K::NC; ++c) K::template phase<p>(a, A.data(), fft.data(), B.data(), K::INVERSE ? nullptr : a.plane + px0, c, th[c]);
         });
         if (K::INVERSE) std::memcpy(a.out + 3 * px0, B.data(), K::B_BYTES);
-        else std::memcpy(a.plane + px0, B.data(), K::B_BYTES);
     }
 }
 

@@ -454,6 +454,51 @@ def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
         cg.close(); cf.close()
 
 
+def test_packed_rgb8_output_conversion_is_exact_for_every_float(wm, ctx):
+    """the saturating-conversion form of round(clamp(v,0,1)*255) used by the inverse row passes, on the device, against
+    the reference-faithful form over all 2^32 float bit patterns (NaN, infinities, negatives, ties included)"""
+    bad = ctypes.c_uint64(1)
+    wm._lib.check(wm.lib.ssw_selftest_pack_u8(ctx.handle, ctypes.byref(bad)))
+    assert bad.value == 0
+
+
+def test_async_host_entry_points_overlap_safely(wm, ctx, so):
+    """ssw_embed_batch_rgb8_async / ssw_extract_batch_rgb8_async: calls are only enqueued; the watermarked frames of an embed
+    call are handed to the extract call WITHOUT a synchronize in between (the library orders the upload behind the
+    download), host buffers are reused across calls (later downloads wait for earlier uploads and vice versa), and the
+    results after one ssw_ctx_synchronize are the bytes of the synchronous entry points"""
+    w, h, B, n = 1280, 720, 3, 700
+    rng = np.random.default_rng(77)
+    frames = [np.stack([so.synth_frame(w, h, seed=30 + r, img=i) for i in range(B)]) for r in range(2)]
+    marks = [rng.standard_normal((B, n)).astype(np.float32) for _ in range(2)]
+    cfg = wm._lib.ssw_config(2, 0.1, 0)
+    pc = ctypes.byref(cfg)
+    want = []
+    for r in range(2):
+        o = np.empty_like(frames[r]); e = np.empty((B, n), np.float32); s_ = np.empty(B, np.float32)
+        wm._lib.check(wm.lib.ssw_embed_batch_rgb8(ctx.handle, frames[r].ctypes.data, w, h, B, pc, marks[r].ctypes.data, n, o.ctypes.data))
+        wm._lib.check(wm.lib.ssw_extract_batch_rgb8(ctx.handle, frames[r].ctypes.data, o.ctypes.data, w, h, B, pc, n, e.ctypes.data,
+                                                    marks[r].ctypes.data, s_.ctypes.data))
+        want.append((o, e, s_))
+    # one set of host buffers for the outputs of BOTH rounds' embeds (reuse = write-after-read hazard through the host)
+    out = np.zeros_like(frames[0])
+    ext = [np.zeros((B, n), np.float32) for _ in range(2)]
+    sim = [np.zeros(B, np.float32) for _ in range(2)]
+    for rep in range(3):
+        for r in range(2):
+            wm._lib.check(wm.lib.ssw_embed_batch_rgb8_async(ctx.handle, frames[r].ctypes.data, w, h, B, pc, marks[r].ctypes.data, n, out.ctypes.data))
+            wm._lib.check(wm.lib.ssw_extract_batch_rgb8_async(ctx.handle, frames[r].ctypes.data, out.ctypes.data, w, h, B, pc, n,
+                                                              ext[r].ctypes.data, marks[r].ctypes.data, sim[r].ctypes.data))
+        ctx.synchronize()
+        assert ctx.last_topk_fallbacks() == 0
+        assert (out == want[1][0]).all()                      # the last embed wrote the shared output buffer
+        for r in range(2):
+            assert (ext[r] == want[r][1]).all() and (sim[r] == want[r][2]).all(), (rep, r)
+        out[...] = 0
+        for r in range(2):
+            ext[r][...] = 0; sim[r][...] = 0
+
+
 def test_sequential_similarity_mode_is_bit_identical(wm, so, monkeypatch):
     """SSW_SIM_EXACT=1: bank and batch scores in the reference's sequential f32 order (src/algorithm.rs:696-714)"""
     import torch

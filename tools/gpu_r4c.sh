@@ -46,5 +46,6 @@ done
 for v in 0 1; do
   SSW_ROW_PIPE=$v timeout 300 python bench.py --workload c3 --no-cpu-baseline --no-e2e --steps 20 > $OUT/bench_c3_${TAG}_p$v.json 2> $OUT/bench_c3_${TAG}_p$v.err; echo "c3 rowpipe=$v rc=$?"; tail -2 $OUT/bench_c3_${TAG}_p$v.err
 done
-python tools/kernels_table.py $OUT/bench_c2_${TAG}_p*.json $OUT/bench_c3_${TAG}_p*.json 2>&1 | grep -E "json|fwd_|inv_|similarity_bank"
+timeout 300 python bench.py --workload c5 --no-cpu-baseline --no-e2e > $OUT/bench_c5_${TAG}.json 2> $OUT/bench_c5_${TAG}.err; echo "c5 rc=$?"; tail -2 $OUT/bench_c5_${TAG}.err
+python tools/kernels_table.py $OUT/bench_c2_${TAG}_p*.json $OUT/bench_c3_${TAG}_p*.json $OUT/bench_c5_${TAG}.json 2>&1 | grep -E "json|fwd_|inv_|similarity_bank|topk"
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -4 $OUT/pytest_gpu_$TAG.log
