@@ -184,6 +184,10 @@ int ssw_embed_batch_rgb8_async(ssw_ctx* ctx, const uint8_t* rgb_host, uint32_t w
 int ssw_extract_batch_rgb8_async(ssw_ctx* ctx, const uint8_t* base_rgb_host, const uint8_t* derived_rgb_host,
                                  uint32_t width, uint32_t height, uint32_t batch, const ssw_config* cfg,
                                  size_t n, float* extracted_host, const float* marks_host, float* sim_host);
+/* completion markers: ssw_ctx_marker hands out a ticket for "everything enqueued so far", ssw_ctx_wait_marker blocks
+ * the host until then (results of those calls are in host memory) without draining later calls. */
+int ssw_ctx_marker(ssw_ctx* ctx, uint64_t* marker);
+int ssw_ctx_wait_marker(ssw_ctx* ctx, uint64_t marker);
 /* Number of frames of the fused calls since the last query whose ordered top-k could not be served by the
  * candidate list (degenerate, noise-like spectrum: more than SSW_TOPK_CAP near-equal keys).  Synchronises the
  * stream.  What the calls did with such frames:

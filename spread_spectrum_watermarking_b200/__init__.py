@@ -294,7 +294,9 @@ class Writer:
 
     def close(self):
         if getattr(self, 'handle', None):
-            lib.ssw_writer_destroy(self.handle)
+            # an object that outlives its context (e.g. kept alive by a traceback) must not touch the destroyed context
+            if getattr(getattr(self, 'ctx', None), 'handle', None):
+                lib.ssw_writer_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -357,7 +359,9 @@ class Reader:
 
     def close(self):
         if getattr(self, 'handle', None):
-            lib.ssw_reader_destroy(self.handle)
+            # an object that outlives its context (e.g. kept alive by a traceback) must not touch the destroyed context
+            if getattr(getattr(self, 'ctx', None), 'handle', None):
+                lib.ssw_reader_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -453,7 +457,9 @@ class Bank:
 
     def close(self):
         if getattr(self, 'handle', None):
-            lib.ssw_bank_destroy(self.handle)
+            # an object that outlives its context (e.g. kept alive by a traceback) must not touch the destroyed context
+            if getattr(getattr(self, 'ctx', None), 'handle', None):
+                lib.ssw_bank_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -101,6 +101,8 @@ SIGNATURES = {
     'ssw_extract_batch_rgb8': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _cfg, c_size_t, _p, _p, _p]),
     'ssw_embed_batch_rgb8_async': (c_int, [_p, _p, c_uint32, c_uint32, c_uint32, _cfg, _p, c_size_t, _p]),
     'ssw_extract_batch_rgb8_async': (c_int, [_p, _p, _p, c_uint32, c_uint32, c_uint32, _cfg, c_size_t, _p, _p, _p]),
+    'ssw_ctx_marker': (c_int, [_p, POINTER(c_uint64)]),
+    'ssw_ctx_wait_marker': (c_int, [_p, c_uint64]),
     'ssw_ctx_last_topk_fallbacks': (c_int, [_p]),
     'ssw_selftest_pack_u8': (c_int, [_p, POINTER(c_uint64)]),
     'ssw_synth_frame_rgb8_dev': (c_int, [_p, c_uint32, c_uint32, c_uint64, c_uint32, c_uint32, _p]),

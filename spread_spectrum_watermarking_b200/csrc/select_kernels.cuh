@@ -53,6 +53,8 @@ struct TopkScratch {
     unsigned* cand_count;  // [batch], zero between calls
     unsigned long long* cand;  // [batch][kTopkCap]
     unsigned* overflow;    // [1] sticky counter of images whose candidate list overflowed
+    unsigned* maxrow;      // [batch] largest coefficient row among the first k ordered indices (low-rank embed inverse);
+                           // zeroed by topk_collect, 0xFFFFFFFF = the ordering of this frame failed
 };
 
 __device__ __forceinline__ unsigned total_cmp_key(float v) {
@@ -262,6 +264,7 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
     const unsigned img = blockIdx.y;
     const float* plane = planes + (long long)img * plane_stride;
     const unsigned bin_sel = ts.sel_bin[img];
+    if (ts.maxrow && blockIdx.x == 0 && threadIdx.x == 0) ts.maxrow[img] = 0u;
     unsigned* count = ts.cand_count + img;
     unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
     const unsigned n4 = n >> 2;
@@ -335,7 +338,9 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
 constexpr int kRankThreads = 256, kRankCtas = 32;
 
 struct TopkApply {
-    int mode;                  // 0: indices only; 1: embed (scatter); 2: extract (gather [+ similarity])
+    int mode;                  // 0: indices only; 1: embed (scatter); 2: extract (gather [+ similarity]);
+                               // 3: embed as deltas: out[r] = f(c, w_r) - c, plane untouched, ts.maxrow = max coefficient row (lowrank.cuh)
+    unsigned width;            // mode 3: frame width (row of a flat index)
     int method; float alpha;   // insertion / extraction option 1..3
     float* planes;             // mode 1: coefficient planes, modified in place; mode 2: base planes (read)
     const float* derived;      // mode 2
@@ -366,8 +371,9 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
     if (bad) {
         for (unsigned r = blockIdx.x * kRankThreads + tid; r < k; r += gridDim.x * kRankThreads) {
             out[r] = kBadIndex;
-            if (ap.mode == 2) ext[r] = 0.f;
+            if (ap.mode >= 2) ext[r] = 0.f;
         }
+        if (ap.mode == 3 && blockIdx.x == 0 && tid == 0) ts.maxrow[img] = 0xFFFFFFFFu;
     } else if (blockIdx.x * 64u < cnt) {
         for (unsigned j = tid; j < cnt; j += kRankThreads) keys[j] = __ldcg(cand + j);
         const unsigned slot = tid & 63u, part = tid >> 6;
@@ -389,6 +395,11 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
                 out[r] = p;
                 if (ap.mode == 1) plane[p] = insert_fn(ap.method, ap.alpha, plane[p], __ldg(mk + r));
                 else if (ap.mode == 2) ext[r] = extract_fn(ap.method, ap.alpha, plane[p], dplane[p]);
+                else if (ap.mode == 3) {
+                    const float c0 = plane[p];
+                    ext[r] = __fsub_rn(insert_fn(ap.method, ap.alpha, c0, __ldg(mk + r)), c0);
+                    atomicMax(ts.maxrow + img, p / ap.width);
+                }
             }
             __syncthreads();
         }

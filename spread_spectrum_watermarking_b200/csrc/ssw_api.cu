@@ -22,6 +22,7 @@
 #include "mark_kernels.cuh"
 #include "select_kernels.cuh"
 #include "select_general.cuh"
+#include "lowrank.cuh"
 
 using namespace ssw;
 
@@ -69,6 +70,7 @@ struct ssw_ctx {
     std::map<int, std::unique_ptr<DevPlan>> plans;
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
+    std::map<unsigned, float*> lr_tab;     // line length -> cosine factors of the low-rank embed inverse (lowrank.cuh)
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     bool pdl = true;                       // SSW_PDL=0: no programmatic dependent launches
     int pdl_mode = 1;                      // SSW_PDL_MODE: 0 dependents released at kernel start everywhere; 1 (default) line kernels
@@ -91,6 +93,10 @@ struct ssw_ctx {
     // fused pipelines: ask the forward column pipeline for the low-frequency-block histogram of the ordering that
     // follows (want), learn whether a pipeline produced it (done) -- see run_topk_fast
     struct { bool want = false, done = false; unsigned k = 0; int ordering = 0; } col_hist;
+    bool lowrank = false;                  // SSW_LOWRANK=1: fused embed adds the low-rank update of the k modified coefficients to the
+                                           // original frame (lowrank.cuh) instead of inverting the whole plane.  Measured slower on
+                                           // B200 (C2: 123 vs 68 us, profiles/r2_lowrank_tensor_core.md), so it is opt-in.
+    bool lowrank_mma = false;              // SSW_LOWRANK_MMA=1: the update product of the low-rank inverse on the tensor cores (3xTF32 mma.sync)
     bool col_hist_on = true;               // SSW_COL_HIST=0: selection bin from the topk_block_bin kernel even where a column pipeline runs
     bool sim_exact = false;                // SSW_SIM_EXACT=1: scores in the reference's sequential order (bit-identical)
     // asynchronous host-buffer entry points: two persistent sets of device staging buffers used alternately (the copies
@@ -98,8 +104,12 @@ struct ssw_ctx {
     // ranges with copies still in flight (a later copy that touches one of them is ordered behind it)
     struct Staging { uint8_t* in = nullptr; size_t in_cap = 0; uint8_t* out = nullptr; size_t out_cap = 0;
                      float* f32 = nullptr; size_t f32_cap = 0; cudaEvent_t done = nullptr; bool used = false; };
-    Staging stage[2];
+    Staging stage[4];
     unsigned stage_next = 0;
+    cudaStream_t copy_in2 = nullptr;       // second upload stream: consecutive asynchronous calls alternate, so an upload
+    unsigned async_calls = 0;              // that waits for a download (derived frames) does not hold up the next call's
+    std::vector<cudaEvent_t> markers;      // ssw_ctx_marker / ssw_ctx_wait_marker: ring of events on the copy-out stream
+    uint64_t marker_next = 0;
     struct HostRange { const char* p; size_t n; cudaEvent_t ev; };
     std::vector<HostRange> pending_d2h, pending_h2d;
     std::vector<cudaEvent_t> range_events;
@@ -198,6 +208,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_in2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     if (const char* s = getenv("SSW_OVERLAP_TOPK")) c->overlap_topk = atoi(s) != 0;
@@ -221,6 +232,8 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
+    if (const char* s = getenv("SSW_LOWRANK")) c->lowrank = atoi(s) != 0;
+    if (const char* s = getenv("SSW_LOWRANK_MMA")) c->lowrank_mma = atoi(s) != 0;
     *out = c.release();
     return SSW_OK;
 }
@@ -230,7 +243,7 @@ extern "C" int ssw_ctx_create(int device, ssw_ctx** out) { return ssw_ctx_create
 static void topk_scratch_free(ssw_ctx* c) {
     if (!c->ts_batch) return;
     cudaFree(c->ts.hist); cudaFree(c->ts.ticket); cudaFree(c->ts.sel_bin);
-    cudaFree(c->ts.cand_count); cudaFree(c->ts.cand); cudaFree(c->ts.overflow);
+    cudaFree(c->ts.cand_count); cudaFree(c->ts.cand); cudaFree(c->ts.overflow); cudaFree(c->ts.maxrow);
     c->ts = TopkScratch{};
     c->ts_batch = 0;
 }
@@ -241,12 +254,15 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->plans) cudaFree(kv.second->tables);
     for (auto& kv : c->fast_tw) cudaFree(kv.second);
+    for (auto& kv : c->lr_tab) cudaFree(kv.second);
     topk_scratch_free(c);
     c->general.release();
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
     if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
     if (c->copy_out) { cudaStreamSynchronize(c->copy_out); cudaStreamDestroy(c->copy_out); }
+    if (c->copy_in2) { cudaStreamSynchronize(c->copy_in2); cudaStreamDestroy(c->copy_in2); }
+    for (cudaEvent_t e : c->markers) cudaEventDestroy(e);
     for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
     for (cudaEvent_t e : c->range_events) cudaEventDestroy(e);
     for (auto& st : c->stage) {
@@ -267,6 +283,7 @@ extern "C" int ssw_ctx_synchronize(ssw_ctx* c) {
     CK(cudaStreamSynchronize(c->stream));
     // the asynchronous host-buffer entry points finish on the copy streams
     if (c->copy_in) CK(cudaStreamSynchronize(c->copy_in));
+    if (c->copy_in2) CK(cudaStreamSynchronize(c->copy_in2));
     if (c->copy_out) CK(cudaStreamSynchronize(c->copy_out));
     if (c->aux) CK(cudaStreamSynchronize(c->aux));
     c->pending_d2h.clear();
@@ -997,6 +1014,8 @@ static int ensure_topk_scratch(ssw_ctx* c, unsigned batch) {
     CK(cudaMalloc(&c->ts.cand_count, b * sizeof(unsigned)));
     CK(cudaMalloc(&c->ts.cand, (size_t)b * kTopkCap * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->ts.overflow, sizeof(unsigned)));
+    CK(cudaMalloc(&c->ts.maxrow, b * sizeof(unsigned)));
+    CK(cudaMemset(c->ts.maxrow, 0, b * sizeof(unsigned)));
     CK(cudaMemset(c->ts.hist, 0, (size_t)b * kHistBins * sizeof(unsigned)));
     CK(cudaMemset(c->ts.ticket, 0, b * sizeof(unsigned)));
     CK(cudaMemset(c->ts.cand_count, 0, b * sizeof(unsigned)));
@@ -1035,7 +1054,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
-        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0;
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.maxrow += b0;
         ts.cand += (size_t)b0 * kTopkCap;
         if (full_hist) {
             KScope ks(c, "topk_hist");
@@ -1057,7 +1076,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
-        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap;
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap; ts.maxrow += b0;
         TopkApply a;
         std::memset(&a, 0, sizeof(a));
         if (ap) {
@@ -1068,7 +1087,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
             if (a.out) a.out += (size_t)b0 * a.out_stride;
             if (a.sim) a.sim += b0;
         }
-        KScope ks(c, ap && ap->mode == 1 ? "topk_rank_embed" : (ap && ap->mode == 2 ? "topk_rank_extract" : "topk_rank"));
+        KScope ks(c, ap && (ap->mode == 1 || ap->mode == 3) ? "topk_rank_embed" : (ap && ap->mode == 2 ? "topk_rank_extract" : "topk_rank"));
         launch_pdl(c, topk_rank_kernel, dim3(kRankCtas, nb), kRankThreads, smem, c->stream, ts, k, d_idx + (long long)b0 * idx_stride, idx_stride, a);
     }
     CK(cudaGetLastError());
@@ -1665,6 +1684,19 @@ static unsigned chunk_images(ssw_ctx* c, size_t np, unsigned batch, int planes_p
     return (unsigned)std::min<size_t>(n, batch);
 }
 
+static int lowrank_table(ssw_ctx* c, unsigned n, const float** out) {
+    auto it = c->lr_tab.find(n);
+    if (it == c->lr_tab.end()) {
+        float* t = nullptr;
+        CK(cudaMalloc(&t, (size_t)kLrTab * n * sizeof(float)));
+        { KScope ks(c, "lowrank_table"); lowrank_table_kernel<<<dim3((n + 255) / 256, kLrTab), 256, 0, c->stream>>>(t, n); }
+        CK(cudaGetLastError());
+        it = c->lr_tab.emplace(n, t).first;
+    }
+    *out = it->second;
+    return SSW_OK;
+}
+
 extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t w, uint32_t h, uint32_t batch,
                                         const ssw_config* cfg, const float* marks, size_t n, uint8_t* out_rgb) {
     if (!c || !rgb || !out_rgb || (n && !marks)) return fail(SSW_ERR_INVALID, "NULL argument");
@@ -1679,29 +1711,69 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
     CKS(ensure_topk_scratch(c, cb));
     float* d_planes = nullptr;
     unsigned* d_idx = nullptr;
+    float* d_delta = nullptr;
     CK(cudaMallocAsync(&d_planes, (size_t)cb * np * sizeof(float), c->stream));
     CK(cudaMallocAsync(&d_idx, (size_t)cb * std::max<size_t>(k, 1) * sizeof(unsigned), c->stream));
+    CK(cudaMallocAsync(&d_delta, (size_t)cb * std::max<size_t>(k, 1) * sizeof(float), c->stream));
     int rc = SSW_OK;
     for (unsigned b0 = 0; b0 < batch && rc == SSW_OK; b0 += cb) {
         const unsigned nb = std::min(cb, batch - b0);
         const uint8_t* src = rgb + (size_t)b0 * np * 3;
         // the forward column pipeline leaves the low-frequency-block histogram of every frame for the ordering
-        c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on; c->col_hist.done = false;
+        // (one frame per launch: the in-pipeline histogram takes a kernel off the latency chain; on batched launches it
+        // was measured slower than the separate topk_block_bin kernel, whose cost is shared by the whole batch)
+        c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = false;
         c->col_hist.k = (unsigned)k; c->col_hist.ordering = cfg->ordering;
         rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
         const bool hist_ready = c->col_hist.done;
         c->col_hist.want = false;
+        const bool lowrank = c->lowrank && k > 0 && (w % 4u) == 0 && w <= 65535u && h <= 65535u && aligned(src, 4) && aligned(out_rgb, 4) &&
+                             ((np * 3) % 4) == 0;
         if (rc == SSW_OK && k) {
-            // ordering + embedding: the ranking kernel applies mark value r to the rank-r coefficient in place
+            // ordering + embedding: the ranking kernel applies mark value r to the rank-r coefficient in place -- or, for
+            // the low-rank inverse, stores the change D_r = f(c, w_r) - c of that coefficient (lowrank.cuh)
             TopkApply ap;
             std::memset(&ap, 0, sizeof(ap));
-            ap.mode = 1; ap.method = cfg->method; ap.alpha = cfg->alpha;
+            ap.mode = lowrank ? 3 : 1; ap.method = cfg->method; ap.alpha = cfg->alpha; ap.width = w;
             ap.planes = d_planes; ap.plane_stride = (long long)np;
             ap.marks = marks + (size_t)b0 * n; ap.mark_stride = (long long)n;
+            ap.out = d_delta; ap.out_stride = (long long)k;
             rc = run_topk_fast(c, d_planes, w, h, nb, cfg->ordering, (unsigned)k, d_idx, (long long)k, c->topk_full_hist, hist_ready, &ap);
         }
-        if (rc == SSW_OK) rc = run_inverse(c, d_planes, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3);
+        if (rc == SSW_OK && lowrank) {
+            // Y' = Y + IDCT(D): Kr x W strip products, then Kr FMAs per pixel on top of the original frame
+            const size_t ent_bytes = k * sizeof(unsigned long long);
+            const float *cx_tab, *cy_tab;
+            CKS(lowrank_table(c, w, &cx_tab));
+            CKS(lowrank_table(c, h, &cy_tab));
+            const void* key = (const void*)lowrank_rows_kernel;
+            auto it = c->smem_attr.find(key);
+            if (it == c->smem_attr.end() || it->second < (int)ent_bytes) {
+                CK(cudaFuncSetAttribute(lowrank_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ent_bytes, 16384)));
+                c->smem_attr[key] = (int)std::max<size_t>(ent_bytes, 16384);
+            }
+            for (unsigned i0 = 0; i0 < nb && rc == SSW_OK; i0 += 65535) {
+                const unsigned ni = std::min(65535u, nb - i0);
+                {
+                    KScope ks(c, "lowrank_rows");
+                    launch_pdl(c, lowrank_rows_kernel, dim3((w + 31) / 32, ni), 256, ent_bytes, c->stream, d_planes + (size_t)i0 * np, (long long)np, w, h,
+                               (const unsigned*)(d_idx + (size_t)i0 * k), (const float*)(d_delta + (size_t)i0 * k), (unsigned)k,
+                               (const unsigned*)(c->ts.maxrow + i0), cx_tab);
+                }
+                {
+                    KScope ks(c, "lowrank_apply");
+                    launch_pdl(c, c->lowrank_mma ? lowrank_apply_mma_kernel : lowrank_apply_kernel,
+                               dim3((w + kLrTileX - 1) / kLrTileX, (h + kLrTileY - 1) / kLrTileY, ni), 256, 0, c->stream,
+                               (const float*)(d_planes + (size_t)i0 * np), (long long)np, w, h, (const unsigned char*)(src + (size_t)i0 * np * 3),
+                               (unsigned char*)(out_rgb + ((size_t)b0 + i0) * np * 3), (const unsigned*)(c->ts.maxrow + i0), cy_tab, -0.0f);
+                }
+                CK(cudaGetLastError());
+            }
+        } else if (rc == SSW_OK) {
+            rc = run_inverse(c, d_planes, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3);
+        }
     }
+    cudaFreeAsync(d_delta, c->stream);
     cudaFreeAsync(d_planes, c->stream);
     cudaFreeAsync(d_idx, c->stream);
     if (rc == SSW_OK) CK(cudaGetLastError());
@@ -1740,7 +1812,7 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         ap.out = extracted + (size_t)b0 * n; ap.out_stride = (long long)n;
         ap.sim = (sim && !c->sim_exact) ? sim + b0 : nullptr;
         auto base_forward = [&]() -> int {
-            c->col_hist.want = !c->topk_full_hist && c->col_hist_on; c->col_hist.done = false;
+            c->col_hist.want = !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = false;
             c->col_hist.k = (unsigned)n; c->col_hist.ordering = cfg->ordering;
             const int r = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
             c->col_hist.want = false;
@@ -1947,8 +2019,8 @@ static int range_event(ssw_ctx* c, cudaEvent_t* ev) {
 }
 
 // the next staging set, large enough, with every stream that will touch it ordered behind its previous user
-static int acquire_stage(ssw_ctx* c, size_t in_bytes, size_t out_bytes, size_t n_f32, ssw_ctx::Staging** out) {
-    ssw_ctx::Staging& st = c->stage[c->stage_next++ & 1];
+static int acquire_stage(ssw_ctx* c, cudaStream_t up, size_t in_bytes, size_t out_bytes, size_t n_f32, ssw_ctx::Staging** out) {
+    ssw_ctx::Staging& st = c->stage[c->stage_next++ & 3];
     if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     if (st.in_cap < in_bytes || st.out_cap < out_bytes || st.f32_cap < n_f32) {
         CKS(ssw_ctx_synchronize(c));   // growth is rare (first calls): everything drains, then the set is reallocated
@@ -1958,7 +2030,7 @@ static int acquire_stage(ssw_ctx* c, size_t in_bytes, size_t out_bytes, size_t n
         st.used = false;
     }
     if (st.used) {
-        CK(cudaStreamWaitEvent(c->copy_in, st.done, 0));
+        CK(cudaStreamWaitEvent(up, st.done, 0));
         CK(cudaStreamWaitEvent(c->stream, st.done, 0));
     }
     st.used = true;
@@ -1981,17 +2053,18 @@ extern "C" int ssw_embed_batch_rgb8_async(ssw_ctx* c, const uint8_t* rgb, uint32
     if (batch == 0) return SSW_OK;
     CKS(ctx_bind(c));
     const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch;
+    cudaStream_t up = (c->async_calls++ & 1) ? c->copy_in2 : c->copy_in;   // consecutive calls alternate upload streams
     ssw_ctx::Staging* st;
-    CKS(acquire_stage(c, bytes, bytes, std::max<size_t>(n * batch, 1), &st));
+    CKS(acquire_stage(c, up, bytes, bytes, std::max<size_t>(n * batch, 1), &st));
     cudaEvent_t ev_up, ev_down;
     CKS(range_event(c, &ev_up));
     CKS(range_event(c, &ev_down));
     // uploads wait for downloads still writing their source ranges; downloads for uploads still reading their target
-    CKS(wait_host_range(c, c->copy_in, c->pending_d2h, rgb, bytes));
-    CKS(wait_host_range(c, c->copy_in, c->pending_d2h, marks, n * batch * sizeof(float)));
+    CKS(wait_host_range(c, up, c->pending_d2h, rgb, bytes));
+    CKS(wait_host_range(c, up, c->pending_d2h, marks, n * batch * sizeof(float)));
     CKS(wait_host_range(c, c->copy_out, c->pending_h2d, out_rgb, bytes));
     CKS(wait_host_range(c, c->copy_out, c->pending_d2h, out_rgb, bytes));
-    if (n) CK(cudaMemcpyAsync(st->f32, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->copy_in));
+    if (n) CK(cudaMemcpyAsync(st->f32, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, up));
     const uint32_t cb = pipe_chunk_frames(fbytes, batch);
     const uint32_t nchunks = (batch + cb - 1) / cb;
     int rc = SSW_OK;
@@ -2000,8 +2073,8 @@ extern "C" int ssw_embed_batch_rgb8_async(ssw_ctx* c, const uint8_t* rgb, uint32
         cudaEvent_t e_in, e_cmp;
         CKS(pipe_event(c, 1 + 2 * (size_t)ci, &e_in));
         CKS(pipe_event(c, 2 + 2 * (size_t)ci, &e_cmp));
-        CK(cudaMemcpyAsync(st->in + f0 * fbytes, rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
-        CK(cudaEventRecord(e_in, c->copy_in));
+        CK(cudaMemcpyAsync(st->in + f0 * fbytes, rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, up));
+        CK(cudaEventRecord(e_in, up));
         CK(cudaStreamWaitEvent(c->stream, e_in, 0));
         rc = ssw_embed_batch_rgb8_dev(c, st->in + f0 * fbytes, w, h, nf, cfg, st->f32 + (size_t)f0 * n, n, st->out + f0 * fbytes);
         if (rc != SSW_OK) break;
@@ -2009,7 +2082,7 @@ extern "C" int ssw_embed_batch_rgb8_async(ssw_ctx* c, const uint8_t* rgb, uint32
         CK(cudaStreamWaitEvent(c->copy_out, e_cmp, 0));
         CK(cudaMemcpyAsync(out_rgb + f0 * fbytes, st->out + f0 * fbytes, nf * fbytes, cudaMemcpyDeviceToHost, c->copy_out));
     }
-    CK(cudaEventRecord(ev_up, c->copy_in));
+    CK(cudaEventRecord(ev_up, up));
     CK(cudaEventRecord(ev_down, c->copy_out));
     CK(cudaEventRecord(st->done, c->copy_out));
     c->pending_h2d.push_back({(const char*)rgb, bytes, ev_up});
@@ -2028,24 +2101,25 @@ extern "C" int ssw_extract_batch_rgb8_async(ssw_ctx* c, const uint8_t* base_rgb,
     if (batch == 0 || n == 0) return SSW_OK;
     CKS(ctx_bind(c));
     const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch, vbytes = n * batch * sizeof(float);
+    cudaStream_t up = (c->async_calls++ & 1) ? c->copy_in2 : c->copy_in;
     ssw_ctx::Staging* st;
     // out: extracted vectors followed by the scores; f32: the marks
-    CKS(acquire_stage(c, 2 * bytes, vbytes + batch * sizeof(float), n * batch, &st));
+    CKS(acquire_stage(c, up, 2 * bytes, vbytes + batch * sizeof(float), n * batch, &st));
     uint8_t *d_b = st->in, *d_d = st->in + bytes;
     float* d_ext = (float*)st->out;
     float* d_sim = sim ? d_ext + n * batch : nullptr;
     cudaEvent_t ev_up, ev_down;
     CKS(range_event(c, &ev_up));
     CKS(range_event(c, &ev_down));
-    CKS(wait_host_range(c, c->copy_in, c->pending_d2h, base_rgb, bytes));
-    if (marks) CKS(wait_host_range(c, c->copy_in, c->pending_d2h, marks, vbytes));
+    CKS(wait_host_range(c, up, c->pending_d2h, base_rgb, bytes));
+    if (marks) CKS(wait_host_range(c, up, c->pending_d2h, marks, vbytes));
     for (const void* q : {(const void*)extracted, (const void*)sim}) {
         if (!q) continue;
         const size_t qn = q == (const void*)extracted ? vbytes : batch * sizeof(float);
         CKS(wait_host_range(c, c->copy_out, c->pending_h2d, q, qn));
         CKS(wait_host_range(c, c->copy_out, c->pending_d2h, q, qn));
     }
-    if (marks) CK(cudaMemcpyAsync(st->f32, marks, vbytes, cudaMemcpyHostToDevice, c->copy_in));
+    if (marks) CK(cudaMemcpyAsync(st->f32, marks, vbytes, cudaMemcpyHostToDevice, up));
     const uint32_t cb = pipe_chunk_frames(2 * fbytes, batch);
     const uint32_t nchunks = (batch + cb - 1) / cb;
     int rc = SSW_OK;
@@ -2053,12 +2127,12 @@ extern "C" int ssw_extract_batch_rgb8_async(ssw_ctx* c, const uint8_t* base_rgb,
         const uint32_t f0 = ci * cb, nf = std::min(cb, batch - f0);
         cudaEvent_t e_in;
         CKS(pipe_event(c, 1 + (size_t)ci, &e_in));
-        CK(cudaMemcpyAsync(d_b + f0 * fbytes, base_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
+        CK(cudaMemcpyAsync(d_b + f0 * fbytes, base_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, up));
         // the derived frames are typically the output of an embed call whose download is still in flight: the base
         // frames above go up beside that download, the derived frames behind it
-        if (ci == 0) CKS(wait_host_range(c, c->copy_in, c->pending_d2h, derived_rgb, bytes));
-        CK(cudaMemcpyAsync(d_d + f0 * fbytes, derived_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, c->copy_in));
-        CK(cudaEventRecord(e_in, c->copy_in));
+        if (ci == 0) CKS(wait_host_range(c, up, c->pending_d2h, derived_rgb, bytes));
+        CK(cudaMemcpyAsync(d_d + f0 * fbytes, derived_rgb + f0 * fbytes, nf * fbytes, cudaMemcpyHostToDevice, up));
+        CK(cudaEventRecord(e_in, up));
         CK(cudaStreamWaitEvent(c->stream, e_in, 0));
         rc = ssw_extract_batch_rgb8_dev(c, d_b + f0 * fbytes, d_d + f0 * fbytes, w, h, nf, cfg, n, d_ext + (size_t)f0 * n,
                                         marks ? st->f32 + (size_t)f0 * n : nullptr, d_sim ? d_sim + f0 : nullptr);
@@ -2071,7 +2145,7 @@ extern "C" int ssw_extract_batch_rgb8_async(ssw_ctx* c, const uint8_t* base_rgb,
         CK(cudaMemcpyAsync(extracted, d_ext, vbytes, cudaMemcpyDeviceToHost, c->copy_out));
         if (d_sim) CK(cudaMemcpyAsync(sim, d_sim, batch * sizeof(float), cudaMemcpyDeviceToHost, c->copy_out));
     }
-    CK(cudaEventRecord(ev_up, c->copy_in));
+    CK(cudaEventRecord(ev_up, up));
     CK(cudaEventRecord(ev_down, c->copy_out));
     CK(cudaEventRecord(st->done, c->copy_out));
     c->pending_h2d.push_back({(const char*)base_rgb, bytes, ev_up});
@@ -2080,6 +2154,36 @@ extern "C" int ssw_extract_batch_rgb8_async(ssw_ctx* c, const uint8_t* base_rgb,
     c->pending_d2h.push_back({(const char*)extracted, vbytes, ev_down});
     if (sim) c->pending_d2h.push_back({(const char*)sim, batch * sizeof(float), ev_down});
     return rc;
+}
+
+// completion markers of the asynchronous calls: ssw_ctx_marker returns a ticket for "everything enqueued so far";
+// ssw_ctx_wait_marker blocks the host until that point is reached (results of the calls before the marker are in host
+// memory) WITHOUT draining later calls -- a caller keeps one or two calls in flight and reads the results of the previous
+// one.  Tickets are valid for the 64 most recent markers.
+extern "C" int ssw_ctx_marker(ssw_ctx* c, uint64_t* marker) {
+    if (!c || !marker) return fail(SSW_ERR_INVALID, "NULL argument");
+    CKS(ctx_bind(c));
+    constexpr size_t kRing = 64;
+    if (c->markers.size() < kRing) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+        c->markers.push_back(e);
+    }
+    cudaEvent_t e = c->markers[c->marker_next % kRing];
+    // downloads are the last stage of every asynchronous call; calls without a download end on the context stream
+    CK(cudaEventRecord(c->ev_join, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_out, c->ev_join, 0));
+    CK(cudaEventRecord(e, c->copy_out));
+    *marker = c->marker_next++;
+    return SSW_OK;
+}
+
+extern "C" int ssw_ctx_wait_marker(ssw_ctx* c, uint64_t marker) {
+    if (!c) return fail(SSW_ERR_INVALID, "ctx is NULL");
+    if (marker >= c->marker_next || marker + 64 < c->marker_next) return fail(SSW_ERR_INVALID, "unknown or expired marker");
+    CKS(ctx_bind(c));
+    CK(cudaEventSynchronize(c->markers[marker % 64]));
+    return SSW_OK;
 }
 
 extern "C" int ssw_ctx_last_topk_fallbacks(ssw_ctx* c) {

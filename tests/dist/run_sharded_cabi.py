@@ -93,11 +93,14 @@ def main():
             print('sharded (C ABI) vs unsharded: rgb8 max |d| %d, differing %.5f%%, identical ranks %.4f, extract max |d| %.2e, similarity %.3f'
                   % (d.max(), 100.0 * (d > 0).mean(), same, float(np.abs(ext - ref_ext).max()), sim))
             ok = ok and d.max() <= 1 and (d > 0).mean() < 0.02 and same > 0.95 and np.abs(ext - ref_ext).max() < 5e-3
+            del plain   # writers / readers go before their context
     if rank == 0:
         print('SHARDED_CABI_OK' if ok else 'SHARDED_CABI_FAILED')
     flag = torch.tensor([1 if ok else 0], device='cuda')
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    import gc
+    gc.collect()
     sh.close()
     ctx.close()
     if world > 1:

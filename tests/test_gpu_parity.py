@@ -391,9 +391,10 @@ def test_fused_batch_embed_extract(wm, ctx, so, w, h, B):
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
     e = ext[last].cpu().numpy()
     assert sim_close(sims[last], so.similarity(e, mk_h[last]))
-    # the same images through the Writer/Reader API give the same bytes as the fused pipeline
+    # the same image through the Writer/Reader API (its own launches of the same kernels): equal up to isolated +-1 LSB ties
     api = wm.Writer.new(f, ctx=ctx).mark_rgb8([mk_h[last]])
-    assert (api == out[last].cpu().numpy()).all()
+    da = np.abs(api.astype(int) - out[last].cpu().numpy().astype(int))
+    assert da.max() <= 1 and (da > 0).mean() < 1e-4, (da.max(), (da > 0).mean())
     # host-buffer end-to-end entry points agree with the device-resident ones
     if B <= 2:
         fh = frames.cpu().numpy()
@@ -452,6 +453,48 @@ def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
         import gc
         gc.collect()
         cg.close(); cf.close()
+
+
+@pytest.mark.parametrize('w,h,B,method', [(3840, 2160, 1, 2), (1920, 1080, 3, 2), (640, 444, 2, 1), (1280, 720, 2, 3), (1000, 333, 1, 2)])
+def test_lowrank_embed_inverse_matches_full_inverse(wm, so, w, h, B, method, monkeypatch):
+    """fused embed: Y + IDCT(changes of the k ordered coefficients) (csrc/lowrank.cuh, SSW_LOWRANK=1) against the inverse
+    transform of the whole modified plane (SSW_LOWRANK=0, the reference's structure, src/algorithm.rs:361-379):
+    the same RGB8 up to isolated +-1 LSB ties, and within 1 LSB of the oracle"""
+    import torch
+    monkeypatch.setenv('SSW_LOWRANK', '0')
+    c_full = wm.Context(0)
+    monkeypatch.setenv('SSW_LOWRANK', '1')            # opt-in (measured slower than the two line passes)
+    monkeypatch.setenv('SSW_LOWRANK_MMA', '0')
+    c_low = wm.Context(0)
+    monkeypatch.setenv('SSW_LOWRANK_MMA', '1')        # the update product as 3xTF32 mma.sync on the tensor cores
+    c_mma = wm.Context(0)
+    monkeypatch.delenv('SSW_LOWRANK_MMA')
+    monkeypatch.delenv('SSW_LOWRANK')
+    try:
+        n = 1000
+        rng = np.random.default_rng(w + method)
+        frames = _synth_dev(wm, c_low, w, h, 9, 0, B)
+        mk_h = rng.standard_normal((B, n)).astype(np.float32)
+        mk = torch.from_numpy(mk_h).cuda()
+        cfg = wm._lib.ssw_config(method, 0.1 if method != 1 else 2000.0, 0)   # Option1 adds alpha*w to coefficients of ~1e4
+        outs = []
+        for cx in (c_full, c_low, c_mma):
+            o = torch.empty_like(frames)
+            torch.cuda.synchronize()
+            wm._lib.check(wm.lib.ssw_embed_batch_rgb8_dev(cx.handle, frames.data_ptr(), w, h, B, ctypes.byref(cfg), mk.data_ptr(), n, o.data_ptr()))
+            cx.synchronize()
+            assert cx.last_topk_fallbacks() == 0
+            outs.append(o.cpu().numpy())
+        for o in outs[1:]:
+            d = np.abs(outs[0].astype(int) - o.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-4, (d.max(), (d > 0).mean())
+        assert (outs[1] != frames.cpu().numpy()).mean() > 0.05          # the mark is really in there
+        if w * h <= 1920 * 1080 and method == 2:
+            ref, _, _ = so.embed(frames[B - 1].cpu().numpy(), [mk_h[B - 1]])
+            dr = np.abs(outs[1][B - 1].astype(int) - ref.astype(int))
+            assert dr.max() <= 1 and (dr > 0).mean() < 1e-3
+    finally:
+        c_full.close(); c_low.close(); c_mma.close()
 
 
 def test_packed_rgb8_output_conversion_is_exact_for_every_float(wm, ctx):
@@ -556,7 +599,8 @@ def test_fused_dev_pipeline_leaves_overflowing_frames_unmarked(wm, ctx, so):
     assert ctx.last_topk_fallbacks() == 1
     o = out.cpu().numpy()
     assert np.abs(o[0].astype(int) - noise[0].astype(int)).max() <= 1      # unmarked: forward + inverse only
-    assert (o[1] == wm.Writer.new(noise[1], ctx=ctx).mark_rgb8([mk_h[1]])).all()
+    d1 = np.abs(o[1].astype(int) - wm.Writer.new(noise[1], ctx=ctx).mark_rgb8([mk_h[1]]).astype(int))
+    assert d1.max() <= 1 and (d1 > 0).mean() < 1e-4          # fused low-rank inverse vs the Writer's full inverse
     ext = torch.empty((2, n), dtype=torch.float32, device='cuda')
     sim = torch.empty((2,), dtype=torch.float32, device='cuda')
     wm._lib.check(wm.lib.ssw_extract_batch_rgb8_dev(ctx.handle, fr.data_ptr(), out.data_ptr(), w, h, 2, ctypes.byref(cfg), n,
@@ -582,7 +626,10 @@ def test_topk_block_bound_is_repaired_on_flat_spectra(wm, ctx, so):
     cfg = wm._lib.ssw_config(2, 0.1, 0)
     wm._lib.check(wm.lib.ssw_embed_batch_rgb8(ctx.handle, noise.ctypes.data, 1920, 1080, 1, ctypes.byref(cfg),
                                               mark.ctypes.data, 1000, out.ctypes.data))
-    assert (out == api).all()
+    # (white noise: the 1000 largest coefficients sit in ~1000 different rows -- the low-rank inverse of the fused
+    # pipeline sweeps all of them and must still agree with the full inverse of the Writer API)
+    d = np.abs(out.astype(int) - api.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
 
 
 def test_bank_100k_marks_at_full_size(wm, ctx, so):
