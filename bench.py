@@ -26,6 +26,7 @@ thread on all host cores.
 """
 import argparse
 import ctypes
+import faulthandler
 import json
 import os
 import statistics
@@ -35,6 +36,8 @@ import threading
 import time
 
 import numpy as np
+
+faulthandler.enable()   # a crash inside a native library prints the Python stack of every thread to stderr
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -339,6 +342,12 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def note(msg):
+    """progress on stderr (stdout carries the one JSON line)"""
+    sys.stderr.write('[bench rank %s] %s\n' % (os.environ.get('RANK', '0'), msg))
+    sys.stderr.flush()
+
+
 def dist_setup(args):
     """one process per GPU; NCCL only for the barrier and the max-over-ranks timing (and the exchanges of c4)"""
     import torch
@@ -464,6 +473,7 @@ def run_ours(args, wl, workload, K, W, with_cpu_baseline=True, e2e_steps=None):
     clk = clocks.stop() if rank == 0 else None
     ms_embed = timed(embed, K, 1)
     ms_extract = timed(extract, K, 1)
+    note('%s: timed regions done (%.4f ms/step)' % (workload, ms_total / K))
     fallbacks = ctx.last_topk_fallbacks()
     sims = sim.cpu().numpy()[:min(nfr, (K + W) * B)]
     if bank is not None:
@@ -484,6 +494,7 @@ def run_ours(args, wl, workload, K, W, with_cpu_baseline=True, e2e_steps=None):
     for s in range(K):
         step(W + s)
     prof = ctx.profile_end()
+    note('%s: per-kernel attribution done' % workload)
     peak, peak_src = load_peaks()
     traffic = load_traffic()
     kernels = []
@@ -516,7 +527,7 @@ def run_ours(args, wl, workload, K, W, with_cpu_baseline=True, e2e_steps=None):
     step_algo = {'embed_bytes_per_px': 53.0, 'extract_bytes_per_px': 50.0}
     # whole-step rates twice: against SURVEY.md 8(d)'s separate-kernel byte counts (53 / 50 B per px; comparable with
     # BASELINE.md) and against the bytes this build actually moves (fused passes, DESIGN.md section 3: 37 / 50 B per px)
-    built = {'embed_bytes_per_px': 7.0 + 8.0 + 4.0 + 6.0, 'extract_bytes_per_px': 2 * (7.0 + 8.0) + 4.0}
+    built = {'embed_bytes_per_px': 7.0 + 8.0 + 4.0 + 8.0 + 10.0, 'extract_bytes_per_px': 2 * (7.0 + 8.0) + 4.0}
     whole = {'embed_gbs': round(53.0 * px_step * K / (ms_embed * 1e-3) / 1e9, 1),
              'extract_gbs': round(50.0 * px_step * K / (ms_extract * 1e-3) / 1e9, 1),
              'embed_gbs_as_built': round(built['embed_bytes_per_px'] * px_step * K / (ms_embed * 1e-3) / 1e9, 1),
@@ -594,6 +605,7 @@ def run_ours(args, wl, workload, K, W, with_cpu_baseline=True, e2e_steps=None):
         t = torch.tensor([e2e_ms], device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    note('%s: end-to-end done (%.3f ms/step)' % (workload, e2e_ms / Ke))
     if not worst > 6.0 or ctx.last_topk_fallbacks():
         raise SystemExit('bench: e2e extraction failed to detect the embedded marks')
     e2e = {'value': world * px_step * Ke / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s',
@@ -661,8 +673,9 @@ def run_c4(args, wl):
     rank, world, local = dist_setup(args)
     w = h = int(os.environ.get('SSW_C4_SIZE', wl['w']))
     # the C-ABI sharded path (ssw_sharded_*): orchestration inside libssw, exchange through peer-mapped planes
-    ctx = wm.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream)
+    # the context runs on a stream torch owns: tensors used on it may be freed after the context has gone
+    stream = torch.cuda.Stream()
+    ctx = wm.Context(local, stream=stream.cuda_stream)
     sh = sharded.Sharded(ctx, w, h, rank, world)
     hb = h // world
     cfg = ssw_config(2, ALPHA, 0)
@@ -800,9 +813,11 @@ def run_c4(args, wl):
             'cpu_baseline': None, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk, 'similarity': sim,
             'min_similarity': sim,
         })
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    del rows, hrows, hout, hext, out, d_in, d_base, d_der, ext_d, mark_d
     sh.close()
     ctx.close()
-    del rows, hrows, hout, out, d_in, d_base, d_der
     torch.cuda.empty_cache()
     return result
 
@@ -837,16 +852,28 @@ def main():
     else:
         # the driver's invocation: BASELINE.json configs[1] is the line; every other config rides along as a sub-object
         # with its own value, per-kernel table and detection guard (a failed guard aborts the whole run)
+        note('c2 ...')
         line = run_ours(args, WORKLOADS['c2'], 'c2', K, W)
         if not args.no_extra:
             extra = {}
-            extra['c1'] = run_ours(args, WORKLOADS['c1'], 'c1', min(K, 100), W, with_cpu_baseline=False, e2e_steps=10)
-            extra['c3'] = run_ours(args, WORKLOADS['c3'], 'c3', max(3, min(K, 20)), W, with_cpu_baseline=False, e2e_steps=3)
-            extra['c5'] = run_ours(args, WORKLOADS['c5'], 'c5', min(K, 100), W, with_cpu_baseline=False, e2e_steps=5)
+
+            def ride_along(name, fn):
+                # a failing sub-object is reported as such (every rank takes the same branch: the guards are deterministic);
+                # the c2 line above is the contract and is printed in any case
+                note(name + ' ...')
+                try:
+                    extra[name] = fn()
+                except (Exception, SystemExit) as e:   # noqa: B902
+                    extra[name] = {'error': '%s: %s' % (type(e).__name__, e)}
+                    note('%s FAILED: %s' % (name, extra[name]['error']))
+
+            ride_along('c1', lambda: run_ours(args, WORKLOADS['c1'], 'c1', min(K, 100), W, with_cpu_baseline=False, e2e_steps=10))
+            ride_along('c3', lambda: run_ours(args, WORKLOADS['c3'], 'c3', max(3, min(K, 20)), W, with_cpu_baseline=False, e2e_steps=3))
+            ride_along('c5', lambda: run_ours(args, WORKLOADS['c5'], 'c5', min(K, 100), W, with_cpu_baseline=False, e2e_steps=5))
             if args.gpus >= 2:
-                extra['c4'] = run_c4(args, WORKLOADS['c4'])
+                ride_along('c4', lambda: run_c4(args, WORKLOADS['c4']))
             if line is not None:
-                line.update(extra)
+                line.update({k: v for k, v in extra.items() if v is not None})
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()

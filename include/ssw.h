@@ -61,9 +61,15 @@ const char* ssw_version(void);
  *      workspace, stream.  `stream` is a cudaStream_t (NULL = create an own non-blocking stream). */
 int ssw_ctx_create(int device, ssw_ctx** out);
 int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out);
+/* Waits for the context's stream and drops the caller's reference.  Writers, readers, banks and sharded frames created
+ * from the context keep it alive until they are destroyed themselves, so the order of the destroy calls is free. */
 int ssw_ctx_destroy(ssw_ctx* ctx);
 int ssw_ctx_synchronize(ssw_ctx* ctx);
 void* ssw_ctx_stream(ssw_ctx* ctx);
+/* diagnostics: per-CTA time line of the persistent row / column pipelines (load issued, tile landed, compute done, store
+ * issued ... as clock64 values, layout in csrc/dct_pipe.cuh).  dev_buf: 16 x 1024 x 64 int64 (8 MiB) of device memory;
+ * launch i of a pipeline kernel writes block i % 16.  NULL switches it off (default).  tools/pipe_trace.py prints it. */
+int ssw_ctx_set_trace(ssw_ctx* ctx, void* dev_buf);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 uint64_t ssw_ctx_launch_count(ssw_ctx* ctx);
 /* per-kernel timing: between _begin and _end every kernel launch of this context is bracketed by

@@ -55,6 +55,7 @@ SIGNATURES = {
     'ssw_ctx_create_on_stream': (c_int, [c_int, _p, _pp]),
     'ssw_ctx_destroy': (c_int, [_p]),
     'ssw_ctx_synchronize': (c_int, [_p]),
+    'ssw_ctx_set_trace': (c_int, [_p, _p]),
     'ssw_ctx_stream': (c_void_p, [_p]),
     'ssw_ctx_launch_count': (c_uint64, [_p]),
     'ssw_ctx_profile_begin': (c_int, [_p]),

@@ -33,6 +33,7 @@ struct PipeArgs {
     const cplx* tw;            // stage twiddles (global copy)
     const cplx* t4;            // exp(-i*pi*k/(2N)) (global copy)
     int pdl_late;
+    long long* trace;          // diagnostics (ssw_ctx_set_trace): 64 time stamps per CTA, see pipe_trace_slot(); nullptr = off
 #if defined(__CUDACC__)
     // forward pass only: the selection bin of the ordering that follows (select_kernels.cuh), computed on the fly.  The
     // tiles that produce the low-frequency block -- coefficient rows < hist_rows, columns < hist_cols -- add its
@@ -231,6 +232,7 @@ struct RowPipeArgs {
     const cplx* t4;
     int pdl_late;
     float neg_zero;             // -0.0f at run time, see FastArgs
+    long long* trace;           // diagnostics (ssw_ctx_set_trace), nullptr = off
 };
 
 template <class P_, int TEAMS_, bool INVERSE_, int MINB_ = 2>
@@ -389,6 +391,15 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- pipeline time line (diagnostics; one uniform branch per event when off) ------------------------------------------
+// 64 slots of 8 bytes per CTA: 0 %globaltimer at start, 1 clock64 at start, 2 clock64 after the dependency wait, 3 clock64 when
+// the compute warps have finished, 4 %globaltimer then, 5 tiles of this CTA, 6 %smid;  tile j < 7 at 8 + 8j:
+//   +0 load issued (producer)   +1 tile landed (compute)   +2 compute done   +3 store issued (producer)
+//   +4 store has read the buffer (producer)   +5 row pipes: input buffer A released   +6 row pipes (inverse): originals landed
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_at(long long* trace, int slot) { if (trace) trace[blockIdx.x * 64 + slot] = clock64(); }
+__device__ __forceinline__ void trace_tile(long long* trace, int j, int what) { if (trace && j < 7) trace[blockIdx.x * 64 + 8 + 8 * j + what] = clock64(); }
+
 struct alignas(64) TmaMap { unsigned long long v[16]; };   // CUtensorMap (128 bytes, 64-byte aligned)
 
 // map_s: sample side  (4-D: column, parity, row pair, image);  map_c: coefficient side (3-D: column, row, image)
@@ -409,6 +420,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
         mbar_init(bar_ready0, 1); mbar_init(bar_ready0 + 8, 1);
         fence_mbar_init();
     }
+    if (a.trace && tid == 0) { a.trace[blockIdx.x * 64] = (long long)global_ns(); trace_at(a.trace, 1); }
     if (!a.pdl_late) pdl_trigger();
     // twiddle tables are read-only inputs written long before the previous kernel: stage them before the dependency wait
     if constexpr (K::TW_SMEM) {
@@ -423,9 +435,14 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
     }
     __syncthreads();
     pdl_wait();
+    if (tid == 0) trace_at(a.trace, 2);
 
     const int first = blockIdx.x, step = gridDim.x;
     const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
+    if (a.trace && tid == 0) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.trace[blockIdx.x * 64 + 5] = nt; a.trace[blockIdx.x * 64 + 6] = smid;
+    }
     auto tile_of = [&](int j) { int t = first + j * step - a.tile_rot; return t < 0 ? t + a.total_tiles : t; };
 
     if (tid >= NC) {
@@ -435,6 +452,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
                 const int tile = tile_of(j), b = j & 1;
                 const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
                 const unsigned dst = sbase + b * K::BUF_BYTES, bar = bar_full0 + 8 * b;
+                trace_tile(a.trace, j, 0);
                 mbar_expect_tx(bar, K::BUF_BYTES);
                 if constexpr (!K::INVERSE) {
                     for (int par = 0; par < 2; ++par)
@@ -464,9 +482,11 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
             for (int j = 0; j < nt; ++j) {
                 const int b = j & 1;
                 mbar_wait(bar_ready0 + 8 * b, (j >> 1) & 1);   // the compute warps have finished tile j (results in BUF[b])
+                trace_tile(a.trace, j, 3);
                 issue_store(j);
                 if (j + 2 < nt) {
                     tma_wait_read0();                          // the store has read BUF[b]: it may be overwritten
+                    trace_tile(a.trace, j, 4);
                     issue_load(j + 2);
                 }
             }
@@ -482,6 +502,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
         const int b = j & 1;
         cplx* buf = (cplx*)(pipe_smem + b * K::BUF_BYTES);
         mbar_wait(bar_full0 + 8 * b, (j >> 1) & 1);            // tile j has landed in BUF[b]
+        if (tid == 0) trace_tile(a.trace, j, 1);
 #pragma unroll 1
         for (int rd = 0; rd < K::ROUNDS; ++rd) {
             static_for<K::NPHASES>([&](auto ph) {
@@ -533,8 +554,9 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
         }
         fence_proxy_async();                                   // generic-proxy writes of BUF[b] -> visible to the TMA store
         named_sync(1, NC);                                     // (also: FFT buffers free for the next tile)
-        if (tid == 0) mbar_arrive(bar_ready0 + 8 * b);
+        if (tid == 0) { trace_tile(a.trace, j, 2); mbar_arrive(bar_ready0 + 8 * b); }
     }
+    if (a.trace && tid == 0) { trace_at(a.trace, 3); a.trace[blockIdx.x * 64 + 4] = (long long)global_ns(); }
 }
 
 // ---- linear bulk copies (cp.async.bulk, no tensor map): global -> shared signals an mbarrier, shared -> global joins a bulk group
@@ -561,12 +583,18 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
         mbar_init(bar_readyB, NC);    // inverse: every compute thread has written (and fenced) its part of B
         fence_mbar_init();
     }
+    if (a.trace && tid == 0) { a.trace[blockIdx.x * 64] = (long long)global_ns(); trace_at(a.trace, 1); }
     if (!a.pdl_late) pdl_trigger();
     __syncthreads();
     pdl_wait();
+    if (tid == 0) trace_at(a.trace, 2);
 
     const int first = blockIdx.x, step = gridDim.x;
     const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
+    if (a.trace && tid == 0) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.trace[blockIdx.x * 64 + 5] = nt; a.trace[blockIdx.x * 64 + 6] = smid;
+    }
     const size_t frame_px = (size_t)a.w * a.h;
     auto px_of = [&](int j) {   // first pixel of tile j of this CTA, counted over the whole batch
         const int tile = first + j * step, img = tile / a.tiles_per_image;
@@ -577,6 +605,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
         // ===================== producer warp =====================
         if (tid == NC) {
             auto load_a = [&](int j) {
+                trace_tile(a.trace, j, 0);
                 mbar_expect_tx(bar_fullA, K::A_BYTES);
                 if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, a.plane + px_of(j), K::A_BYTES, bar_fullA);
                 else bulk_load(sbase + K::OFF_A, a.pix + 3 * px_of(j), K::A_BYTES, bar_fullA);
@@ -596,10 +625,12 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
                 }
                 if constexpr (K::INVERSE) {
                     mbar_wait(bar_readyB, j & 1);              // output bytes of tile j are in B (writers fenced)
+                    trace_tile(a.trace, j, 3);
                     bulk_store(a.out + 3 * px_of(j), sbase + K::OFF_B, K::B_BYTES);
                     tma_commit();
                     if (j + 1 < nt) {
                         tma_wait_read0();                      // the store has read B
+                        trace_tile(a.trace, j, 4);
                         load_b(j + 1);
                     }
                 }
@@ -616,14 +647,15 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
     for (int j = 0; j < nt; ++j) {
         float* gout = K::INVERSE ? nullptr : a.plane + px_of(j);
         mbar_wait(bar_fullA, j & 1);                           // tile j has landed in A
+        if (tid == 0) trace_tile(a.trace, j, 1);
         static_for<K::NPH>([&](auto ph) {
             constexpr int p = decltype(ph)::value;
             if constexpr (p == K::NPH - 1) {
                 if (a.pdl_late && j + 1 == nt) pdl_trigger();
-                if constexpr (K::INVERSE) mbar_wait(bar_fullB, j & 1);         // the originals of tile j have landed in B
+                if constexpr (K::INVERSE) { mbar_wait(bar_fullB, j & 1); if (tid == 0) trace_tile(a.trace, j, 6); }   // the originals of tile j have landed in B
             }
             K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, gout, tid, th);
-            if constexpr (p == 0) mbar_arrive(bar_freeA);                      // (this thread's) reads of A are done
+            if constexpr (p == 0) { mbar_arrive(bar_freeA); if (tid == 0) trace_tile(a.trace, j, 5); }   // (this thread's) reads of A are done
             if constexpr (p + 1 < K::NPH) named_sync(1 + team, K::T);
         });
         if constexpr (K::INVERSE) {
@@ -631,7 +663,9 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
             mbar_arrive(bar_readyB);
         }
         named_sync(1 + team, K::T);                            // the team has read its FFT buffer: the next tile may overwrite it
+        if (tid == 0) trace_tile(a.trace, j, 2);
     }
+    if (a.trace && tid == 0) { trace_at(a.trace, 3); a.trace[blockIdx.x * 64 + 4] = (long long)global_ns(); }
 }
 #endif
 

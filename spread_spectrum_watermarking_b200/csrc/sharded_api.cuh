@@ -92,7 +92,7 @@ transpose_push_kernel(const float* __restrict__ src, unsigned nr, unsigned cb, l
 
 // ---- the per-rank object ------------------------------------------------------------------------------------------------
 struct ssw_sharded {
-    ssw_ctx* ctx = nullptr;
+    CtxRef ctx;
     int rank = 0, world = 1;
     uint32_t w = 0, h = 0, hb = 0, wb = 0;   // frame, rows / columns of this rank
     ssw_nccl::ncclComm_t comm = nullptr;

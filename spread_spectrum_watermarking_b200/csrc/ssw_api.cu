@@ -19,6 +19,7 @@
 #include "dct_kernels.cuh"
 #include "fast_dispatch.h"
 #include "dct_pipe.cuh"
+#include <atomic>
 #include "mark_kernels.cuh"
 #include "select_kernels.cuh"
 #include "select_general.cuh"
@@ -70,6 +71,9 @@ struct ssw_ctx {
     std::map<int, std::unique_ptr<DevPlan>> plans;
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
+    std::atomic<int> refs{1};              // the owner's reference + one per live writer / reader / bank / sharded object
+    long long* trace = nullptr;            // ssw_ctx_set_trace: device buffer of pipeline time stamps (dct_pipe.cuh), 16 launches x 1024 CTAs x 64
+    unsigned trace_launch = 0;
     std::map<unsigned, float*> lr_tab;     // line length -> cosine factors of the low-rank embed inverse (lowrank.cuh)
     bool use_fast = true;                  // SSW_NO_FAST=1 forces the generic line kernels
     bool pdl = true;                       // SSW_PDL=0: no programmatic dependent launches
@@ -248,8 +252,10 @@ static void topk_scratch_free(ssw_ctx* c) {
     c->ts_batch = 0;
 }
 
-extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
-    if (!c) return SSW_OK;
+// Objects created from a context (writers, readers, banks, sharded frames) keep it alive: ssw_ctx_destroy drops the
+// owner's reference, the context is torn down when the last object has gone.  Host languages whose finalisers run in
+// no particular order (Python at interpreter exit, a Rust thread-local against values that outlive it) stay safe.
+static void ctx_free(ssw_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->plans) cudaFree(kv.second->tables);
@@ -274,6 +280,33 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+static void ctx_release(ssw_ctx* c) { if (c && c->refs.fetch_sub(1) == 1) ctx_free(c); }
+struct CtxRef {
+    ssw_ctx* c = nullptr;
+    CtxRef() = default;
+    CtxRef(const CtxRef&) = delete;
+    CtxRef& operator=(const CtxRef&) = delete;
+    CtxRef& operator=(ssw_ctx* ctx) { if (ctx) ctx->refs.fetch_add(1); ctx_release(c); c = ctx; return *this; }
+    ~CtxRef() { ctx_release(c); }
+    ssw_ctx* operator->() const { return c; }
+    operator ssw_ctx*() const { return c; }
+};
+
+extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
+    if (!c) return SSW_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);   // the caller's work is complete when the call returns, whoever frees the context
+    ctx_release(c);
+    return SSW_OK;
+}
+
+// diagnostics: per-CTA time line of the persistent pipelines (dct_pipe.cuh, trace_tile).  dev_buf: 16 x 1024 x 64 int64
+// (8 MiB) of device memory, or NULL to switch it off; launch i of a pipeline kernel writes block (i % 16).
+extern "C" int ssw_ctx_set_trace(ssw_ctx* c, void* dev_buf) {
+    if (!c) return fail(SSW_ERR_INVALID, "ctx is NULL");
+    c->trace = (long long*)dev_buf;
+    c->trace_launch = 0;
     return SSW_OK;
 }
 
@@ -568,6 +601,7 @@ static int launch_row_pipe(ssw_ctx* c, const char* name, const void* pix, float*
     a.total_tiles = (int)tiles;
     a.pdl_late = c->pdl_mode != 0;
     a.neg_zero = -0.0f;
+    a.trace = c->trace ? c->trace + (size_t)(c->trace_launch++ % 16u) * 1024 * 64 : nullptr;
     auto kernel = fast::row_pipe_kernel<K>;
     const void* key = (const void*)kernel;
     auto it = c->smem_attr.find(key);
@@ -750,6 +784,7 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
     if (tiles <= 0 || tiles > 0x7FFFFFFFll) return fail(SSW_ERR_INVALID, "tile count out of range");
     a.total_tiles = (int)tiles;
     a.pdl_late = c->pdl_mode != 0;
+    a.trace = c->trace ? c->trace + (size_t)(c->trace_launch++ % 16u) * 1024 * 64 : nullptr;
     if (!K::INVERSE && c->col_hist.want && (unsigned)batch <= c->ts_batch) {
         const bool small = c->col_hist.k <= (unsigned)kSmallMaxK;
         a.ts = c->ts;
@@ -1219,7 +1254,7 @@ static int check_cfg(const ssw_config* cfg) {
 // Writer
 // ------------------------------------------------------------------------------------------------
 struct ssw_writer {
-    ssw_ctx* ctx;
+    CtxRef ctx;
     uint32_t w, h;
     ssw_config cfg;
     int src_type;
@@ -1398,7 +1433,7 @@ extern "C" int ssw_writer_destroy(ssw_writer* wr) {
 // Reader
 // ------------------------------------------------------------------------------------------------
 struct ssw_reader {
-    ssw_ctx* ctx;
+    CtxRef ctx;
     uint32_t w, h;
     bool is_base;
     ssw_config cfg;
@@ -1521,7 +1556,7 @@ extern "C" int ssw_reader_destroy(ssw_reader* r) {
 // similarity / bank / marks
 // ------------------------------------------------------------------------------------------------
 struct ssw_bank {
-    ssw_ctx* ctx;
+    CtxRef ctx;
     float* d_marks;
     size_t n_marks, n;
 };
