@@ -28,6 +28,7 @@ extern "C" {
     pub fn ssw_ctx_destroy(ctx: *mut ssw_ctx) -> c_int;
     pub fn ssw_ctx_synchronize(ctx: *mut ssw_ctx) -> c_int;
     pub fn ssw_ctx_stream(ctx: *mut ssw_ctx) -> *mut c_void;
+    pub fn ssw_ctx_set_trace(ctx: *mut ssw_ctx, dev_buf: *mut c_void) -> c_int;
     pub fn ssw_ctx_marker(ctx: *mut ssw_ctx, marker: *mut u64) -> c_int;
     pub fn ssw_ctx_wait_marker(ctx: *mut ssw_ctx, marker: u64) -> c_int;
     pub fn ssw_ctx_last_topk_fallbacks(ctx: *mut ssw_ctx) -> c_int;

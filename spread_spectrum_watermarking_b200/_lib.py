@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libssw.so')
+LIB_PATH = os.environ.get('SSW_LIB') or os.path.join(HERE, 'csrc', 'libssw.so')   # SSW_LIB: another build of the same library (A/B, -DSSW_TRACE)
 
 SSW_OK = 0
 SSW_ERR_INVALID = -1

@@ -45,7 +45,19 @@ struct PipeArgs {
     int hist_rows, hist_cols;
     OrderConsts oc;
     int tile_rot;   // tile = (first + j*step + total - tile_rot) % total: keeps the histogram tiles off the CTAs that get one tile more
+    // collect != 0 (needs ts.hist): every tile also appends its candidates of the ordering -- coefficients at or above the
+    // selection bin -- to ts.cand straight from shared memory, which takes the topk_collect kernel (one more read of the
+    // plane) off the step.  The bin is published as ts.sel_bin[image] = bin | 0x80000000 by the last histogram tile; tiles
+    // that finish earlier wait for it (all CTAs of a persistent grid are resident and the histogram tiles come first in
+    // every CTA's sequence, so the wait cannot deadlock).  topk_rank clears the word again.
+    int collect;
 #endif
+    // Tile schedule.  Tiles [0, full_tiles) are dealt round-robin to the CTAs as whole tiles (2G columns); the remaining
+    // total_tiles - full_tiles tiles are cut into half_tiles = 2 * (total_tiles - full_tiles) half tiles (G columns), one
+    // for each of the first half_tiles CTAs, processed in a single round.  One 4K frame is 480 tiles on 148 CTAs: 3 rounds
+    // of whole tiles + 72 half tiles instead of a fourth round that keeps 36 SMs busy and 112 idle.
+    int full_tiles, half_tiles;
+    int tab_bulk;   // twiddle tables are 16-byte aligned: the producer stages them with bulk copies (else: a loop of all threads)
 };
 
 // largest divisor of n that is <= cap (rows per TMA box)
@@ -89,6 +101,19 @@ struct ColPipe {
     static constexpr int RB_HALF = box_rows(N / 2, 256), RB_FULL = box_rows(N, 256);
     static constexpr int NBOX_HALF = (N / 2) / RB_HALF, NBOX_FULL = N / RB_FULL;
     static_assert((RB_HALF * ROWB) % 128 == 0 && (RB_FULL * ROWB) % 128 == 0, "TMA boxes must start on 128-byte boundaries");
+    // half tiles (G columns = G/2 line pairs in one round): the layout of the buffer becomes [row][G floats]
+    static constexpr int GH = G_ / 2;
+    // Only the 2-team, one-CTA-per-SM shape carries the half-tile and candidate-collecting code: it has registers to spare
+    // (13 warps: up to 128 per thread), while the 4-team / two-CTA shapes run at the 72-register cap of 25-26 warps per SM
+    // and spill as soon as the kernel grows (measured: 1080-point fwd_cols 242 -> 317 us per 64-frame launch).
+    static constexpr bool HALF_OK = (G_ == 4 && TEAMS_ == 2 && MINB_ == 1) && ((RB_HALF * ROWB / 2) % 128 == 0) && ((RB_FULL * ROWB / 2) % 128 == 0);
+    static constexpr bool COLLECT_OK = (TEAMS_ == 2 && MINB_ == 1);
+    // 2 teams read and write HALF rows of the tile buffer per round (line pairs {0,1} or {2,3} of the four in a 32-byte row):
+    // rows r and r+4 would meet on the same banks (2-way conflicts, measured 21 % of the wavefronts).  The tensor maps of
+    // whole tiles therefore use the 32-byte swizzle (16-byte half of a row ^= bit 2 of the row index): lanes that walk
+    // down the rows alternate between the bank groups.  sw(row, q): line pair q of buffer row `row` -> its slot.
+    static constexpr bool SWZ = (G_ == 4 && TEAMS_ == 2);
+    template <int GG> static SSW_HD int sw(int row, int q) { return (SWZ && GG == 4) ? (q ^ ((row >> 1) & 2)) : q; }
     using Thread = ThreadState<P_>;
     static int tiles_per_image(int w, int h) { (void)h; return (w + 2 * G - 1) / (2 * G); }
 
@@ -108,11 +133,13 @@ struct ColPipe {
     static constexpr int NPH_FWD = 2 * P_::NST;       // 0: S0 load+store | 1..2(NST-1): stages 1.. | last: post
     static constexpr int NPH_INV = 2 * P_::NST + 2;   // 0: pre | 1..2NST: stages 0.. | last: output
 
-    // forward phase 0: stage 0 from the tile buffer
+    // forward phase 0: stage 0 from the tile buffer (GG: line pairs per buffer row -- G, or G/2 for a half tile)
+    template <int GG>
     static SSW_HD void fwd_stage0(const cplx* buf, cplx* fft, int rd, int c) {
         using I = StageInfo<P, 0>;
         constexpr int R = I::R, NB = I::NB;
         const int qq = c % TEAMS, jj = c / TEAMS;   // c < NC: jj < T
+        if (GG < TEAMS && qq >= GG) return;         // half tile on a 4-team CTA: two line pairs
         const int q = rd * TEAMS + qq;
         cplx* s = fft + qq * PITCH;
 #pragma unroll
@@ -122,7 +149,8 @@ struct ColPipe {
                 cplx x[R];
                 static_for<R>([&](auto rc) {
                     constexpr int r = decltype(rc)::value;
-                    x[r] = buf[semi(j + r * NB) * G + q];
+                    const int row = semi(j + r * NB);
+                    x[r] = buf[row * GG + sw<GG>(row, q)];
                 });
                 Dft<R>::run(x);
                 const int j0 = j * R, b0 = P::idx(j0);
@@ -135,32 +163,36 @@ struct ColPipe {
     }
 
     // forward last phase: post pass -> coefficient rows (natural order) in the slots of this round's pairs
+    template <int GG>
     static SSW_HD void fwd_post(cplx* buf, const cplx* fft, const cplx* t4, int rd, int c, float scale0, float scalen) {
+        constexpr int TT = GG < TEAMS ? GG : TEAMS;   // line pairs in flight per round
 #pragma unroll 2
-        for (int e = c; e < (N / 2 + 1) * TEAMS; e += NC) {
-            const int k = e / TEAMS, qq = e - k * TEAMS;
+        for (int e = c; e < (N / 2 + 1) * TT; e += NC) {
+            const int k = e / TT, qq = e - k * TT;
             const int kr = k ? N - k : 0;
             const cplx* s = fft + qq * PITCH;
             float xa, xb, ya, yb;
             dct2_post(s[P::idx(k)], s[P::idx(kr)], t4[k], xa, xb, ya, yb);
             const float sk = k ? scalen : scale0;
-            const int q = rd * TEAMS + qq;
-            buf[k * G + q] = cmul_lanes(mk(xa, xb), sk, sk);
-            if (k && kr != k) buf[kr * G + q] = cmul_lanes(mk(ya, yb), scalen, scalen);
+            const int q = rd * TT + qq;
+            buf[k * GG + sw<GG>(k, q)] = cmul_lanes(mk(xa, xb), sk, sk);
+            if (k && kr != k) buf[kr * GG + sw<GG>(kr, q)] = cmul_lanes(mk(ya, yb), scalen, scalen);
         }
     }
 
     // inverse phase 0: pre pass, coefficient rows of this round's pairs -> FFT buffers
+    template <int GG>
     static SSW_HD void inv_pre(const cplx* buf, cplx* fft, const cplx* t4, int rd, int c) {
+        constexpr int TT = GG < TEAMS ? GG : TEAMS;   // line pairs in flight per round
 #pragma unroll 2
-        for (int e = c; e < (N / 2 + 1) * TEAMS; e += NC) {
-            const int k = e / TEAMS, qq = e - k * TEAMS;
+        for (int e = c; e < (N / 2 + 1) * TT; e += NC) {
+            const int k = e / TT, qq = e - k * TT;
             const int kr = k ? N - k : 0;
-            const int q = rd * TEAMS + qq;
+            const int q = rd * TT + qq;
             cplx* s = fft + qq * PITCH;
-            const cplx pv = buf[k * G + q];
+            const cplx pv = buf[k * GG + sw<GG>(k, q)];
             cplx qv = mk(0.f, 0.f);
-            if (k) qv = buf[kr * G + q];
+            if (k) qv = buf[kr * GG + sw<GG>(kr, q)];
             cplx zk, zr;
             dct3_pre(pv.x, pv.y, qv.x, qv.y, t4[k], zk, zr);
             s[P::idx(k)] = zk;
@@ -169,30 +201,32 @@ struct ColPipe {
     }
 
     // inverse last phase: FFT buffers -> sample rows (semi-Makhoul order) in the slots of this round's pairs
+    template <int GG>
     static SSW_HD void inv_out(cplx* buf, const cplx* fft, int rd, int c, float scale) {
+        constexpr int TT = GG < TEAMS ? GG : TEAMS;   // line pairs in flight per round
 #pragma unroll 4
-        for (int e = c; e < N * TEAMS; e += NC) {
-            const int n = e / TEAMS, qq = e - n * TEAMS;
-            const int q = rd * TEAMS + qq;
+        for (int e = c; e < N * TT; e += NC) {
+            const int n = e / TT, qq = e - n * TT;
+            const int q = rd * TT + qq;
             const cplx f = fft[qq * PITCH + P::idx(semi(n))];   // row n of the buffer holds FFT position semi(n) (an involution)
-            buf[n * G + q] = cmul_lanes(f, scale, -scale);
+            buf[n * GG + sw<GG>(n, q)] = cmul_lanes(f, scale, -scale);
         }
     }
 
     // all phases of one round, as the emulation and the kernel run them; `sync_all(id)` / `sync_team()` are supplied
     // by the caller (named barriers on the device, nothing on the CPU where phases run one after the other)
-    template <int PH>
+    template <int PH, int GG = G_>
     static SSW_HD void phase(const PipeArgs& a, cplx* buf, cplx* fft, const cplx* tw, const cplx* t4, int rd, int c, Thread& th) {
         const int g = c / T, t = c - g * T;       // team mapping of the middle stages
         cplx* s = fft + g * PITCH;
         if constexpr (!INVERSE) {
-            if constexpr (PH == 0) fwd_stage0(buf, fft, rd, c);
-            else if constexpr (PH == NPH_FWD - 1) fwd_post(buf, fft, t4, rd, c, a.scale0, a.scalen);
-            else fft_phase<P, PH + 2, TW_SMEM>(s, tw, t, th.v);   // PH 1 -> fft_phase 3 (load of stage 1), ...
+            if constexpr (PH == 0) fwd_stage0<GG>(buf, fft, rd, c);
+            else if constexpr (PH == NPH_FWD - 1) fwd_post<GG>(buf, fft, t4, rd, c, a.scale0, a.scalen);
+            else { if (GG >= TEAMS || g < GG) fft_phase<P, PH + 2, TW_SMEM>(s, tw, t, th.v); }   // PH 1 -> fft_phase 3 (load of stage 1), ...
         } else {
-            if constexpr (PH == 0) inv_pre(buf, fft, t4, rd, c);
-            else if constexpr (PH == NPH_INV - 1) inv_out(buf, fft, rd, c, a.scale0);
-            else fft_phase<P, PH, TW_SMEM>(s, tw, t, th.v);       // PH 1 -> fft_phase 1 (load of stage 0), ...
+            if constexpr (PH == 0) inv_pre<GG>(buf, fft, t4, rd, c);
+            else if constexpr (PH == NPH_INV - 1) inv_out<GG>(buf, fft, rd, c, a.scale0);
+            else { if (GG >= TEAMS || g < GG) fft_phase<P, PH, TW_SMEM>(s, tw, t, th.v); }       // PH 1 -> fft_phase 1 (load of stage 0), ...
         }
     }
     static constexpr int NPHASES = INVERSE_ ? NPH_INV : NPH_FWD;
@@ -396,16 +430,40 @@ __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wa
 // the compute warps have finished, 4 %globaltimer then, 5 tiles of this CTA, 6 %smid;  tile j < 7 at 8 + 8j:
 //   +0 load issued (producer)   +1 tile landed (compute)   +2 compute done   +3 store issued (producer)
 //   +4 store has read the buffer (producer)   +5 row pipes: input buffer A released   +6 row pipes (inverse): originals landed
+#if defined(SSW_TRACE)
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void trace_at(long long* trace, int slot) { if (trace) trace[blockIdx.x * 64 + slot] = clock64(); }
 __device__ __forceinline__ void trace_tile(long long* trace, int j, int what) { if (trace && j < 7) trace[blockIdx.x * 64 + 8 + 8 * j + what] = clock64(); }
+__device__ __forceinline__ void trace_begin(long long* trace) { if (trace) { trace[blockIdx.x * 64] = (long long)global_ns(); trace[blockIdx.x * 64 + 1] = clock64(); } }
+__device__ __forceinline__ void trace_info(long long* trace, int nt) {
+    if (trace) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); trace[blockIdx.x * 64 + 5] = nt; trace[blockIdx.x * 64 + 6] = smid; }
+}
+__device__ __forceinline__ void trace_end(long long* trace) { if (trace) { trace[blockIdx.x * 64 + 3] = clock64(); trace[blockIdx.x * 64 + 4] = (long long)global_ns(); } }
+#else   // the stamps cost registers and issue slots in the tile loops (measured: fwd_cols 30.3 -> 33.9 us): diagnostic builds only (-DSSW_TRACE)
+__device__ __forceinline__ void trace_at(long long*, int) {}
+__device__ __forceinline__ void trace_tile(long long*, int, int) {}
+__device__ __forceinline__ void trace_begin(long long*) {}
+__device__ __forceinline__ void trace_info(long long*, int) {}
+__device__ __forceinline__ void trace_end(long long*) {}
+#endif
 
 struct alignas(64) TmaMap { unsigned long long v[16]; };   // CUtensorMap (128 bytes, 64-byte aligned)
 
-// map_s: sample side  (4-D: column, parity, row pair, image);  map_c: coefficient side (3-D: column, row, image)
+// ---- linear bulk copies (cp.async.bulk, no tensor map): global -> shared signals an mbarrier, shared -> global joins a bulk group
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// map_s: sample side  (4-D: column, parity, row pair, image);  map_c: coefficient side (3-D: column, row, image);
+// map_s2 / map_c2: the same views with boxes of G columns (half tiles, PipeArgs::half_tiles)
 template <class K>
 __global__ void __launch_bounds__(K::THREADS, K::MINB)
-col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaMap map_s, const __grid_constant__ TmaMap map_c) {
+col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaMap map_s, const __grid_constant__ TmaMap map_c,
+                const __grid_constant__ TmaMap map_s2, const __grid_constant__ TmaMap map_c2) {
     extern __shared__ __align__(1024) unsigned char pipe_smem[];
     constexpr int NC = K::NC;
     const int tid = threadIdx.x;
@@ -415,65 +473,93 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
     const cplx* tw = a.tw;
     const cplx* t4 = a.t4;
 
+    const unsigned bar_tab = bar_full0 + 32;
     if (tid == 0) {
         mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1);
         mbar_init(bar_ready0, 1); mbar_init(bar_ready0 + 8, 1);
+        mbar_init(bar_tab, 1);
         fence_mbar_init();
     }
-    if (a.trace && tid == 0) { a.trace[blockIdx.x * 64] = (long long)global_ns(); trace_at(a.trace, 1); }
+    if (tid == 0) trace_begin(a.trace);
     if (!a.pdl_late) pdl_trigger();
-    // twiddle tables are read-only inputs written long before the previous kernel: stage them before the dependency wait
-    if constexpr (K::TW_SMEM) {
-        cplx* d = (cplx*)(pipe_smem + K::OFF_TW);
-        for (int i = tid; i < K::P::TW_TOTAL; i += K::THREADS) d[i] = __ldg(a.tw + i);
-        tw = d;
-    }
-    if constexpr (K::T4_SMEM) {
-        cplx* d = (cplx*)(pipe_smem + K::OFF_T4);
-        for (int i = tid; i < K::N / 2 + 1; i += K::THREADS) d[i] = __ldg(a.t4 + i);
-        t4 = d;
+    // twiddle tables (read-only, written long before the previous kernel) go to shared memory: as bulk copies issued by the
+    // producer thread that land beside the first tile (a loop of all threads costs ~3 us in front of every launch: nothing
+    // of the previous grid is left to overlap it with once this CTA has found room on an SM)
+    constexpr bool TAB = K::TW_SMEM || K::T4_SMEM;
+    if constexpr (K::TW_SMEM) tw = (const cplx*)(pipe_smem + K::OFF_TW);
+    if constexpr (K::T4_SMEM) t4 = (const cplx*)(pipe_smem + K::OFF_T4);
+    if (TAB && !a.tab_bulk) {
+        if constexpr (K::TW_SMEM) { cplx* d = (cplx*)(pipe_smem + K::OFF_TW); for (int i = tid; i < K::P::TW_TOTAL; i += K::THREADS) d[i] = __ldg(a.tw + i); }
+        if constexpr (K::T4_SMEM) { cplx* d = (cplx*)(pipe_smem + K::OFF_T4); for (int i = tid; i < K::N / 2 + 1; i += K::THREADS) d[i] = __ldg(a.t4 + i); }
     }
     __syncthreads();
+    if (TAB && a.tab_bulk && tid == NC) {
+        mbar_expect_tx(bar_tab, (K::TW_SMEM ? K::TW_BYTES : 0) + (K::T4_SMEM ? K::T4_BYTES : 0));
+        if constexpr (K::TW_SMEM) bulk_load(sbase + K::OFF_TW, a.tw, K::TW_BYTES, bar_tab);
+        if constexpr (K::T4_SMEM) bulk_load(sbase + K::OFF_T4, a.t4, K::T4_BYTES, bar_tab);
+    }
     pdl_wait();
     if (tid == 0) trace_at(a.trace, 2);
 
+    // this CTA's sequence: its whole tiles (round-robin), then at most one half tile
     const int first = blockIdx.x, step = gridDim.x;
-    const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
-    if (a.trace && tid == 0) {
-        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        a.trace[blockIdx.x * 64 + 5] = nt; a.trace[blockIdx.x * 64 + 6] = smid;
-    }
-    auto tile_of = [&](int j) { int t = first + j * step - a.tile_rot; return t < 0 ? t + a.total_tiles : t; };
+    const int nt_full = first < a.full_tiles ? (a.full_tiles - first + step - 1) / step : 0;
+    const int half_idx = first - (step - a.half_tiles);       // the LAST half_tiles CTAs take one (the histogram tiles live on the first)
+    const bool has_half = K::HALF_OK && a.half_tiles > 0 && half_idx >= 0;
+    const int nt = nt_full + (has_half ? 1 : 0);
+    if (tid == 0) trace_info(a.trace, nt);
+    // j-th element of the sequence -> image, first column, half tile?
+    auto tile_at = [&](int j, int& img, int& c0) -> bool {
+        if (j < nt_full) {
+            int t = first + j * step - a.tile_rot;
+            if (t < 0) t += a.full_tiles;
+            img = t / a.tiles_per_image;
+            c0 = (t - img * a.tiles_per_image) * 2 * K::G;
+            return false;
+        }
+        const int t = a.full_tiles + (half_idx >> 1);
+        img = t / a.tiles_per_image;
+        c0 = (t - img * a.tiles_per_image) * 2 * K::G + (half_idx & 1) * K::G;
+        return true;
+    };
 
     if (tid >= NC) {
         // ===================== producer warp =====================
         if (tid == NC) {
             auto issue_load = [&](int j) {
-                const int tile = tile_of(j), b = j & 1;
-                const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
+                int img, c0;
+                const bool half = tile_at(j, img, c0) && K::HALF_OK;
+                const int b = j & 1;
                 const unsigned dst = sbase + b * K::BUF_BYTES, bar = bar_full0 + 8 * b;
+                const unsigned rowb = half ? K::ROWB / 2 : K::ROWB;
                 trace_tile(a.trace, j, 0);
-                mbar_expect_tx(bar, K::BUF_BYTES);
+                mbar_expect_tx(bar, half ? K::BUF_BYTES / 2 : K::BUF_BYTES);
                 if constexpr (!K::INVERSE) {
+                    const TmaMap* m = half ? &map_s2 : &map_s;
                     for (int par = 0; par < 2; ++par)
                         for (int bx = 0; bx < K::NBOX_HALF; ++bx)
-                            tma_load_4d(dst + (par * (K::N / 2) + bx * K::RB_HALF) * K::ROWB, &map_s, bar, c0, par, bx * K::RB_HALF, img);
+                            tma_load_4d(dst + (par * (K::N / 2) + bx * K::RB_HALF) * rowb, m, bar, c0, par, bx * K::RB_HALF, img);
                 } else {
+                    const TmaMap* m = half ? &map_c2 : &map_c;
                     for (int bx = 0; bx < K::NBOX_FULL; ++bx)
-                        tma_load_3d(dst + bx * K::RB_FULL * K::ROWB, &map_c, bar, c0, bx * K::RB_FULL, img);
+                        tma_load_3d(dst + bx * K::RB_FULL * rowb, m, bar, c0, bx * K::RB_FULL, img);
                 }
             };
             auto issue_store = [&](int j) {
-                const int tile = tile_of(j), b = j & 1;
-                const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
+                int img, c0;
+                const bool half = tile_at(j, img, c0) && K::HALF_OK;
+                const int b = j & 1;
                 const unsigned src = sbase + b * K::BUF_BYTES;
+                const unsigned rowb = half ? K::ROWB / 2 : K::ROWB;
                 if constexpr (!K::INVERSE) {
+                    const TmaMap* m = half ? &map_c2 : &map_c;
                     for (int bx = 0; bx < K::NBOX_FULL; ++bx)
-                        tma_store_3d(&map_c, src + bx * K::RB_FULL * K::ROWB, c0, bx * K::RB_FULL, img);
+                        tma_store_3d(m, src + bx * K::RB_FULL * rowb, c0, bx * K::RB_FULL, img);
                 } else {
+                    const TmaMap* m = half ? &map_s2 : &map_s;
                     for (int par = 0; par < 2; ++par)
                         for (int bx = 0; bx < K::NBOX_HALF; ++bx)
-                            tma_store_4d(&map_s, src + (par * (K::N / 2) + bx * K::RB_HALF) * K::ROWB, c0, par, bx * K::RB_HALF, img);
+                            tma_store_4d(m, src + (par * (K::N / 2) + bx * K::RB_HALF) * rowb, c0, par, bx * K::RB_HALF, img);
                 }
                 tma_commit();
             };
@@ -498,39 +584,54 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
     // ===================== compute warps =====================
     typename K::Thread th;
     const int team = tid / K::T;
+    if (TAB && a.tab_bulk) mbar_wait(bar_tab, 0);              // twiddle tables have landed
     for (int j = 0; j < nt; ++j) {
         const int b = j & 1;
         cplx* buf = (cplx*)(pipe_smem + b * K::BUF_BYTES);
+        int img, c0;
+        const bool half = tile_at(j, img, c0) && K::HALF_OK;   // (uniform over the CTA)
         mbar_wait(bar_full0 + 8 * b, (j >> 1) & 1);            // tile j has landed in BUF[b]
         if (tid == 0) trace_tile(a.trace, j, 1);
+        if (!half) {
 #pragma unroll 1
-        for (int rd = 0; rd < K::ROUNDS; ++rd) {
-            static_for<K::NPHASES>([&](auto ph) {
+            for (int rd = 0; rd < K::ROUNDS; ++rd) {
+                static_for<K::NPHASES>([&](auto ph) {
+                    constexpr int p = decltype(ph)::value;
+                    if constexpr (p == K::NPHASES - 1) { if (a.pdl_late && j + 1 == nt && rd + 1 == K::ROUNDS) pdl_trigger(); }
+                    K::template phase<p>(a, buf, fft, tw, t4, rd, tid, th);
+                    if constexpr (p + 1 < K::NPHASES) {
+                        if constexpr (K::template AllAfter<p>::value) named_sync(1, NC);
+                        else named_sync(2 + team, K::T);
+                    }
+                });
+                if (rd + 1 < K::ROUNDS) named_sync(1, NC);     // FFT buffers are free for the next round
+            }
+        } else if constexpr (K::HALF_OK) {
+            static_for<K::NPHASES>([&](auto ph) {              // one round over the G/2 line pairs of a half tile
                 constexpr int p = decltype(ph)::value;
-                if constexpr (p == K::NPHASES - 1) { if (a.pdl_late && j + 1 == nt && rd + 1 == K::ROUNDS) pdl_trigger(); }
-                K::template phase<p>(a, buf, fft, tw, t4, rd, tid, th);
+                if constexpr (p == K::NPHASES - 1) { if (a.pdl_late && j + 1 == nt) pdl_trigger(); }
+                K::template phase<p, K::GH>(a, buf, fft, tw, t4, 0, tid, th);
                 if constexpr (p + 1 < K::NPHASES) {
                     if constexpr (K::template AllAfter<p>::value) named_sync(1, NC);
                     else named_sync(2 + team, K::T);
                 }
             });
-            if (rd + 1 < K::ROUNDS) named_sync(1, NC);         // FFT buffers are free for the next round
         }
         if constexpr (!K::INVERSE) {
             if (a.ts.hist) {
-                const int tile = tile_of(j), img = tile / a.tiles_per_image;
-                const int c0 = (tile - img * a.tiles_per_image) * 2 * K::G;
+                const int cols = (K::HALF_OK && half) ? K::G : 2 * K::G;   // floats per buffer row
+                unsigned* sh = (unsigned*)fft;                 // 4096 bins + scratch, free once the post passes are done
+                static_assert(K::FFT_BYTES >= (kHistBins + 40) * 4, "the FFT buffers double as the histogram");
                 if (c0 < a.hist_cols) {                        // (uniform over the CTA)
-                    static_assert(K::FFT_BYTES >= (kHistBins + 40) * 4, "the FFT buffers double as the histogram");
-                    unsigned* sh = (unsigned*)fft;             // 4096 bins + scratch, free once the post passes are done
                     named_sync(1, NC);                         // the post pass of every team has written its coefficient rows
                     for (int i = tid; i < kHistBins; i += NC) sh[i] = 0u;
                     named_sync(1, NC);
-                    const float* cf = (const float*)buf;       // row k of the tile: 2G adjacent columns starting at c0
-                    for (int e = tid; e < a.hist_rows * 2 * K::G; e += NC) {
-                        const int r = e / (2 * K::G), cc = e - r * (2 * K::G);
+                    const float* cf = (const float*)buf;       // row k of the tile: `cols` adjacent columns starting at c0
+                    for (int e = tid; e < a.hist_rows * cols; e += NC) {
+                        const int r = e / cols, cc = e - r * cols;
                         const unsigned pidx = (unsigned)r * (unsigned)a.w + (unsigned)(c0 + cc);
-                        if (pidx && c0 + cc < a.hist_cols) atomicAdd(sh + (order_key(cf[e], pidx, a.oc) >> (32 - kHistBits)), 1u);
+                        const int ep = (K::SWZ && !half) ? (e ^ (r & 4)) : e;   // swizzled whole tiles: the 16-byte halves of rows 4..7 (mod 8) are swapped
+                        if (pidx && c0 + cc < a.hist_cols) atomicAdd(sh + (order_key(cf[ep], pidx, a.oc) >> (32 - kHistBits)), 1u);
                     }
                     named_sync(1, NC);
                     unsigned* gh = a.ts.hist + (size_t)img * kHistBins;
@@ -546,26 +647,58 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
                         for (int i = tid; i < kHistBins; i += NC) { sh[i] = __ldcg(gh + i); gh[i] = 0u; }
                         named_sync(1, NC);
                         const unsigned bsel = find_kth_bin_team(sh, a.hist_k, tid, NC, 1, sh + kHistBins);
-                        if (tid == 0) { a.ts.sel_bin[img] = bsel; a.ts.ticket[img] = 0u; }
+                        if (tid == 0) {
+                            a.ts.ticket[img] = 0u;
+                            __threadfence();
+                            *(volatile unsigned*)(a.ts.sel_bin + img) = a.collect ? (bsel | 0x80000000u) : bsel;
+                        }
                     }
                     named_sync(1, NC);                         // the FFT buffers go back to the next tile
+                }
+                if (K::COLLECT_OK && a.collect) {
+                    named_sync(1, NC);                         // every team's coefficient rows are in BUF[b]; the FFT buffers are free
+                    if (tid == 0) {
+                        unsigned v = 0;
+                        for (unsigned spin = 0; ; ++spin) {
+                            v = *(volatile const unsigned*)(a.ts.sel_bin + img);
+                            if (v & 0x80000000u) break;
+                            if (spin > (1u << 22)) __trap();   // protocol error: report a launch failure instead of hanging
+                            __nanosleep(40);
+                        }
+                        sh[0] = v & 0x7FFFFFFFu;
+                    }
+                    named_sync(1, NC);
+                    const unsigned bin_sel = sh[0];
+                    unsigned* count = a.ts.cand_count + img;
+                    unsigned long long* cand = a.ts.cand + (size_t)img * kTopkCap;
+                    // Energy ordering: key = bits(c*c) | 2^31, so "bin(key) >= bin_sel" is "c*c >= thr" for the float whose bits are
+                    // (bin_sel - 2^11) << 20 -- two instructions per coefficient; the few that pass (and NaNs) take the exact path
+                    const float thr = bin_sel > (1u << (kHistBits - 1)) ? __uint_as_float((bin_sel - (1u << (kHistBits - 1))) << (32 - kHistBits)) : 0.f;
+                    const float4* c4 = (const float4*)buf;
+                    const int n4 = K::N * cols / 4;
+                    const int shift = half ? (K::G == 4 ? 2 : 1) : (K::G == 4 ? 3 : 2);   // log2(cols), G = 2 or 4
+#pragma unroll 4
+                    for (int e = tid; e < n4; e += NC) {
+                        const float4 v = c4[e];
+                        const bool lo = (v.x * v.x < thr) & (v.y * v.y < thr) & (v.z * v.z < thr) & (v.w * v.w < thr);
+                        if (!lo) {
+                            const int f = e * 4, r = f >> shift, cp = f - (r << shift);
+                            const int cc = (K::SWZ && !half) ? (cp ^ (r & 4)) : cp;   // (un-swizzle: see the histogram above)
+                            const unsigned p0 = (unsigned)r * (unsigned)a.w + (unsigned)(c0 + cc);
+                            const float ev[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (p0 + u && c0 + cc + u < a.w) topk_push(order_key(ev[u], p0 + u, a.oc), p0 + u, bin_sel, count, cand);
+                        }
+                    }
                 }
             }
         }
         fence_proxy_async();                                   // generic-proxy writes of BUF[b] -> visible to the TMA store
-        named_sync(1, NC);                                     // (also: FFT buffers free for the next tile)
+        named_sync(1, NC);                                     // (also: FFT buffers free for the next tile, candidates read)
         if (tid == 0) { trace_tile(a.trace, j, 2); mbar_arrive(bar_ready0 + 8 * b); }
     }
-    if (a.trace && tid == 0) { trace_at(a.trace, 3); a.trace[blockIdx.x * 64 + 4] = (long long)global_ns(); }
-}
-
-// ---- linear bulk copies (cp.async.bulk, no tensor map): global -> shared signals an mbarrier, shared -> global joins a bulk group
-__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+    if (tid == 0) trace_end(a.trace);
 }
 
 // mbarriers (8 bytes each, at OFF_BAR): fullA, freeA; inverse also fullB (originals landed) and readyB (output bytes written)
@@ -583,7 +716,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
         mbar_init(bar_readyB, NC);    // inverse: every compute thread has written (and fenced) its part of B
         fence_mbar_init();
     }
-    if (a.trace && tid == 0) { a.trace[blockIdx.x * 64] = (long long)global_ns(); trace_at(a.trace, 1); }
+    if (tid == 0) trace_begin(a.trace);
     if (!a.pdl_late) pdl_trigger();
     __syncthreads();
     pdl_wait();
@@ -591,10 +724,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
 
     const int first = blockIdx.x, step = gridDim.x;
     const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
-    if (a.trace && tid == 0) {
-        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        a.trace[blockIdx.x * 64 + 5] = nt; a.trace[blockIdx.x * 64 + 6] = smid;
-    }
+    if (tid == 0) trace_info(a.trace, nt);
     const size_t frame_px = (size_t)a.w * a.h;
     auto px_of = [&](int j) {   // first pixel of tile j of this CTA, counted over the whole batch
         const int tile = first + j * step, img = tile / a.tiles_per_image;
@@ -665,7 +795,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
         named_sync(1 + team, K::T);                            // the team has read its FFT buffer: the next tile may overwrite it
         if (tid == 0) trace_tile(a.trace, j, 2);
     }
-    if (a.trace && tid == 0) { trace_at(a.trace, 3); a.trace[blockIdx.x * 64 + 4] = (long long)global_ns(); }
+    if (tid == 0) trace_end(a.trace);
 }
 #endif
 

@@ -283,6 +283,46 @@ similarity_bank_warp_kernel(const float* __restrict__ bank, size_t n_marks, unsi
     const float rden = __fsqrt_rn(__ldg(den + e));
     const unsigned n4 = n >> 2;
     const float4* ex4 = (const float4*)ex;
+    if (n4 <= 8u * 32u && (n & 3u) == 0u && ((((size_t)bank) & 15) == 0)) {
+        // rows of up to 1024 values (every row 16-byte aligned): the loads of the warp's NEXT row are issued before the
+        // current row is reduced, so the memory pipe never drains between rows (two register sets, loop unrolled by two)
+        auto load_row = [&](size_t m, float4* v) {
+            const float4* r4 = (const float4*)(bank + m * n);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned j = 32 * u + lane;
+                v[u] = j < n4 ? ld_stream4(r4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto reduce_row = [&](size_t m, const float4* v) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned j = 32 * u + lane;
+                const float4 x = j < n4 ? ex4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                a0 = fmaf(x.x, v[u].x, a0); a1 = fmaf(x.y, v[u].y, a1); a2 = fmaf(x.z, v[u].z, a2); a3 = fmaf(x.w, v[u].w, a3);
+            }
+            float sum = (a0 + a1) + (a2 + a3);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+            if (lane == 0) out[(long long)e * out_stride + m] = __fdiv_rn(sum, rden);
+        };
+        float4 va[8], vb[8];
+        size_t m = warp0;
+        if (m < n_marks) load_row(m, va);
+        while (m < n_marks) {
+            size_t mn = m + nwarps;
+            if (mn < n_marks) load_row(mn, vb);
+            reduce_row(m, va);
+            m = mn;
+            if (m >= n_marks) break;
+            mn = m + nwarps;
+            if (mn < n_marks) load_row(mn, va);
+            reduce_row(m, vb);
+            m = mn;
+        }
+        return;
+    }
     for (size_t m = warp0; m < n_marks; m += nwarps) {
         const float* row = bank + m * n;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;

@@ -413,6 +413,7 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
         if (bad) atomicAdd(ts.overflow, 1u);
         ts.cand_count[img] = 0;
         ts.ticket[img] = 0;
+        ts.sel_bin[img] = 0;   // clears the "bin published" flag of the collecting column pipeline (dct_pipe.cuh, PipeArgs::collect)
     }
     if (ap.mode == 2 && ap.sim) {
         __threadfence();   // the other CTAs' extracted values (their fence + ticket precede ours)

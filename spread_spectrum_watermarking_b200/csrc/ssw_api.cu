@@ -96,7 +96,12 @@ struct ssw_ctx {
     struct { bool active = false; int seg_shift = -1, chunk_shift = 0, ranks = 1, lines = 0; } seg;  // ssw_lines_forward_seg_dev
     // fused pipelines: ask the forward column pipeline for the low-frequency-block histogram of the ordering that
     // follows (want), learn whether a pipeline produced it (done) -- see run_topk_fast
-    struct { bool want = false, done = false; unsigned k = 0; int ordering = 0; } col_hist;
+    struct { bool want = false, done = false, collected = false; unsigned k = 0; int ordering = 0; } col_hist;
+    bool col_split = true;                 // SSW_COL_SPLIT=0: no half tiles in the column pipelines (PipeArgs::half_tiles)
+    bool col_collect = false;              // SSW_COL_COLLECT=1: the forward column pipeline appends the candidates of the ordering from its
+                                           // tiles (PipeArgs::collect) instead of the topk_collect kernel.  Measured on B200 (C2): the kernel
+                                           // it removes costs ~6 us inside the programmatic launch chain, the wait for the selection bin and
+                                           // the extra pass over each tile cost the column pipeline ~7 us: 0.214 -> 0.222 ms/step.  Opt-in.
     bool lowrank = false;                  // SSW_LOWRANK=1: fused embed adds the low-rank update of the k modified coefficients to the
                                            // original frame (lowrank.cuh) instead of inverting the whole plane.  Measured slower on
                                            // B200 (C2: 123 vs 68 us, profiles/r2_lowrank_tensor_core.md), so it is opt-in.
@@ -236,6 +241,8 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
+    if (const char* s = getenv("SSW_COL_SPLIT")) c->col_split = atoi(s) != 0;
+    if (const char* s = getenv("SSW_COL_COLLECT")) c->col_collect = atoi(s) != 0;
     if (const char* s = getenv("SSW_LOWRANK")) c->lowrank = atoi(s) != 0;
     if (const char* s = getenv("SSW_LOWRANK_MMA")) c->lowrank_mma = atoi(s) != 0;
     *out = c.release();
@@ -305,6 +312,9 @@ extern "C" int ssw_ctx_destroy(ssw_ctx* c) {
 // (8 MiB) of device memory, or NULL to switch it off; launch i of a pipeline kernel writes block (i % 16).
 extern "C" int ssw_ctx_set_trace(ssw_ctx* c, void* dev_buf) {
     if (!c) return fail(SSW_ERR_INVALID, "ctx is NULL");
+#if !defined(SSW_TRACE)
+    if (dev_buf) return fail(SSW_ERR_UNSUPPORTED, "this libssw was built without -DSSW_TRACE (tools/build_tmp.sh trace -DSSW_TRACE)");
+#endif
     c->trace = (long long*)dev_buf;
     c->trace_launch = 0;
     return SSW_OK;
@@ -729,9 +739,12 @@ static OrderConsts make_order(int ordering, int w, int h);
 // tensor maps of a coefficient plane [batch][h][w] f32 for tiles of 2*g columns:
 //   sample side      4-D (column, row parity, row pair, image)  -- even rows / odd rows as separate boxes (Makhoul split)
 //   coefficient side 3-D (column, row, image)
-static int tma_maps_for(ssw_ctx* c, const float* plane, int w, int h, int batch, int g, int rb_half, int rb_full,
+// swz: 32-byte swizzle (boxes of exactly 8 floats): the 16-byte halves of a buffer row are swapped in rows 4..7 (mod 8)
+static int tma_maps_for(ssw_ctx* c, const float* plane, int w, int h, int batch, int g, int rb_half, int rb_full, bool swz,
                         const std::pair<fast::TmaMap, fast::TmaMap>** out) {
-    const ssw_ctx::MapKey key{plane, w, h, batch, g};
+    if (swz && g != 4) return fail(SSW_ERR_INVALID, "the 32-byte swizzle needs boxes of 8 columns");
+    const ssw_ctx::MapKey key{plane, w, h, batch, g + (swz ? 100 : 0)};
+    const CUtensorMapSwizzle swizzle = swz ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     auto it = c->tma_maps.find(key);
     if (it != c->tma_maps.end()) { *out = &it->second; return SSW_OK; }
     if (!c->encode_tiled) {
@@ -753,7 +766,7 @@ static int tma_maps_for(ssw_ctx* c, const float* plane, int w, int h, int batch,
         const cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)w * 8, (cuuint64_t)w * h * 4};
         const cuuint32_t box[4] = {(cuuint32_t)(2 * g), 1, (cuuint32_t)rb_half, 1};
         const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)plane, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SSW_ERR_CUDA, "cuTensorMapEncodeTiled (4-D sample view) failed: " + std::to_string((int)r));
         std::memcpy(&maps.first, &m, sizeof(m));
     }
@@ -763,7 +776,7 @@ static int tma_maps_for(ssw_ctx* c, const float* plane, int w, int h, int batch,
         const cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
         const cuuint32_t box[3] = {(cuuint32_t)(2 * g), (cuuint32_t)rb_full, 1};
         const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)plane, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SSW_ERR_CUDA, "cuTensorMapEncodeTiled (3-D coefficient view) failed: " + std::to_string((int)r));
         std::memcpy(&maps.second, &m, sizeof(m));
     }
@@ -795,7 +808,9 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
         c->col_hist.done = true;
     }
     const std::pair<fast::TmaMap, fast::TmaMap>* maps;
-    CKS(tma_maps_for(c, d_plane, w, h, batch, K::G, K::RB_HALF, K::RB_FULL, &maps));
+    CKS(tma_maps_for(c, d_plane, w, h, batch, K::G, K::RB_HALF, K::RB_FULL, K::SWZ, &maps));
+    const std::pair<fast::TmaMap, fast::TmaMap>* maps2 = maps;   // boxes of G columns for half tiles
+    if (K::HALF_OK) CKS(tma_maps_for(c, d_plane, w, h, batch, K::G / 2, K::RB_HALF, K::RB_FULL, false, &maps2));
     auto kernel = fast::col_pipe_kernel<K>;
     const void* key = (const void*)kernel;
     auto it = c->smem_attr.find(key);
@@ -807,14 +822,25 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
     }
     const long long slots = (long long)it->second * c->sm_count;
     const unsigned grid = (unsigned)std::min<long long>(tiles, slots);
-    if (!K::INVERSE && a.ts.hist && batch == 1) {
-        // one frame: `rot` CTAs get one tile more than the others and finish last -- keep the histogram tiles off them
-        const long long rot = tiles % grid, nh = (a.hist_cols + 2 * K::G - 1) / (2 * K::G);
-        if (rot + nh <= grid) a.tile_rot = (int)rot;
+    // schedule: whole rounds of whole tiles; a remainder that would keep less than half of the CTAs busy for one more
+    // round is cut into half tiles, one per CTA (single frames: 480 tiles on 148 CTAs = 3 rounds + 72 half tiles)
+    a.full_tiles = a.total_tiles; a.half_tiles = 0;
+    const long long rounds = tiles / grid, rem = tiles % grid;
+    if (K::HALF_OK && c->col_split && batch == 1 && rounds >= 1 && rem > 0 && 2 * rem <= (long long)grid && (w % (2 * K::G)) == 0) {
+        a.full_tiles = (int)(rounds * grid);
+        a.half_tiles = (int)(2 * rem);
     }
+    if (!K::INVERSE && a.ts.hist && batch == 1 && a.half_tiles == 0) {
+        // one frame: `rot` CTAs get one tile more than the others and finish last -- keep the histogram tiles off them
+        const long long nh = (a.hist_cols + 2 * K::G - 1) / (2 * K::G);
+        if (rem + nh <= grid) a.tile_rot = (int)rem;
+    }
+    // the candidates of the ordering straight from the tiles (Energy ordering; see PipeArgs::collect)
+    if (K::COLLECT_OK && !K::INVERSE && a.ts.hist && c->col_collect && !c->lowrank && c->col_hist.ordering == 0 && batch == 1) { a.collect = 1; c->col_hist.collected = true; }
+    a.tab_bulk = aligned(a.tw, 16) && aligned(a.t4, 16);
     {
         KScope ks(c, name);
-        launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a, maps->first, maps->second);
+        launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a, maps->first, maps->second, maps2->first, maps2->second);
     }
     CK(cudaGetLastError());
     return SSW_OK;
@@ -829,9 +855,13 @@ static int pipe_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_
     auto run = [&](auto k) { using K = decltype(k); rc = launch_col_pipe<K>(c, name, w, h, batch, d_plane, scale0, scalen); *done = true; };
     if (h == 2160) {
         using P = fast::Plan2160;
+        // SSW_COL_PIPE=1 (default): 4 teams, one round per tile (800 threads at the 72-register cap of 25 warps per SM);
+        // =2: 2 teams x 2 rounds per tile (416 threads, registers to spare) with the split schedule (half tiles) and 32-byte
+        // swizzled tile buffers.  Measured on one 4K frame (profiles/r2_col_pipeline_variants.md): the kernels are equal
+        // alone (fwd 29.2 / 29.5 us, inv 31.2 / 31.2 us), the step is 0.214 / 0.217 ms.
         if (c->col_pipe == 2) { if (inverse) run(fast::ColPipe<P, 4, 2, true>{}); else run(fast::ColPipe<P, 4, 2, false>{}); }
         else if (c->col_pipe == 3) { if (inverse) run(fast::ColPipe<P, 2, 2, true, 2>{}); else run(fast::ColPipe<P, 2, 2, false, 2>{}); }
-        else { if (inverse) run(fast::ColPipe<P, 4, 4, true>{}); else run(fast::ColPipe<P, 4, 4, false>{}); }
+        else { if (inverse) run(fast::ColPipe<P, 4, 4, true>{}); else run(fast::ColPipe<P, 4, 4, false>{}); }   // SSW_COL_PIPE=1
     } else if (h == 1080) {
         using P = fast::Plan1080;
         if (c->col_pipe == 2) { if (inverse) run(fast::ColPipe<P, 4, 4, true, 1>{}); else run(fast::ColPipe<P, 4, 4, false, 1>{}); }
@@ -1051,6 +1081,7 @@ static int ensure_topk_scratch(ssw_ctx* c, unsigned batch) {
     CK(cudaMalloc(&c->ts.overflow, sizeof(unsigned)));
     CK(cudaMalloc(&c->ts.maxrow, b * sizeof(unsigned)));
     CK(cudaMemset(c->ts.maxrow, 0, b * sizeof(unsigned)));
+    CK(cudaMemset(c->ts.sel_bin, 0, b * sizeof(unsigned)));   // bit 31 = "bin published" (collecting column pipeline)
     CK(cudaMemset(c->ts.hist, 0, (size_t)b * kHistBins * sizeof(unsigned)));
     CK(cudaMemset(c->ts.ticket, 0, b * sizeof(unsigned)));
     CK(cudaMemset(c->ts.cand_count, 0, b * sizeof(unsigned)));
@@ -1076,7 +1107,7 @@ static OrderConsts make_order(int ordering, int w, int h) {
 // full_hist = true : selection bin from a histogram of the whole plane (two passes) -- the repair path.
 // ap: what the ranking kernel does with (rank, index) beyond storing the index list (embed / extract [+ score]).
 static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsigned batch, int ordering,
-                         unsigned k, unsigned* d_idx, long long idx_stride, bool full_hist, bool hist_ready = false,
+                         unsigned k, unsigned* d_idx, long long idx_stride, bool full_hist, int hist_ready = 0,
                          const TopkApply* ap = nullptr, cudaEvent_t join_before_apply = nullptr) {
     CKS(ensure_topk_scratch(c, batch));
     const unsigned n = (unsigned)((size_t)w * h);
@@ -1098,7 +1129,9 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
             KScope ks(c, "topk_block_bin");
             launch_pdl(c, topk_block_bin_kernel, dim3(nb), kBinThreads, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
-        { KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts); }
+        if (hist_ready < 2) {   // 2: the forward column pipeline has appended the candidates as well (PipeArgs::collect)
+            KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts);
+        }
         CK(cudaGetLastError());
     }
     if (join_before_apply) CK(cudaStreamWaitEvent(c->stream, join_before_apply, 0));   // extract: the derived planes
@@ -1111,7 +1144,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
-        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap; ts.maxrow += b0;
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap; ts.maxrow += b0;
         TopkApply a;
         std::memset(&a, 0, sizeof(a));
         if (ap) {
@@ -1757,10 +1790,10 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
         // the forward column pipeline leaves the low-frequency-block histogram of every frame for the ordering
         // (one frame per launch: the in-pipeline histogram takes a kernel off the latency chain; on batched launches it
         // was measured slower than the separate topk_block_bin kernel, whose cost is shared by the whole batch)
-        c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = false;
+        c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = c->col_hist.collected = false;
         c->col_hist.k = (unsigned)k; c->col_hist.ordering = cfg->ordering;
         rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
-        const bool hist_ready = c->col_hist.done;
+        const int hist_ready = c->col_hist.done ? (c->col_hist.collected ? 2 : 1) : 0;
         c->col_hist.want = false;
         const bool lowrank = c->lowrank && k > 0 && (w % 4u) == 0 && w <= 65535u && h <= 65535u && aligned(src, 4) && aligned(out_rgb, 4) &&
                              ((np * 3) % 4) == 0;
@@ -1847,13 +1880,13 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         ap.out = extracted + (size_t)b0 * n; ap.out_stride = (long long)n;
         ap.sim = (sim && !c->sim_exact) ? sim + b0 : nullptr;
         auto base_forward = [&]() -> int {
-            c->col_hist.want = !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = false;
+            c->col_hist.want = !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = c->col_hist.collected = false;
             c->col_hist.k = (unsigned)n; c->col_hist.ordering = cfg->ordering;
             const int r = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
             c->col_hist.want = false;
             return r;
         };
-        bool hist_ready = false;
+        int hist_ready = 0;
         if (c->overlap_topk && !c->profiling) {   // per-kernel profiling times every kernel alone, on one stream
             // fork: the derived frame's forward transform runs on the side stream beside the base frame's forward
             // transform and the candidate collection; CTAs of the two transforms fill each other's partial waves.
@@ -1865,11 +1898,11 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
             rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
             c->stream = main_stream;
             CK(cudaEventRecord(c->ev_join, c->aux));
-            if (rc == SSW_OK) { rc = base_forward(); hist_ready = c->col_hist.done; }
+            if (rc == SSW_OK) { rc = base_forward(); hist_ready = c->col_hist.done ? (c->col_hist.collected ? 2 : 1) : 0; }
             if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist, hist_ready, &ap, c->ev_join);
             else CK(cudaStreamWaitEvent(main_stream, c->ev_join, 0));   // error paths: keep the streams ordered
         } else {
-            rc = base_forward(); hist_ready = c->col_hist.done;
+            rc = base_forward(); hist_ready = c->col_hist.done ? (c->col_hist.collected ? 2 : 1) : 0;
             if (rc == SSW_OK) rc = run_forward(c, PIX_RGB8, derived_rgb + (size_t)b0 * np * 3, w, h, nb, pd, SSW_DCT2);
             if (rc == SSW_OK) rc = run_topk_fast(c, pb, w, h, nb, cfg->ordering, (unsigned)n, d_idx, (long long)n, c->topk_full_hist, hist_ready, &ap);
         }

@@ -77,22 +77,50 @@ FastArgs base_args(int w, int h) {
 // persistent TMA column pipelines (dct_pipe.cuh): memcpy stands in for the tensor-map copies -- the sample side of a
 // tile is [even rows | odd rows] (the 4-D parity view), the coefficient side the rows in natural order; columns past
 // the frame read as zero and are not written back (TMA out-of-bounds rules)
+// grid > 0: the kernel's split schedule for `grid` CTAs -- whole rounds of whole tiles, the remainder as half tiles (G
+// columns, one round over G/2 line pairs, buffer layout [row][G floats]) when it would occupy at most half of the CTAs
 template <class K>
-void emulate_col_pipe(PipeArgs a, float* plane, const cplx* tw, const cplx* t4) {
+void emulate_col_pipe(PipeArgs a, float* plane, const cplx* tw, const cplx* t4, int grid = 0) {
     constexpr int N = K::N, G = K::G;
     std::vector<cplx> buf((size_t)N * G), fft((size_t)K::TEAMS * K::PITCH + 8);
     std::vector<typename K::Thread> th(K::NC);
     a.tiles_per_image = K::tiles_per_image(a.w, a.h);
     a.total_tiles = a.tiles_per_image * a.batch;
     auto sample_row = [](int n) { return n < N / 2 ? 2 * n : 2 * (n - N / 2) + 1; };   // buffer row -> frame row (sample side)
-    for (int tile = 0; tile < a.total_tiles; ++tile) {
+    int full_tiles = a.total_tiles;
+    if constexpr (K::HALF_OK) {
+        if (grid > 0 && a.batch == 1) {
+            const int rounds = a.total_tiles / grid, rem = a.total_tiles % grid;
+            if (rounds >= 1 && rem > 0 && 2 * rem <= grid && a.w % (2 * G) == 0) full_tiles = rounds * grid;
+        }
+        for (int hh = 0; hh < 2 * (a.total_tiles - full_tiles); ++hh) {
+            constexpr int GH = K::GH;
+            const int tile = full_tiles + (hh >> 1), img = tile / a.tiles_per_image;
+            const int c0 = (tile - img * a.tiles_per_image) * 2 * G + (hh & 1) * G;
+            float* pl = plane + (size_t)img * a.w * a.h;
+            for (int n = 0; n < N; ++n) {
+                const int r = K::INVERSE ? n : sample_row(n);
+                for (int x = 0; x < G; ++x) ((float*)&buf[(size_t)n * GH])[x] = (c0 + x < a.w) ? pl[(size_t)r * a.w + c0 + x] : 0.f;
+            }
+            static_for<K::NPHASES>([&](auto ph) {
+                constexpr int p = decltype(ph)::value;
+                for (int c = 0; c < K::NC; ++c) K::template phase<p, GH>(a, buf.data(), fft.data(), tw, t4, 0, c, th[c]);
+            });
+            for (int n = 0; n < N; ++n) {
+                const int r = K::INVERSE ? sample_row(n) : n;
+                for (int x = 0; x < G; ++x)
+                    if (c0 + x < a.w) pl[(size_t)r * a.w + c0 + x] = ((float*)&buf[(size_t)n * GH])[x];
+            }
+        }
+    }
+    for (int tile = 0; tile < full_tiles; ++tile) {
         const int img = tile / a.tiles_per_image, c0 = (tile - img * a.tiles_per_image) * 2 * G;
         float* pl = plane + (size_t)img * a.w * a.h;
         for (int n = 0; n < N; ++n) {
             const int r = K::INVERSE ? n : sample_row(n);
             for (int x = 0; x < 2 * G; ++x) {
                 const float v = (c0 + x < a.w) ? pl[(size_t)r * a.w + c0 + x] : 0.f;
-                ((float*)&buf[(size_t)n * G])[x] = v;
+                ((float*)&buf[(size_t)n * G])[K::SWZ ? (x ^ (n & 4)) : x] = v;   // 32-byte swizzle of the tensor map
             }
         }
         for (int rd = 0; rd < K::ROUNDS; ++rd)
@@ -103,7 +131,7 @@ void emulate_col_pipe(PipeArgs a, float* plane, const cplx* tw, const cplx* t4) 
         for (int n = 0; n < N; ++n) {
             const int r = K::INVERSE ? sample_row(n) : n;
             for (int x = 0; x < 2 * G; ++x)
-                if (c0 + x < a.w) pl[(size_t)r * a.w + c0 + x] = ((float*)&buf[(size_t)n * G])[x];
+                if (c0 + x < a.w) pl[(size_t)r * a.w + c0 + x] = ((float*)&buf[(size_t)n * G])[K::SWZ ? (x ^ (n & 4)) : x];
         }
     }
 }
@@ -159,7 +187,8 @@ int emul_row_pipe(int inverse, const unsigned char* pix, int w, int h, int batch
     return ran ? 0 : -2;
 }
 
-// variant: 1 = 4 pairs x 4 teams, 2 = 4 pairs x 2 teams (2 rounds), 3 = 2 pairs x 2 teams
+// variant: 1 = 4 pairs x 4 teams, 2 = 4 pairs x 2 teams (2 rounds), 3 = 2 pairs x 2 teams, 4 = variant 2 with the split
+// schedule of a 2-CTA grid (remainder tiles as half tiles; batch 1 only)
 int emul_col_pipe(int variant, int inverse, int w, int h, int batch, float* plane, float scale0, float scalen) {
     if ((w % 4) || (h & 1)) return -2;
     bool ran = false;
@@ -171,13 +200,13 @@ int emul_col_pipe(int variant, int inverse, int w, int h, int batch, float* plan
         a.w = w; a.h = h; a.batch = batch; a.scale0 = scale0; a.scalen = scalen;
         const cplx* tw = (const cplx*)tb.tw.data();
         const cplx* t4 = (const cplx*)tb.t4.data();
-        auto run = [&](auto k) { emulate_col_pipe<decltype(k)>(a, plane, tw, t4); ran = true; };
+        auto run = [&](auto k) { emulate_col_pipe<decltype(k)>(a, plane, tw, t4, variant >= 4 ? 2 : 0); ran = true; };
         if constexpr (ColPipe<P, 4, 4, false>::FITS && (box_rows(P::N / 2, 256) * 16) % 128 == 0) {
             if (variant == 3) { if (inverse) run(ColPipe<P, 2, 2, true, 2>{}); else run(ColPipe<P, 2, 2, false, 2>{}); return; }
         }
         if constexpr (ColPipe<P, 4, 4, false>::FITS) {
-            if (variant == 2) { if (inverse) run(ColPipe<P, 4, 2, true>{}); else run(ColPipe<P, 4, 2, false>{}); }
-            else { if (inverse) run(ColPipe<P, 4, 4, true>{}); else run(ColPipe<P, 4, 4, false>{}); }
+            if (variant == 2 || variant == 4) { if (inverse) run(ColPipe<P, 4, 2, true>{}); else run(ColPipe<P, 4, 2, false>{}); }
+            else { if (inverse) run(ColPipe<P, 4, 4, true>{}); else run(ColPipe<P, 4, 4, false>{}); }   // 1, and 5 = 1 with the split schedule
         }
     }) && ran ? 0 : -2;
 }

@@ -227,6 +227,21 @@ def test_col_pipe_matches_col_pass(emul, n, variant, inverse):
     assert np.array_equal(ref, got)
 
 
+@pytest.mark.parametrize('variant', [4])   # the 2-team pipeline: one round per half tile
+@pytest.mark.parametrize('inverse', [0, 1])
+def test_col_pipe_half_tiles_match_col_pass(emul, inverse, variant):
+    """split schedule of the column pipelines (PipeArgs::half_tiles): 3 tiles on a 2-CTA grid = one round of whole tiles + the
+    third tile as two half tiles (4 columns, one round over 2 line pairs, buffer rows of 4 floats) -- bit-identical planes"""
+    w, n = 24, 2160
+    rng = np.random.default_rng(77 + inverse)
+    a = (rng.random((1, n, w)).astype(np.float32) - 0.5) * 3.0
+    ref, got = a.copy(), a.copy()
+    assert emul.emul_fast_col(inverse, w, n, 1, ptr(ref), f32(1.0 if inverse else 0.7), f32(1.0 if inverse else 1.3)) == 0
+    assert emul.emul_col_pipe(variant, inverse, w, n, 1, ptr(got), f32(1.0 if inverse else 0.7), f32(1.0 if inverse else 1.3)) == 0
+    assert np.abs(ref).max() > 1.0
+    assert np.array_equal(ref, got)
+
+
 @pytest.mark.parametrize('n,h', [(3840, 4), (1920, 8), (1080, 4), (2160, 2), (640, 8), (1280, 4), (720, 4), (2560, 2), (1440, 4)])
 def test_row_pipe_matches_row_kernels(emul, so, n, h):
     """persistent bulk-copy row pipelines (csrc/dct_pipe.cuh RowPipe), phases run on the CPU with memcpy standing in for the

@@ -455,6 +455,53 @@ def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
         cg.close(); cf.close()
 
 
+@pytest.mark.parametrize('env', [
+    {'SSW_COL_PIPE': '1'},                                               # 4 teams (default)
+    {'SSW_COL_PIPE': '2'},                                               # 2 teams, half tiles, 32-byte swizzled tile buffers
+    {'SSW_COL_PIPE': '2', 'SSW_COL_SPLIT': '0'},
+    {'SSW_COL_PIPE': '2', 'SSW_COL_COLLECT': '1'},                        # candidates appended by the column pipeline
+    {'SSW_COL_PIPE': '3'},                                               # 4-column tiles, two CTAs per SM
+    {'SSW_COL_PIPE': '1', 'SSW_COL_HIST': '0'},                           # selection bin from topk_block_bin
+])
+def test_pipeline_variants_are_bit_identical(wm, so, env, monkeypatch):
+    """every shape of the persistent pipelines (csrc/dct_pipe.cuh) against the one-CTA-per-tile kernels (SSW_COL_PIPE=0,
+    SSW_ROW_PIPE=0) through the fused device-resident entry points on 4K frames: identical watermarked bytes, identical
+    extracted vectors and scores -- the variants only move the same arithmetic around"""
+    import torch
+    w, h, n = 3840, 2160, 1000
+    monkeypatch.setenv('SSW_COL_PIPE', '0'); monkeypatch.setenv('SSW_ROW_PIPE', '0')
+    c_ref = wm.Context(0)
+    monkeypatch.delenv('SSW_ROW_PIPE')
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c_var = wm.Context(0)
+    for k in list(env) + ['SSW_COL_PIPE']:
+        monkeypatch.delenv(k, raising=False)
+    try:
+        for B in (1, 3):   # one frame: split schedule / histogram in the pipeline; three: tiles of several images per CTA
+            frames = _synth_dev(wm, c_var, w, h, 21, 0, B)
+            mk = torch.from_numpy(np.random.default_rng(B).standard_normal((B, n)).astype(np.float32)).cuda()
+            cfg = wm._lib.ssw_config(2, 0.1, 0)
+            res = []
+            for cx in (c_ref, c_var):
+                out = torch.empty_like(frames)
+                ext = torch.empty((B, n), dtype=torch.float32, device='cuda')
+                sim = torch.empty((B,), dtype=torch.float32, device='cuda')
+                torch.cuda.synchronize()
+                wm._lib.check(wm.lib.ssw_embed_batch_rgb8_dev(cx.handle, frames.data_ptr(), w, h, B, ctypes.byref(cfg), mk.data_ptr(), n, out.data_ptr()))
+                wm._lib.check(wm.lib.ssw_extract_batch_rgb8_dev(cx.handle, frames.data_ptr(), out.data_ptr(), w, h, B, ctypes.byref(cfg), n,
+                                                                ext.data_ptr(), mk.data_ptr(), sim.data_ptr()))
+                cx.synchronize()
+                assert cx.last_topk_fallbacks() == 0
+                res.append((out.cpu().numpy(), ext.cpu().numpy(), sim.cpu().numpy()))
+            assert (res[0][0] != frames.cpu().numpy()).mean() > 0.05
+            assert np.array_equal(res[0][0], res[1][0])
+            assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+            assert (res[1][2] > 20).all()
+    finally:
+        c_ref.close(); c_var.close()
+
+
 @pytest.mark.parametrize('w,h,B,method', [(3840, 2160, 1, 2), (1920, 1080, 3, 2), (640, 444, 2, 1), (1280, 720, 2, 3), (1000, 333, 1, 2)])
 def test_lowrank_embed_inverse_matches_full_inverse(wm, so, w, h, B, method, monkeypatch):
     """fused embed: Y + IDCT(changes of the k ordered coefficients) (csrc/lowrank.cuh, SSW_LOWRANK=1) against the inverse

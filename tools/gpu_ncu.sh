@@ -12,4 +12,4 @@ for i in $(seq 0 $((CNT-1))); do
 done
 ls -la $OUT/prof_$TAG.ncu-rep
 SZ=$(stat -c %s $OUT/prof_$TAG.ncu-rep 2>/dev/null || echo 0)
-if [ "$SZ" -gt 40000000 ]; then rm -f $OUT/prof_$TAG.ncu-rep; echo "rep removed (too large)"; fi
+if [ "$SZ" -gt 40000000 ] && [ -z "$KEEP_REP" ]; then rm -f $OUT/prof_$TAG.ncu-rep; echo "rep removed (too large)"; fi

@@ -21,7 +21,10 @@ acc = {}
 for r in rows[2:]:
     k = r[col['Kernel Name']]
     name = None
-    for pat, nm in NAMES:
+    m = re.search(r'(ColPipe|RowPipe)<.*>,\s*(?:\(int\))?\d+,\s*(?:(?:\(int\))?\d+,\s*)?(?:\(bool\))?(\d),\s*(?:\(int\))?\d+>\s*>', k)
+    if m:   # persistent pipelines: ColPipe<Plan, G, TEAMS, INVERSE, MINB>, RowPipe<Plan, TEAMS, INVERSE, MINB>
+        name = ('inv_' if m.group(2) == '1' else 'fwd_') + ('cols' if m.group(1) == 'ColPipe' else 'rows')
+    for pat, nm in ([] if name else NAMES):
         if pat in k:
             name = nm
             if pat == 'ColPass':
