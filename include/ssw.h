@@ -107,7 +107,9 @@ int ssw_writer_new_rgb8_dev(ssw_ctx* ctx, const uint8_t* rgb_dev, uint32_t width
                             const ssw_config* cfg, ssw_writer** out);
 /* Writer::embed(&mut self, marks) (:348-352, embed_watermark :382-410).  Marks longer than
  * width*height-1 are truncated like the reference's zip (:396).  Several marks: deltas against the
- * original coefficients are summed (:399-408). */
+ * original coefficients are summed (:399-408).  The reference fixes the ordering in Writer::new (:324-327); here it is
+ * computed for the longest mark of the first embed (or an earlier ssw_writer_indices call): a later embed that needs
+ * MORE ordered coefficients returns SSW_ERR_STATE instead of ordering already modified coefficients. */
 int ssw_writer_embed(ssw_writer* w, const float* const* marks_host, const size_t* lens, size_t n_marks);
 /* Writer::coefficient_image() (:319-321): copy of the [h][w] coefficient plane. */
 int ssw_writer_coefficients(ssw_writer* w, float* out_host);

@@ -106,7 +106,7 @@ struct ColPipe {
     // Only the 2-team, one-CTA-per-SM shape carries the half-tile and candidate-collecting code: it has registers to spare
     // (13 warps: up to 128 per thread), while the 4-team / two-CTA shapes run at the 72-register cap of 25-26 warps per SM
     // and spill as soon as the kernel grows (measured: 1080-point fwd_cols 242 -> 317 us per 64-frame launch).
-    static constexpr bool HALF_OK = (G_ == 4 && TEAMS_ == 2 && MINB_ == 1) && ((RB_HALF * ROWB / 2) % 128 == 0) && ((RB_FULL * ROWB / 2) % 128 == 0);
+    static constexpr bool HALF_OK = (G_ == 4 && (TEAMS_ == 2 || TEAMS_ == 4) && MINB_ == 1) && ((RB_HALF * ROWB / 2) % 128 == 0) && ((RB_FULL * ROWB / 2) % 128 == 0);
     static constexpr bool COLLECT_OK = (TEAMS_ == 2 && MINB_ == 1);
     // 2 teams read and write HALF rows of the tile buffer per round (line pairs {0,1} or {2,3} of the four in a 32-byte row):
     // rows r and r+4 would meet on the same banks (2-way conflicts, measured 21 % of the wavefronts).  The tensor maps of
@@ -509,7 +509,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
     const int nt = nt_full + (has_half ? 1 : 0);
     if (tid == 0) trace_info(a.trace, nt);
     // j-th element of the sequence -> image, first column, half tile?
-    auto tile_at = [&](int j, int& img, int& c0) -> bool {
+    auto tile_at = [&](int j, int& img, int& c0) __attribute__((always_inline)) -> bool {
         if (j < nt_full) {
             int t = first + j * step - a.tile_rot;
             if (t < 0) t += a.full_tiles;
@@ -526,7 +526,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
     if (tid >= NC) {
         // ===================== producer warp =====================
         if (tid == NC) {
-            auto issue_load = [&](int j) {
+            auto issue_load = [&](int j) __attribute__((always_inline)) {
                 int img, c0;
                 const bool half = tile_at(j, img, c0) && K::HALF_OK;
                 const int b = j & 1;
@@ -545,7 +545,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
                         tma_load_3d(dst + bx * K::RB_FULL * rowb, m, bar, c0, bx * K::RB_FULL, img);
                 }
             };
-            auto issue_store = [&](int j) {
+            auto issue_store = [&](int j) __attribute__((always_inline)) {
                 int img, c0;
                 const bool half = tile_at(j, img, c0) && K::HALF_OK;
                 const int b = j & 1;
@@ -595,7 +595,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
         if (!half) {
 #pragma unroll 1
             for (int rd = 0; rd < K::ROUNDS; ++rd) {
-                static_for<K::NPHASES>([&](auto ph) {
+                static_for<K::NPHASES>([&](auto ph) __attribute__((always_inline)) {
                     constexpr int p = decltype(ph)::value;
                     if constexpr (p == K::NPHASES - 1) { if (a.pdl_late && j + 1 == nt && rd + 1 == K::ROUNDS) pdl_trigger(); }
                     K::template phase<p>(a, buf, fft, tw, t4, rd, tid, th);
@@ -607,7 +607,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
                 if (rd + 1 < K::ROUNDS) named_sync(1, NC);     // FFT buffers are free for the next round
             }
         } else if constexpr (K::HALF_OK) {
-            static_for<K::NPHASES>([&](auto ph) {              // one round over the G/2 line pairs of a half tile
+            static_for<K::NPHASES>([&](auto ph) __attribute__((always_inline)) {              // one round over the G/2 line pairs of a half tile
                 constexpr int p = decltype(ph)::value;
                 if constexpr (p == K::NPHASES - 1) { if (a.pdl_late && j + 1 == nt) pdl_trigger(); }
                 K::template phase<p, K::GH>(a, buf, fft, tw, t4, 0, tid, th);
@@ -726,7 +726,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
     const int nt = first < a.total_tiles ? (a.total_tiles - first + step - 1) / step : 0;
     if (tid == 0) trace_info(a.trace, nt);
     const size_t frame_px = (size_t)a.w * a.h;
-    auto px_of = [&](int j) {   // first pixel of tile j of this CTA, counted over the whole batch
+    auto px_of = [&](int j) __attribute__((always_inline)) {   // first pixel of tile j of this CTA, counted over the whole batch
         const int tile = first + j * step, img = tile / a.tiles_per_image;
         return img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N;
     };
@@ -734,13 +734,13 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
     if (tid >= NC) {
         // ===================== producer warp =====================
         if (tid == NC) {
-            auto load_a = [&](int j) {
+            auto load_a = [&](int j) __attribute__((always_inline)) {
                 trace_tile(a.trace, j, 0);
                 mbar_expect_tx(bar_fullA, K::A_BYTES);
                 if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, a.plane + px_of(j), K::A_BYTES, bar_fullA);
                 else bulk_load(sbase + K::OFF_A, a.pix + 3 * px_of(j), K::A_BYTES, bar_fullA);
             };
-            auto load_b = [&](int j) {   // inverse only: the original pixels of the tile
+            auto load_b = [&](int j) __attribute__((always_inline)) {   // inverse only: the original pixels of the tile
                 mbar_expect_tx(bar_fullB, K::B_BYTES);
                 bulk_load(sbase + K::OFF_B, a.pix + 3 * px_of(j), K::B_BYTES, bar_fullB);
             };
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
         float* gout = K::INVERSE ? nullptr : a.plane + px_of(j);
         mbar_wait(bar_fullA, j & 1);                           // tile j has landed in A
         if (tid == 0) trace_tile(a.trace, j, 1);
-        static_for<K::NPH>([&](auto ph) {
+        static_for<K::NPH>([&](auto ph) __attribute__((always_inline)) {
             constexpr int p = decltype(ph)::value;
             if constexpr (p == K::NPH - 1) {
                 if (a.pdl_late && j + 1 == nt) pdl_trigger();

@@ -64,11 +64,14 @@ static Api* api() {
 // 64 x 32 tiles: a warp stores 64 consecutive floats (256 bytes) of one destination line.
 struct PeerPtrs { float* p[16]; };
 
+// Destination order: rank r sends to r+1, r+2, ... (mod G) and copies its own block last, so at any moment every rank's
+// stores go to a different owner (no incast on one NVLink ingress while the others idle).
 __global__ void __launch_bounds__(256)
-transpose_push_kernel(const float* __restrict__ src, unsigned nr, unsigned cb, long long ld, PeerPtrs dst, long long dst_ld, long long dst_off) {
+transpose_push_kernel(const float* __restrict__ src, unsigned nr, unsigned cb, long long ld, PeerPtrs dst, long long dst_ld, long long dst_off,
+                      unsigned rank) {
     pdl_enter();
     __shared__ float tile[64][33];
-    const unsigned g = blockIdx.z;
+    const unsigned g = (blockIdx.z + rank + 1u) % gridDim.z;
     const float* s = src + (long long)g * cb;
     float* d = dst.p[g];
     const unsigned c0 = blockIdx.x * 32, r0 = blockIdx.y * 64;
@@ -180,7 +183,12 @@ extern "C" int ssw_sharded_create(ssw_ctx* c, const void* id, int rank, int worl
     CK(cudaMalloc(&s->d_part, (kTopkCap / 2) * sizeof(float)));
     CK(cudaMemset(s->d_overflow, 0, sizeof(unsigned)));
     CK(cudaMemset(s->d_barrier, 0, sizeof(float)));
-    CK(cudaStreamCreateWithFlags(&s->push, cudaStreamNonBlocking));
+    {   // the pushes run beside the line kernels of the next slice: highest priority, so that their CTAs take the SM slots
+        // the line kernel frees first (the exchange, not the arithmetic, is the longer of the two)
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s->push, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
     // slices of a local pass whose push overlaps the next slice's line kernels
     s->chunks = 1;
@@ -268,7 +276,7 @@ static int sharded_exchange(ssw_sharded* s, bool forward, const uint8_t* rows_rg
             KScope ks(c, "transpose_push");
             const dim3 grid((cb + 31) / 32, (lc + 63) / 64, (unsigned)G);
             transpose_push_kernel<<<grid, 256, 0, ps>>>(lines, lc, cb, (long long)n, dst, dst_ld,
-                                                        (long long)s->rank * n_lines + (long long)l0);
+                                                        (long long)s->rank * n_lines + (long long)l0, (unsigned)s->rank);
         }
         CK(cudaGetLastError());
     }

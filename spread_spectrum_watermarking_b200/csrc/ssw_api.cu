@@ -71,6 +71,7 @@ struct ssw_ctx {
     std::map<int, std::unique_ptr<DevPlan>> plans;
     std::map<const void*, int> smem_attr;  // kernel -> configured dynamic smem
     std::map<int, void*> fast_tw;          // line length -> stage twiddles of the compile-time plan
+    cudaMemPool_t pool = nullptr;          // private stream-ordered memory pool (cudaMallocFromPoolAsync)
     std::atomic<int> refs{1};              // the owner's reference + one per live writer / reader / bank / sharded object
     long long* trace = nullptr;            // ssw_ctx_set_trace: device buffer of pipeline time stamps (dct_pipe.cuh), 16 launches x 1024 CTAs x 64
     unsigned trace_launch = 0;
@@ -209,10 +210,18 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    {   // stream-ordered allocations come from a pool the context owns (it keeps what it has freed: sub-batches of up to
+        // 2 GiB are reused call after call) -- the device's default pool, which other libraries of the process share, is left alone
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CK(cudaMemPoolCreate(&c->pool, &props));
+        uint64_t thr = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
     CK(cudaHostAlloc((void**)&c->h_flag, 64, cudaHostAllocDefault));
     CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
@@ -286,6 +295,7 @@ static void ctx_free(ssw_ctx* c) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(c->pool); }   // frees of the other streams have run
     delete c;
 }
 static void ctx_release(ssw_ctx* c) { if (c && c->refs.fetch_sub(1) == 1) ctx_free(c); }
@@ -1220,7 +1230,7 @@ extern "C" int ssw_dct2_2d(ssw_ctx* c, int type, uint32_t w, uint32_t h, float* 
     CKS(ctx_bind(c));
     const size_t bytes = (size_t)w * h * sizeof(float);
     float* d = nullptr;
-    CK(cudaMallocAsync(&d, bytes, c->stream));
+    CK(cudaMallocFromPoolAsync(&d, bytes, c->pool, c->stream));
     CK(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, c->stream));
     int rc = ssw_dct2_2d_dev(c, type, w, h, d);
     if (rc == SSW_OK) {
@@ -1242,7 +1252,7 @@ extern "C" int ssw_rgb32f_to_yiq(ssw_ctx* c, const float* rgb, uint32_t w, uint3
     CKS(ctx_bind(c));
     const size_t np = (size_t)w * h;
     float* d = nullptr;
-    CK(cudaMallocAsync(&d, np * 6 * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d, np * 6 * sizeof(float), c->pool, c->stream));
     CK(cudaMemcpyAsync(d, rgb, np * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     float* dy = d + 3 * np;
     { KScope ks(c, "rgb32f_to_yiq"); rgb32f_to_yiq_kernel<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(d, np, dy, dy + np, dy + 2 * np); }
@@ -1260,7 +1270,7 @@ extern "C" int ssw_yiq_to_rgb32f(ssw_ctx* c, const float* y, const float* i, con
     CKS(ctx_bind(c));
     const size_t np = (size_t)w * h;
     float* d = nullptr;
-    CK(cudaMallocAsync(&d, np * 6 * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d, np * 6 * sizeof(float), c->pool, c->stream));
     CK(cudaMemcpyAsync(d, y, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d + np, i, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d + 2 * np, q, np * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -1297,6 +1307,7 @@ struct ssw_writer {
     unsigned* d_idx;
     size_t k_cached;
     bool consumed;
+    bool embedded;   // an embed has modified the coefficients: the cached ordering can no longer be extended
 };
 
 static int writer_new(ssw_ctx* c, int src_type, const void* src, bool src_on_device, uint32_t w, uint32_t h,
@@ -1307,18 +1318,18 @@ static int writer_new(ssw_ctx* c, int src_type, const void* src, bool src_on_dev
     CKS(ctx_bind(c));
     auto wr = std::make_unique<ssw_writer>();
     wr->ctx = c; wr->w = w; wr->h = h; wr->cfg = *cfg; wr->src_type = src_type;
-    wr->d_idx = nullptr; wr->k_cached = 0; wr->consumed = false;
+    wr->d_idx = nullptr; wr->k_cached = 0; wr->consumed = false; wr->embedded = false;
     const size_t np = (size_t)w * h;
     const size_t src_bytes = np * 3 * (src_type == PIX_RGB8 ? 1 : 4);
     if (src_on_device) {
         wr->d_src = const_cast<void*>(src);
         wr->own_src = false;
     } else {
-        CK(cudaMallocAsync(&wr->d_src, src_bytes, c->stream));
+        CK(cudaMallocFromPoolAsync(&wr->d_src, src_bytes, c->pool, c->stream));
         wr->own_src = true;
         CK(cudaMemcpyAsync(wr->d_src, src, src_bytes, cudaMemcpyHostToDevice, c->stream));
     }
-    CK(cudaMallocAsync(&wr->d_plane, np * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&wr->d_plane, np * sizeof(float), c->pool, c->stream));
     int rc = run_forward(c, src_type, wr->d_src, w, h, 1, wr->d_plane, SSW_DCT2);
     if (!src_on_device) {
         // the upload reads caller memory asynchronously: finish before returning control
@@ -1348,7 +1359,7 @@ static int ensure_indices(ssw_ctx* c, const float* d_plane, uint32_t w, uint32_t
                           unsigned** d_idx, size_t* k_cached) {
     if (k <= *k_cached) return SSW_OK;
     if (*d_idx) { CK(cudaFreeAsync(*d_idx, c->stream)); *d_idx = nullptr; *k_cached = 0; }
-    CK(cudaMallocAsync(d_idx, k * sizeof(unsigned), c->stream));
+    CK(cudaMallocFromPoolAsync(d_idx, k * sizeof(unsigned), c->pool, c->stream));
     CKS(run_topk_exact(c, d_plane, w, h, ordering, k, *d_idx));
     *k_cached = k;
     return SSW_OK;
@@ -1370,14 +1381,20 @@ extern "C" int ssw_writer_embed(ssw_writer* wr, const float* const* marks, const
         kmax = std::max(kmax, l);
     }
     if (kmax == 0) return SSW_OK;
+    // the reference orders once, in Writer::new, from the original coefficients (src/algorithm.rs:324-327); here the ordering
+    // is computed for the length first asked for -- a later, longer mark would be ordered on modified coefficients
+    if (wr->embedded && kmax > wr->k_cached)
+        return fail(SSW_ERR_STATE, "a second embed needs more ordered coefficients than the first one fixed; embed the longest mark first "
+                                   "or call ssw_writer_indices(n) before the first embed");
     CKS(ensure_indices(c, wr->d_plane, wr->w, wr->h, wr->cfg.ordering, kmax, &wr->d_idx, &wr->k_cached));
+    wr->embedded = true;
     // stage marks as [n_marks][kmax] zero-padded + lens
     std::vector<float> stage(n_marks * kmax, 0.f);
     for (size_t m = 0; m < n_marks; ++m) std::memcpy(&stage[m * kmax], marks[m], hl[m] * sizeof(float));
     float* d_marks = nullptr;
     unsigned* d_lens = nullptr;
-    CK(cudaMallocAsync(&d_marks, stage.size() * sizeof(float), c->stream));
-    CK(cudaMallocAsync(&d_lens, n_marks * sizeof(unsigned), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_marks, stage.size() * sizeof(float), c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_lens, n_marks * sizeof(unsigned), c->pool, c->stream));
     CK(cudaMemcpyAsync(d_marks, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_lens, hl.data(), n_marks * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
     {
@@ -1432,7 +1449,7 @@ static int writer_result(ssw_writer* wr, int dst_type, void* out, bool out_on_de
     const size_t np = (size_t)wr->w * wr->h;
     const size_t bytes = np * 3 * (dst_type == PIX_RGB8 ? 1 : 4);
     void* d_out = out;
-    if (!out_on_device) CK(cudaMallocAsync(&d_out, bytes, c->stream));
+    if (!out_on_device) CK(cudaMallocFromPoolAsync(&d_out, bytes, c->pool, c->stream));
     int rc = run_inverse(c, wr->d_plane, wr->src_type, wr->d_src, wr->w, wr->h, 1, dst_type, d_out);
     wr->consumed = true;
     if (!out_on_device) {
@@ -1489,10 +1506,10 @@ static int reader_new(ssw_ctx* c, int src_type, const void* src, bool src_on_dev
     const size_t src_bytes = np * 3 * (src_type == PIX_RGB8 ? 1 : 4);
     void* d_src = const_cast<void*>(src);
     if (!src_on_device) {
-        CK(cudaMallocAsync(&d_src, src_bytes, c->stream));
+        CK(cudaMallocFromPoolAsync(&d_src, src_bytes, c->pool, c->stream));
         CK(cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, c->stream));
     }
-    CK(cudaMallocAsync(&rd->d_plane, np * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&rd->d_plane, np * sizeof(float), c->pool, c->stream));
     int rc = run_forward(c, src_type, d_src, w, h, 1, rd->d_plane, SSW_DCT2);
     if (!src_on_device) {
         cudaFreeAsync(d_src, c->stream);
@@ -1537,7 +1554,7 @@ static int reader_extract(ssw_reader* base, ssw_reader* derived, float* out, siz
     CKS(ctx_bind(c));
     CKS(ensure_indices(c, base->d_plane, base->w, base->h, base->cfg.ordering, n, &base->d_idx, &base->k_cached));
     float* d_out = out;
-    if (!out_on_device) CK(cudaMallocAsync(&d_out, n * sizeof(float), c->stream));
+    if (!out_on_device) CK(cudaMallocFromPoolAsync(&d_out, n * sizeof(float), c->pool, c->stream));
     {
         KScope ks(c, "extract_gather");
         launch_pdl(c, extract_gather_kernel, dim3((unsigned)((n + 255) / 256), 1), 256, 0, c->stream, 
@@ -1612,7 +1629,7 @@ static int launch_similarity(ssw_ctx* c, const float* d_bank, size_t n_marks, si
     const size_t gx = (n_marks + kSimMarks - 1) / kSimMarks;
     if (gx > 0x7FFFFFFFull || n_ext > 65535 || n > 0xFFFFFFFFull) return fail(SSW_ERR_INVALID, "similarity problem too large");
     float* d_den = nullptr;
-    CK(cudaMallocAsync(&d_den, n_ext * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_den, n_ext * sizeof(float), c->pool, c->stream));
     {
         KScope ks(c, "similarity_den");
         launch_pdl(c, similarity_den_kernel, (unsigned)((n_ext + 3) / 4), 128, 0, c->stream, d_ext, (unsigned)n, (long long)n, (unsigned)n_ext, d_den);
@@ -1639,7 +1656,7 @@ extern "C" int ssw_similarity(ssw_ctx* c, const float* extracted, const float* m
     if (!c || !out || (n && (!extracted || !mark))) return fail(SSW_ERR_INVALID, "NULL argument");
     CKS(ctx_bind(c));
     float* d = nullptr;
-    CK(cudaMallocAsync(&d, (2 * n + 1) * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d, (2 * n + 1) * sizeof(float), c->pool, c->stream));
     if (n) {
         CK(cudaMemcpyAsync(d, extracted, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(d + n, mark, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -1710,8 +1727,8 @@ extern "C" int ssw_bank_similarity(ssw_bank* b, const float* ext, size_t n_ext, 
     ssw_ctx* c = b->ctx;
     CKS(ctx_bind(c));
     float *d_ext = nullptr, *d_out = nullptr;
-    CK(cudaMallocAsync(&d_ext, std::max<size_t>(n_ext * b->n, 1) * sizeof(float), c->stream));
-    CK(cudaMallocAsync(&d_out, std::max<size_t>(n_ext * b->n_marks, 1) * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_ext, std::max<size_t>(n_ext * b->n, 1) * sizeof(float), c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_out, std::max<size_t>(n_ext * b->n_marks, 1) * sizeof(float), c->pool, c->stream));
     CK(cudaMemcpyAsync(d_ext, ext, n_ext * b->n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CKS(launch_similarity(c, b->d_marks, b->n_marks, b->n, d_ext, n_ext, false, d_out));
     CK(cudaMemcpyAsync(out, d_out, n_ext * b->n_marks * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1735,7 +1752,7 @@ extern "C" int ssw_mark_generate_normal(ssw_ctx* c, uint64_t seed, size_t n, flo
     if (n == 0) return SSW_OK;
     CKS(ctx_bind(c));
     float* d = nullptr;
-    CK(cudaMallocAsync(&d, n * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d, n * sizeof(float), c->pool, c->stream));
     CKS(fill_normal(c, d, n, seed));
     CK(cudaMemcpyAsync(out, d, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaFreeAsync(d, c->stream));
@@ -1780,9 +1797,9 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
     float* d_planes = nullptr;
     unsigned* d_idx = nullptr;
     float* d_delta = nullptr;
-    CK(cudaMallocAsync(&d_planes, (size_t)cb * np * sizeof(float), c->stream));
-    CK(cudaMallocAsync(&d_idx, (size_t)cb * std::max<size_t>(k, 1) * sizeof(unsigned), c->stream));
-    CK(cudaMallocAsync(&d_delta, (size_t)cb * std::max<size_t>(k, 1) * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_planes, (size_t)cb * np * sizeof(float), c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_idx, (size_t)cb * std::max<size_t>(k, 1) * sizeof(unsigned), c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_delta, (size_t)cb * std::max<size_t>(k, 1) * sizeof(float), c->pool, c->stream));
     int rc = SSW_OK;
     for (unsigned b0 = 0; b0 < batch && rc == SSW_OK; b0 += cb) {
         const unsigned nb = std::min(cb, batch - b0);
@@ -1864,8 +1881,8 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
     CKS(ensure_topk_scratch(c, cb));
     float* d_planes = nullptr;
     unsigned* d_idx = nullptr;
-    CK(cudaMallocAsync(&d_planes, (size_t)cb * np * 2 * sizeof(float), c->stream));
-    CK(cudaMallocAsync(&d_idx, (size_t)cb * n * sizeof(unsigned), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_planes, (size_t)cb * np * 2 * sizeof(float), c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_idx, (size_t)cb * n * sizeof(unsigned), c->pool, c->stream));
     int rc = SSW_OK;
     for (unsigned b0 = 0; b0 < batch && rc == SSW_OK; b0 += cb) {
         const unsigned nb = std::min(cb, batch - b0);
@@ -1945,9 +1962,9 @@ extern "C" int ssw_embed_batch_rgb8(ssw_ctx* c, const uint8_t* rgb, uint32_t w, 
     const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch;
     uint8_t *d_in = nullptr, *d_out = nullptr;
     float* d_marks = nullptr;
-    CK(cudaMallocAsync(&d_in, bytes, c->stream));
-    CK(cudaMallocAsync(&d_out, bytes, c->stream));
-    CK(cudaMallocAsync(&d_marks, std::max<size_t>(n * batch, 1) * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_in, bytes, c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_out, bytes, c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_marks, std::max<size_t>(n * batch, 1) * sizeof(float), c->pool, c->stream));
     if (n) CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     const uint32_t cb = pipe_chunk_frames(fbytes, batch);
     const uint32_t nchunks = (batch + cb - 1) / cb;
@@ -2002,12 +2019,12 @@ extern "C" int ssw_extract_batch_rgb8(ssw_ctx* c, const uint8_t* base_rgb, const
     const size_t fbytes = (size_t)w * h * 3, bytes = fbytes * batch;
     uint8_t *d_b = nullptr, *d_d = nullptr;
     float *d_ext = nullptr, *d_marks = nullptr, *d_sim = nullptr;
-    CK(cudaMallocAsync(&d_b, bytes, c->stream));
-    CK(cudaMallocAsync(&d_d, bytes, c->stream));
-    CK(cudaMallocAsync(&d_ext, n * batch * sizeof(float), c->stream));
+    CK(cudaMallocFromPoolAsync(&d_b, bytes, c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_d, bytes, c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_ext, n * batch * sizeof(float), c->pool, c->stream));
     if (sim && marks) {
-        CK(cudaMallocAsync(&d_marks, n * batch * sizeof(float), c->stream));
-        CK(cudaMallocAsync(&d_sim, batch * sizeof(float), c->stream));
+        CK(cudaMallocFromPoolAsync(&d_marks, n * batch * sizeof(float), c->pool, c->stream));
+        CK(cudaMallocFromPoolAsync(&d_sim, batch * sizeof(float), c->pool, c->stream));
         CK(cudaMemcpyAsync(d_marks, marks, n * batch * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
     const uint32_t cb = pipe_chunk_frames(2 * fbytes, batch);
@@ -2292,7 +2309,7 @@ extern "C" int ssw_selftest_pack_u8(ssw_ctx* c, uint64_t* mismatches) {
     if (!c || !mismatches) return fail(SSW_ERR_INVALID, "NULL argument");
     CKS(ctx_bind(c));
     unsigned long long* d = nullptr;
-    CK(cudaMallocAsync(&d, sizeof(unsigned long long), c->stream));
+    CK(cudaMallocFromPoolAsync(&d, sizeof(unsigned long long), c->pool, c->stream));
     CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
     { KScope ks(c, "selftest_pack_u8"); selftest_pack_u8_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d, -0.0f); }
     CK(cudaGetLastError());

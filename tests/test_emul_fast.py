@@ -227,7 +227,7 @@ def test_col_pipe_matches_col_pass(emul, n, variant, inverse):
     assert np.array_equal(ref, got)
 
 
-@pytest.mark.parametrize('variant', [4])   # the 2-team pipeline: one round per half tile
+@pytest.mark.parametrize('variant', [4, 5])   # 2 teams: one round per half tile; 4 teams: teams 0 and 1 take the half tile
 @pytest.mark.parametrize('inverse', [0, 1])
 def test_col_pipe_half_tiles_match_col_pass(emul, inverse, variant):
     """split schedule of the column pipelines (PipeArgs::half_tiles): 3 tiles on a 2-CTA grid = one round of whole tiles + the

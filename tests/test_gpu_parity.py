@@ -455,6 +455,25 @@ def test_fast_path_matches_generic_kernels(wm, so, w, h, monkeypatch):
         cg.close(); cf.close()
 
 
+def test_second_embed_with_a_longer_mark_is_refused(wm, ctx, so):
+    """the reference orders the coefficients once, from the originals (src/algorithm.rs:324-327); a second embed that needs
+    more ordered coefficients than the first one fixed must not order the modified plane: SSW_ERR_STATE"""
+    rgb = so.synth_frame(640, 480, seed=3)
+    rng = np.random.default_rng(1)
+    short, long_ = rng.standard_normal(100).astype(np.float32), rng.standard_normal(300).astype(np.float32)
+    wr = wm.Writer.new(rgb, ctx=ctx)
+    wr.embed([short])
+    wr.embed([short])                      # same length again: fine
+    with pytest.raises(wm.SswError) as e:
+        wr.embed([long_])
+    assert e.value.status == wm._lib.SSW_ERR_STATE
+    wr2 = wm.Writer.new(rgb, ctx=ctx)
+    wr2.indices(300)                       # fixes 300 ordered coefficients first, as Writer::new does for all of them
+    wr2.embed([short])
+    wr2.embed([long_])
+    del wr, wr2
+
+
 @pytest.mark.parametrize('env', [
     {'SSW_COL_PIPE': '1'},                                               # 4 teams (default)
     {'SSW_COL_PIPE': '2'},                                               # 2 teams, half tiles, 32-byte swizzled tile buffers
