@@ -18,6 +18,7 @@
 // Like every fast kernel the compute part is written as PHASES, `ColPipe::phase<PH>(...)`, executed for all compute
 // threads between barriers; tests/emul runs the same phase functions on the CPU with memcpy standing in for the TMA.
 #pragma once
+#include <type_traits>
 #include "dct_fast.cuh"
 #if defined(__CUDACC__)
 #include "select_kernels.cuh"
@@ -269,11 +270,17 @@ struct RowPipeArgs {
     long long* trace;           // diagnostics (ssw_ctx_set_trace), nullptr = off
 };
 
-template <class P_, int TEAMS_, bool INVERSE_, int MINB_ = 2>
+// INPLACE_ (inverse only): the coefficient rows land IN the FFT buffers (a row pair is 8N bytes, exactly the N complex values
+// it becomes) and the pre pass runs in place -- every thread reads its operands into registers, the team synchronises, then
+// the pre-twiddled values overwrite them.  No buffer A: 14N instead of 22N bytes per team, i.e. a third resident CTA per SM
+// for the 3840-point rows (54 KB), at the price of the prefetch of A (the next tile's coefficient rows are requested when
+// this tile's output phase has read the FFT buffers; the other resident CTAs cover the wait).
+template <class P_, int TEAMS_, bool INVERSE_, int MINB_ = 2, bool INPLACE_ = false>
 struct RowPipe {
     using P = P_;
     static constexpr int N = P_::N, T = P_::T, TEAMS = TEAMS_, ROWS = 2 * TEAMS_, MINB = MINB_;
-    static constexpr bool INVERSE = INVERSE_;
+    static constexpr bool INVERSE = INVERSE_, INPLACE = INPLACE_;
+    static_assert(!INPLACE_ || INVERSE_, "the in-place pre pass belongs to the inverse pipeline");
     static constexpr int NC = TEAMS_ * P_::T, THREADS = NC + 32;
     static constexpr int PIX_ROW = 3 * N, COEF_ROW = 4 * N;              // bytes per row
     static constexpr int PIX_BYTES = ROWS * PIX_ROW, COEF_BYTES = ROWS * COEF_ROW;
@@ -281,12 +288,15 @@ struct RowPipe {
     static constexpr int A_BYTES = INVERSE_ ? COEF_BYTES : PIX_BYTES;    // input side
     static constexpr int B_BYTES = INVERSE_ ? PIX_BYTES : 0;             // inverse: originals in, output bytes out (in place)
     static constexpr int al128(int b) { return (b + 127) / 128 * 128; }
-    static constexpr int OFF_A = 0, OFF_B = al128(A_BYTES), OFF_FFT = OFF_B + al128(B_BYTES);
+    static constexpr int OFF_B = INPLACE_ ? 0 : al128(A_BYTES), OFF_FFT = OFF_B + al128(B_BYTES);
+    static constexpr int OFF_A = INPLACE_ ? OFF_FFT : 0;                  // in place: team g's rows at OFF_FFT + g * PITCH * 8
     static constexpr int FFT_BYTES = TEAMS_ * P_::PITCH * (int)sizeof(cplx);
     static constexpr int OFF_BAR = OFF_FFT + al128(FFT_BYTES);
     static constexpr int SMEM = OFF_BAR + 64;
     static constexpr bool FITS = SMEM <= (228 * 1024) / MINB_ - 1024;
-    static constexpr int NPH = 2 + 2 * P_::NST;
+    static constexpr int NPH = 2 + 2 * P_::NST + (INPLACE_ ? 1 : 0);     // in place: the pre pass is two phases (read | write)
+    static constexpr int PRE_IT = (N / 2 + 1 + T - 1) / T;               // pre-pass elements per thread
+    static constexpr bool INPLACE_OK = 2 * PRE_IT <= MaxRegs<P_>::value && (P_::PITCH * (int)sizeof(cplx)) % 16 == 0 && P_::PITCH >= N;
     using Thread = ThreadState<P_>;
     static bool supports(int w, int h) { return w == N && h > 0 && h % ROWS == 0; }
     static int tiles_per_image(int w, int h) { (void)w; return h / ROWS; }
@@ -296,8 +306,36 @@ struct RowPipe {
     static SSW_HD void phase(const RowPipeArgs& a, unsigned char* bufA, cplx* fft, unsigned char* bufB, float* gout, int c, Thread& th) {
         const int g = c / T, t = c - g * T;
         cplx* s = fft + g * P::PITCH;
-        if constexpr (PH > 0 && PH < NPH - 1) {
-            fft_phase<P, PH>(s, a.tw, t, th.v);
+        if constexpr (INPLACE && PH == 0) {
+            // in-place pre pass, first half: the operands of this thread's elements -> registers (the coefficient rows of the
+            // team lie where its FFT buffer is: row a = floats [0, N), row b = floats [N, 2N))
+            const float* ia = (const float*)s;
+            const float* ib = ia + N;
+#pragma unroll
+            for (int it = 0; it < PRE_IT; ++it) {
+                const int k = t + it * T;
+                if (k <= N / 2) {
+                    const int kr = k ? N - k : 0;
+                    th.v[2 * it] = mk(ia[k], ib[k]);
+                    th.v[2 * it + 1] = k ? mk(ia[kr], ib[kr]) : mk(0.f, 0.f);
+                }
+            }
+        } else if constexpr (INPLACE && PH == 1) {
+            // second half (every operand of the team is in registers): pre-twiddled values -> the same buffer
+#pragma unroll
+            for (int it = 0; it < PRE_IT; ++it) {
+                const int k = t + it * T;
+                if (k <= N / 2) {
+                    const int kr = k ? N - k : 0;
+                    const cplx pv = th.v[2 * it], qv = th.v[2 * it + 1];
+                    cplx zk, zr;
+                    dct3_pre(pv.x, pv.y, qv.x, qv.y, SSW_LDG(&a.t4[k]), zk, zr);
+                    s[P::idx(k)] = zk;
+                    if (k && kr != k) s[P::idx(kr)] = zr;
+                }
+            }
+        } else if constexpr (PH > (INPLACE ? 1 : 0) && PH < NPH - 1) {
+            fft_phase<P, PH - (INPLACE ? 1 : 0)>(s, a.tw, t, th.v);
         } else if constexpr (!INVERSE && PH == 0) {
             // staged RGB8 bytes -> luma -> Makhoul-ordered FFT input (RowFwd phase 0 without the global loads)
             const unsigned* sa = (const unsigned*)(bufA + (2 * g) * PIX_ROW);
@@ -376,6 +414,12 @@ template <class P> struct RowPipeCfg {
                                (TEAMS * P::T + 32) <= 1024;
     using Fwd = RowPipe<P, TEAMS, false, MINB_F>;
     using Inv = RowPipe<P, TEAMS, true, MINB_I>;
+    // in-place pre pass: worth it where it buys one more resident CTA (and the registers of that many threads exist)
+    static constexpr int MINB_P = MINB_I + 1;
+    using InvPTry = RowPipe<P, TEAMS, true, MINB_P, true>;
+    static constexpr bool INPLACE_OK = OK && InvPTry::INPLACE_OK && InvPTry::FITS && !RowPipe<P, TEAMS, true, MINB_P>::FITS &&
+                                       (TEAMS * P::T + 32) * MINB_P * 72 <= 65536;
+    using InvP = std::conditional_t<INPLACE_OK, InvPTry, Inv>;   // == Inv where the in-place shape does not apply
 };
 
 #if defined(__CUDACC__)
@@ -737,7 +781,10 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
             auto load_a = [&](int j) __attribute__((always_inline)) {
                 trace_tile(a.trace, j, 0);
                 mbar_expect_tx(bar_fullA, K::A_BYTES);
-                if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, a.plane + px_of(j), K::A_BYTES, bar_fullA);
+                if constexpr (K::INPLACE) {   // one row pair per team, straight into its FFT buffer
+                    for (int g = 0; g < K::TEAMS; ++g)
+                        bulk_load(sbase + K::OFF_FFT + g * K::P::PITCH * (int)sizeof(cplx), a.plane + px_of(j) + (size_t)g * 2 * K::N, 2 * K::COEF_ROW, bar_fullA);
+                } else if constexpr (K::INVERSE) bulk_load(sbase + K::OFF_A, a.plane + px_of(j), K::A_BYTES, bar_fullA);
                 else bulk_load(sbase + K::OFF_A, a.pix + 3 * px_of(j), K::A_BYTES, bar_fullA);
             };
             auto load_b = [&](int j) __attribute__((always_inline)) {   // inverse only: the original pixels of the tile
@@ -785,12 +832,15 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
                 if constexpr (K::INVERSE) { mbar_wait(bar_fullB, j & 1); if (tid == 0) trace_tile(a.trace, j, 6); }   // the originals of tile j have landed in B
             }
             K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, gout, tid, th);
-            if constexpr (p == 0) { mbar_arrive(bar_freeA); if (tid == 0) trace_tile(a.trace, j, 5); }   // (this thread's) reads of A are done
+            if constexpr (p == 0 && !K::INPLACE) { mbar_arrive(bar_freeA); if (tid == 0) trace_tile(a.trace, j, 5); }   // (this thread's) reads of A are done
             if constexpr (p + 1 < K::NPH) named_sync(1 + team, K::T);
         });
         if constexpr (K::INVERSE) {
             fence_proxy_async();                               // generic-proxy writes of B -> visible to the bulk store
             mbar_arrive(bar_readyB);
+            // in place, A is the FFT buffer: busy until the output phase has read it (the fence above also orders this
+            // thread's FFT-stage writes before the bulk copy that overwrites them)
+            if constexpr (K::INPLACE) { mbar_arrive(bar_freeA); if (tid == 0) trace_tile(a.trace, j, 5); }
         }
         named_sync(1 + team, K::T);                            // the team has read its FFT buffer: the next tile may overwrite it
         if (tid == 0) trace_tile(a.trace, j, 2);

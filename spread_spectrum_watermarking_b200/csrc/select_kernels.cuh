@@ -257,6 +257,15 @@ __device__ __forceinline__ void topk_push(unsigned key, unsigned p, unsigned bin
     }
 }
 
+// the exact test for the four coefficients of one 16-byte load (Energy ordering, flat index == position); out of line:
+// one call per ~8000 loads, and the scan loop of topk_collect keeps its registers for the loads in flight
+__device__ __noinline__ void topk_push4_energy(float4 v, unsigned p, unsigned bin_sel, unsigned* count, unsigned long long* cand) {
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+        if (p + x) topk_push(total_cmp_key(__fmul_rn(e[x], e[x])), p + x, bin_sel, count, cand);
+}
+
 __global__ void __launch_bounds__(512)
 topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, unsigned n, OrderConsts oc,
                     TopkScratch ts) {
@@ -271,14 +280,41 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
     const bool vec = ((((size_t)plane) & 15) == 0);
     if (vec) {
         const float4* p4 = (const float4*)plane;
-        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-            const float4 v = __ldg(p4 + i);
-            const unsigned p = i << 2;
-            const float e[4] = {v.x, v.y, v.z, v.w};
+        const unsigned stride = gridDim.x * blockDim.x;
+        unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (oc.mode == 0 && oc.t_ld == 0u) {
+            // Energy ordering of an unsharded plane (the hot case): key = bits(c*c) | 2^31, so "bin(key) >= bin_sel" is
+            // "c*c >= thr" for the float whose bits are (bin_sel - 2^11) << 20 -- two instructions per coefficient instead of
+            // ~15, and four independent 16-byte loads in flight per thread.  The few elements that pass (and NaNs, and every
+            // element when the bound is degenerate: thr = 0 or a NaN pattern) take the exact path below, so the candidate
+            // set is the one the exact test selects.
+            const float thr = bin_sel > (1u << (kHistBits - 1)) ? __uint_as_float((bin_sel - (1u << (kHistBits - 1))) << (32 - kHistBits)) : 0.f;
+            constexpr int U = 4;
+            for (; i < n4; i += U * stride) {
+                float4 v[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned g = flat_index(p + u, oc);
-                if (g) topk_push(order_key(e[u], g, oc), g, bin_sel, count, cand);
+                for (int u = 0; u < U; ++u) {
+                    const unsigned q = i + u * stride;
+                    v[u] = q < n4 ? __ldg(p4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned q = i + u * stride;
+                    const bool lo = (__fmul_rn(v[u].x, v[u].x) < thr) & (__fmul_rn(v[u].y, v[u].y) < thr) &
+                                    (__fmul_rn(v[u].z, v[u].z) < thr) & (__fmul_rn(v[u].w, v[u].w) < thr);
+                    if (!lo && q < n4) topk_push4_energy(v[u], q << 2, bin_sel, count, cand);
+                }
+            }
+        } else {
+            for (; i < n4; i += stride) {
+                const float4 v = __ldg(p4 + i);
+                const unsigned p = i << 2;
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned g = flat_index(p + u, oc);
+                    if (g) topk_push(order_key(e[u], g, oc), g, bin_sel, count, cand);
+                }
             }
         }
         for (unsigned p = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -325,7 +361,7 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
 // of candidates with a larger key.  With ~k + one bin of candidates (1049 for k = 1000 on the 4K frame) the
 // n^2 comparisons (1.1 M) spread over kRankCtas CTAs take ~1 us -- far less than a single-CTA bitonic network,
 // whose 66 dependent exchange steps (shuffles, shared-memory round trips, barriers) cost 12-14 us.
-// CTA b ranks candidates [64 b, 64 b + 64) (+ strides of 64 * gridDim.x); 4 thread groups split the comparison
+// CTA b ranks candidates [32 b, 32 b + 32) (+ strides of 32 * gridDim.x); 8 thread groups split the comparison
 // range.  The thread that learns "candidate p has rank r < k" is also the one that knows everything the next step
 // of the fused pipelines needs, so it performs it in place (TopkApply): the embedding of mark value r into
 // coefficient p (Writer::embed_watermark, /root/reference/src/algorithm.rs:394-398) or the extraction of value r
@@ -335,7 +371,9 @@ topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned*
 // A frame whose candidate list overflowed (or came up short) is NOT consumed: its index list is filled with
 // kBadIndex, its coefficients stay untouched (the inverse transform then returns the unmarked frame), its extracted
 // vector is zero and its score NaN -- and the sticky overflow counter tells the host (ssw_ctx_last_topk_fallbacks).
-constexpr int kRankThreads = 256, kRankCtas = 32;
+constexpr int kRankThreads = 256, kRankCtas = 64;
+constexpr int kRankSlots = 32, kRankParts = kRankThreads / kRankSlots;   // candidates ranked per CTA and pass x thread groups splitting the comparisons
+constexpr int kRankSpec = 8;   // keys per thread loaded before the count is known (2048 candidates: the usual list in one round trip)
 
 struct TopkApply {
     int mode;                  // 0: indices only; 1: embed (scatter); 2: extract (gather [+ similarity]);
@@ -355,14 +393,23 @@ __global__ void __launch_bounds__(kRankThreads)
 topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, long long idx_stride, TopkApply ap) {
     pdl_enter();
     extern __shared__ unsigned long long keys[];  // up to kTopkCap candidates
-    __shared__ unsigned rank[64];
+    __shared__ unsigned rank[kRankSlots];
     __shared__ unsigned s_last;
     __shared__ float red[2][kRankThreads / 32];
     const unsigned img = blockIdx.y, tid = threadIdx.x;
+    const unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
+    // the head of the list is fetched together with its length (one L2 round trip instead of two on the latency chain
+    // of the step); entries at or beyond the length are stale words of the scratch buffer and are never looked at
+    static_assert(kRankSpec * kRankThreads <= kTopkCap, "speculative loads stay inside the candidate buffer");
+    // (as many as a list of k + one bin usually holds; CTAs whose slots lie beyond that will most likely find no work and skip it)
+    const unsigned spec_want = min((unsigned)(kRankSpec * kRankThreads), k + (k >> 2) + 64u);
+    const unsigned spec_n = blockIdx.x * (unsigned)kRankSlots < spec_want ? spec_want : 0u;
+    unsigned long long spec[kRankSpec];
+#pragma unroll
+    for (int u = 0; u < kRankSpec; ++u) spec[u] = tid + u * kRankThreads < spec_n ? __ldcg(cand + tid + u * kRankThreads) : 0ull;
     const unsigned total = __ldcg(ts.cand_count + img);
     const unsigned cnt = total < (unsigned)kTopkCap ? total : (unsigned)kTopkCap;
     const bool bad = total > (unsigned)kTopkCap || cnt < k;
-    const unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
     unsigned* out = idx_out + (long long)img * idx_stride;
     float* plane = ap.planes ? ap.planes + (long long)img * ap.plane_stride : nullptr;
     const float* dplane = ap.derived ? ap.derived + (long long)img * ap.plane_stride : nullptr;
@@ -374,12 +421,15 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
             if (ap.mode >= 2) ext[r] = 0.f;
         }
         if (ap.mode == 3 && blockIdx.x == 0 && tid == 0) ts.maxrow[img] = 0xFFFFFFFFu;
-    } else if (blockIdx.x * 64u < cnt) {
-        for (unsigned j = tid; j < cnt; j += kRankThreads) keys[j] = __ldcg(cand + j);
-        const unsigned slot = tid & 63u, part = tid >> 6;
-        const unsigned j0 = (unsigned)(((unsigned long long)cnt * part) >> 2), j1 = (unsigned)(((unsigned long long)cnt * (part + 1)) >> 2);
-        for (unsigned base = blockIdx.x * 64u; base < cnt; base += gridDim.x * 64u) {
-            if (tid < 64u) rank[tid] = 0u;
+    } else if (blockIdx.x * (unsigned)kRankSlots < cnt) {
+#pragma unroll
+        for (int u = 0; u < kRankSpec; ++u)
+            if (tid + u * kRankThreads < spec_n) keys[tid + u * kRankThreads] = spec[u];
+        for (unsigned j = spec_n + tid; j < cnt; j += kRankThreads) keys[j] = __ldcg(cand + j);
+        const unsigned slot = tid % (unsigned)kRankSlots, part = tid / (unsigned)kRankSlots;
+        const unsigned j0 = (unsigned)(((unsigned long long)cnt * part) / kRankParts), j1 = (unsigned)(((unsigned long long)cnt * (part + 1)) / kRankParts);
+        for (unsigned base = blockIdx.x * (unsigned)kRankSlots; base < cnt; base += gridDim.x * (unsigned)kRankSlots) {
+            if (tid < (unsigned)kRankSlots) rank[tid] = 0u;
             __syncthreads();   // keys (first round) and rank[] ready
             const unsigned i = base + slot;
             if (i < cnt) {
@@ -390,7 +440,7 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
                 atomicAdd(&rank[slot], above);
             }
             __syncthreads();
-            if (tid < 64u && i < cnt && rank[tid] < k) {
+            if (tid < (unsigned)kRankSlots && i < cnt && rank[tid] < k) {
                 const unsigned r = rank[tid], p = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
                 out[r] = p;
                 if (ap.mode == 1) plane[p] = insert_fn(ap.method, ap.alpha, plane[p], __ldg(mk + r));

@@ -88,6 +88,8 @@ struct ssw_ctx {
     bool topk_full_hist = false;           // fused pipelines: threshold bin from the whole plane (repair mode)
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
     int row_pipe = 1;                      // SSW_ROW_PIPE: 0 RowFwd / RowInv (one CTA per tile); 1 persistent bulk-copy pipelines (dct_pipe.cuh)
+    int collect_occ = 0;                   // resident CTAs per SM of topk_collect (queried once)
+    int row_inplace = 0;                   // SSW_ROW_INPLACE=1: inverse row pipeline with the in-place pre pass (RowPipeCfg::InvP: a third CTA per SM for 3840 / 1920-point rows)
     int col_pipe = 1;                      // SSW_COL_PIPE: 0 ColPass (one CTA per tile); 1..3 persistent TMA pipelines (dct_pipe.cuh):
                                            // 1 = 8 columns, 4 teams; 2 = 8 columns, 2 teams x 2 rounds; 3 = 4 columns, 2 teams (2 CTAs / SM)
     void* encode_tiled = nullptr;          // cuTensorMapEncodeTiled (driver entry point, resolved once)
@@ -248,6 +250,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_FORCE_LINE1")) c->force_line1 = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_PIPE")) c->col_pipe = atoi(s);
     if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
+    if (const char* s = getenv("SSW_ROW_INPLACE")) c->row_inplace = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_SPLIT")) c->col_split = atoi(s) != 0;
@@ -654,7 +657,8 @@ static int pipe_row(ssw_ctx* c, bool inverse, const void* d_pix, float* d_plane,
         using Cfg = fast::RowPipeCfg<P>;
         if constexpr (Cfg::OK) {
             if (!Cfg::Fwd::supports(w, h)) return;
-            if (inverse) rc = launch_row_pipe<typename Cfg::Inv>(c, "inv_rows", d_pix, d_plane, d_out, w, h, batch, scale0, scalen);
+            if (inverse && c->row_inplace && Cfg::INPLACE_OK) rc = launch_row_pipe<typename Cfg::InvP>(c, "inv_rows", d_pix, d_plane, d_out, w, h, batch, scale0, scalen);
+            else if (inverse) rc = launch_row_pipe<typename Cfg::Inv>(c, "inv_rows", d_pix, d_plane, d_out, w, h, batch, scale0, scalen);
             else rc = launch_row_pipe<typename Cfg::Fwd>(c, "fwd_rows", d_pix, d_plane, nullptr, w, h, batch, scale0, scalen);
             *done = true;
         }
@@ -1125,6 +1129,14 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     const long long stride = (long long)n;
     unsigned blocks = (unsigned)std::min<size_t>(((size_t)n / 4 + 511) / 512, (size_t)std::max(1u, (unsigned)(c->sm_count * 4) / std::min(batch, (unsigned)(c->sm_count * 4))));
     blocks = std::max(1u, blocks);
+    // the collecting scan runs as exactly one wave of its own occupancy (its loop keeps four 16-byte loads in flight per thread)
+    if (!c->collect_occ) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topk_collect_kernel, 512, 0));
+        c->collect_occ = std::max(1, occ);
+    }
+    const unsigned wave = (unsigned)(c->sm_count * c->collect_occ);
+    const unsigned cblocks = std::max(1u, (unsigned)std::min<size_t>(((size_t)n / 4 + 511) / 512, (size_t)std::max(1u, wave / std::min(batch, wave))));
     // hist_ready: the forward column pipeline has already left the selection bin of the low-frequency block in ts.sel_bin
     if (full_hist && hist_ready) return fail(SSW_ERR_STATE, "selection bin requested from both the block and the full plane");
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
@@ -1140,7 +1152,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
             launch_pdl(c, topk_block_bin_kernel, dim3(nb), kBinThreads, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
         if (hist_ready < 2) {   // 2: the forward column pipeline has appended the candidates as well (PipeArgs::collect)
-            KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(blocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts);
+            KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(cblocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts);
         }
         CK(cudaGetLastError());
     }

@@ -75,4 +75,6 @@ def ctx(wm):
 
 
 def ptr(a):
-    return ctypes.c_void_p(a.ctypes.data)
+    # data_as keeps a reference to the array, so ptr(x.copy()) stays valid for the duration of the call it is passed to
+    # (a bare c_void_p of the address would let the temporary be freed -- and its memory reused -- before the callee reads it)
+    return a.ctypes.data_as(ctypes.c_void_p)

@@ -150,7 +150,12 @@ void emulate_row_pipe(RowPipeArgs a) {
         const int img = tile / a.tiles_per_image;
         const size_t px0 = img * frame_px + (size_t)(tile - img * a.tiles_per_image) * K::ROWS * K::N;
         if (K::INVERSE) {
-            std::memcpy(A.data(), a.plane + px0, K::A_BYTES);
+            if constexpr (K::INPLACE) {   // one row pair per team, straight into its FFT buffer
+                for (int g = 0; g < K::TEAMS; ++g)
+                    std::memcpy((unsigned char*)(fft.data() + (size_t)g * K::P::PITCH), a.plane + px0 + (size_t)g * 2 * K::N, 2 * K::COEF_ROW);
+            } else {
+                std::memcpy(A.data(), a.plane + px0, K::A_BYTES);
+            }
             std::memcpy(B.data(), a.pix + 3 * px0, K::B_BYTES);
         } else {
             std::memcpy(A.data(), a.pix + 3 * px0, K::A_BYTES);
@@ -180,7 +185,10 @@ int emul_row_pipe(int inverse, const unsigned char* pix, int w, int h, int batch
             std::memset(&a, 0, sizeof(a));
             a.w = w; a.h = h; a.batch = batch; a.pix = pix; a.plane = plane; a.out = out; a.scale0 = scale0; a.scalen = scalen;
             a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
-            if (inverse) emulate_row_pipe<typename Cfg::Inv>(a); else emulate_row_pipe<typename Cfg::Fwd>(a);
+            // inverse == 2: the in-place shape (RowPipeCfg::InvP); lengths without one report -2
+            if (inverse == 2) { if constexpr (Cfg::INPLACE_OK) emulate_row_pipe<typename Cfg::InvP>(a); else return; }
+            else if (inverse) emulate_row_pipe<typename Cfg::Inv>(a);
+            else emulate_row_pipe<typename Cfg::Fwd>(a);
             ran = true;
         }
     });

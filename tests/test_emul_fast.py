@@ -255,6 +255,15 @@ def test_row_pipe_matches_row_kernels(emul, so, n, h):
     coef = ((rng.random((2 * h, n)).astype(np.float32) - 0.5) * 2.0)
     coef[:, 0] += 80.0
     o1, o2 = np.zeros_like(rgb), np.zeros_like(rgb)
-    assert emul.emul_fast_row_inv(0, 0, ptr(coef.copy()), ptr(rgb), n, h, 2, ptr(o1), f32(2.0 / n)) == 0
-    assert emul.emul_row_pipe(1, ptr(rgb), n, h, 2, ptr(coef.copy()), ptr(o2), f32(2.0 / n), f32(2.0 / n)) == 0
+    c1, c2, c3 = coef.copy(), coef.copy(), coef.copy()   # (named: a temporary would be freed before the call reads it)
+    assert emul.emul_fast_row_inv(0, 0, ptr(c1), ptr(rgb), n, h, 2, ptr(o1), f32(2.0 / n)) == 0
+    assert emul.emul_row_pipe(1, ptr(rgb), n, h, 2, ptr(c2), ptr(o2), f32(2.0 / n), f32(2.0 / n)) == 0
     assert len(np.unique(o1)) > 50 and np.array_equal(o1, o2)
+    # in-place shape of the inverse pipeline (coefficient rows land in the FFT buffers, two-phase pre pass)
+    o3 = np.zeros_like(rgb)
+    rc = emul.emul_row_pipe(2, ptr(rgb), n, h, 2, ptr(c3), ptr(o3), f32(2.0 / n), f32(2.0 / n))
+    assert rc in (0, -2)
+    if n in (3840, 1920):
+        assert rc == 0   # the shapes the in-place pipeline is built for
+    if rc == 0:
+        assert np.array_equal(o1, o3)

@@ -481,16 +481,20 @@ def test_second_embed_with_a_longer_mark_is_refused(wm, ctx, so):
     {'SSW_COL_PIPE': '2', 'SSW_COL_COLLECT': '1'},                        # candidates appended by the column pipeline
     {'SSW_COL_PIPE': '3'},                                               # 4-column tiles, two CTAs per SM
     {'SSW_COL_PIPE': '1', 'SSW_COL_HIST': '0'},                           # selection bin from topk_block_bin
+    {'SSW_ROW_INPLACE': '0'},                                            # inverse rows with a separate input buffer, two CTAs per SM
+    {'SSW_ROW_INPLACE': '1'},                                            # inverse rows with the in-place pre pass, three CTAs per SM
+    {'SSW_ROW_INPLACE': '1', 'dims': (1920, 1080)},                      # ... on the two-team shape of the 1920-point rows
 ])
 def test_pipeline_variants_are_bit_identical(wm, so, env, monkeypatch):
     """every shape of the persistent pipelines (csrc/dct_pipe.cuh) against the one-CTA-per-tile kernels (SSW_COL_PIPE=0,
     SSW_ROW_PIPE=0) through the fused device-resident entry points on 4K frames: identical watermarked bytes, identical
     extracted vectors and scores -- the variants only move the same arithmetic around"""
     import torch
-    w, h, n = 3840, 2160, 1000
+    env = dict(env)
+    (w, h), n = env.pop('dims', (3840, 2160)), 1000
     monkeypatch.setenv('SSW_COL_PIPE', '0'); monkeypatch.setenv('SSW_ROW_PIPE', '0')
     c_ref = wm.Context(0)
-    monkeypatch.delenv('SSW_ROW_PIPE')
+    monkeypatch.delenv('SSW_ROW_PIPE'); monkeypatch.delenv('SSW_COL_PIPE')
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     c_var = wm.Context(0)

@@ -7,5 +7,5 @@ rm -rf $D; mkdir -p $D/spread_spectrum_watermarking_b200 $D/include
 cp -r spread_spectrum_watermarking_b200/csrc $D/spread_spectrum_watermarking_b200/
 cp include/ssw.h $D/include/
 cd $D/spread_spectrum_watermarking_b200/csrc && rm -f libssw.so
-nvcc "$@" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared --split-compile 0 -o /tmp/libssw_$TAG.so ssw_api.cu > /tmp/build_$TAG.log 2>&1
+nvcc "$@" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared -o /tmp/libssw_$TAG.so ssw_api.cu > /tmp/build_$TAG.log 2>&1
 echo "nvcc rc=$?" >> /tmp/build_$TAG.log
