@@ -527,7 +527,11 @@ def run_ours(args, wl, workload, K, W, with_cpu_baseline=True, e2e_steps=None):
     step_algo = {'embed_bytes_per_px': 53.0, 'extract_bytes_per_px': 50.0}
     # whole-step rates twice: against SURVEY.md 8(d)'s separate-kernel byte counts (53 / 50 B per px; comparable with
     # BASELINE.md) and against the bytes this build actually moves (fused passes, DESIGN.md section 3: 37 / 50 B per px)
-    built = {'embed_bytes_per_px': 7.0 + 8.0 + 4.0 + 8.0 + 10.0, 'extract_bytes_per_px': 2 * (7.0 + 8.0) + 4.0}
+    # (partial inverse: the inverse column pass only touches the columns that hold a modified coefficient -- its 8 B/px are gone
+    # when the step ran 'inv_cols_part' instead of 'inv_cols')
+    partial = 'inv_cols_part' in prof and 'inv_cols' not in prof
+    built = {'embed_bytes_per_px': 7.0 + 8.0 + 4.0 + (0.0 if partial else 8.0) + 10.0, 'extract_bytes_per_px': 2 * (7.0 + 8.0) + 4.0,
+             'inverse_column_pass': 'modified columns only' if partial else 'all columns'}
     whole = {'embed_gbs': round(53.0 * px_step * K / (ms_embed * 1e-3) / 1e9, 1),
              'extract_gbs': round(50.0 * px_step * K / (ms_extract * 1e-3) / 1e9, 1),
              'embed_gbs_as_built': round(built['embed_bytes_per_px'] * px_step * K / (ms_embed * 1e-3) / 1e9, 1),

@@ -58,6 +58,13 @@ struct PipeArgs {
     // for each of the first half_tiles CTAs, processed in a single round.  One 4K frame is 480 tiles on 148 CTAs: 3 rounds
     // of whole tiles + 72 half tiles instead of a fourth round that keeps 36 SMs busy and 112 idle.
     int full_tiles, half_tiles;
+    // inverse pass only: *col_limit = the largest column index whose coefficients were modified after the forward transform
+    // (written by topk_rank); tiles beyond it are not processed.  The pass then runs OUT OF PLACE (tensor maps of two planes):
+    // it reads the coefficient plane and overwrites, in the plane that still holds the row-transformed frame of the forward
+    // pass, exactly the columns that changed -- the other columns of that plane ARE the inverse column transform of the
+    // unchanged coefficients, up to the round-off of the two column passes.  nullptr: all tiles.
+    const unsigned* col_limit;
+    const unsigned* col_limit_img;   // [batch] the same per image: a scheduled tile beyond its own image's limit is not stored
     int tab_bulk;   // twiddle tables are 16-byte aligned: the producer stages them with bulk copies (else: a loop of all threads)
 };
 
@@ -268,6 +275,13 @@ struct RowPipeArgs {
     int pdl_late;
     float neg_zero;             // -0.0f at run time, see FastArgs
     long long* trace;           // diagnostics (ssw_ctx_set_trace), nullptr = off
+    // inverse pass after a PARTIAL inverse column pass (PipeArgs::col_limit): the columns of image i beyond
+    // ((col_cut_img[i] >> col_tile_shift) + 1) << col_tile_shift were not transformed back and still hold the forward row
+    // transform, which is the inverse column transform of their coefficients up to that pass pair's gain h/2 -- applied here,
+    // to the coefficients as they are read (col_gain = h/2).  nullptr: every column went through the inverse column pass.
+    const unsigned* col_cut_img;
+    int col_tile_shift;
+    float col_gain;
 };
 
 // INPLACE_ (inverse only): the coefficient rows land IN the FFT buffers (a row pair is 8N bytes, exactly the N complex values
@@ -302,8 +316,9 @@ struct RowPipe {
     static int tiles_per_image(int w, int h) { (void)w; return h / ROWS; }
 
     // c: compute thread id (team g = c / T owns rows 2g, 2g+1 of the tile); gout: the tile's coefficient rows in the plane (forward)
+    // kcut (inverse): first column whose coefficients still need the gain of the skipped column passes (RowPipeArgs::col_cut_img)
     template <int PH>
-    static SSW_HD void phase(const RowPipeArgs& a, unsigned char* bufA, cplx* fft, unsigned char* bufB, float* gout, int c, Thread& th) {
+    static SSW_HD void phase(const RowPipeArgs& a, unsigned char* bufA, cplx* fft, unsigned char* bufB, float* gout, int c, Thread& th, int kcut = N + 1) {
         const int g = c / T, t = c - g * T;
         cplx* s = fft + g * P::PITCH;
         if constexpr (INPLACE && PH == 0) {
@@ -316,8 +331,9 @@ struct RowPipe {
                 const int k = t + it * T;
                 if (k <= N / 2) {
                     const int kr = k ? N - k : 0;
-                    th.v[2 * it] = mk(ia[k], ib[k]);
-                    th.v[2 * it + 1] = k ? mk(ia[kr], ib[kr]) : mk(0.f, 0.f);
+                    const float gk = k >= kcut ? a.col_gain : 1.f, gr = kr >= kcut ? a.col_gain : 1.f;
+                    th.v[2 * it] = mk(SSW_FMUL(ia[k], gk), SSW_FMUL(ib[k], gk));
+                    th.v[2 * it + 1] = k ? mk(SSW_FMUL(ia[kr], gr), SSW_FMUL(ib[kr], gr)) : mk(0.f, 0.f);
                 }
             }
         } else if constexpr (INPLACE && PH == 1) {
@@ -374,8 +390,9 @@ struct RowPipe {
 #pragma unroll 4
             for (int k = t; k <= N / 2; k += T) {
                 const int kr = k ? N - k : 0;
-                const float pa = ia[k], pb = ib[k];
-                const float qa = k ? ia[kr] : 0.f, qb = k ? ib[kr] : 0.f;
+                const float gk = k >= kcut ? a.col_gain : 1.f, gr = kr >= kcut ? a.col_gain : 1.f;
+                const float pa = SSW_FMUL(ia[k], gk), pb = SSW_FMUL(ib[k], gk);
+                const float qa = k ? SSW_FMUL(ia[kr], gr) : 0.f, qb = k ? SSW_FMUL(ib[kr], gr) : 0.f;
                 cplx zk, zr;
                 dct3_pre(pa, pb, qa, qb, SSW_LDG(&a.t4[k]), zk, zr);
                 s[P::idx(k)] = zk;
@@ -547,23 +564,35 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
 
     // this CTA's sequence: its whole tiles (round-robin), then at most one half tile
     const int first = blockIdx.x, step = gridDim.x;
-    const int nt_full = first < a.full_tiles ? (a.full_tiles - first + step - 1) / step : 0;
-    const int half_idx = first - (step - a.half_tiles);       // the LAST half_tiles CTAs take one (the histogram tiles live on the first)
-    const bool has_half = K::HALF_OK && a.half_tiles > 0 && half_idx >= 0;
+    int tiles_per_image = a.tiles_per_image, full_tiles = a.full_tiles, half_tiles = a.half_tiles;
+    if constexpr (K::INVERSE) {
+        // partial inverse (PipeArgs::col_limit): only the columns 0 .. *col_limit hold coefficients that differ from the forward
+        // transform's; the tile schedule shrinks to them (same rule as the host's: whole rounds of whole tiles, a remainder
+        // that keeps at most half of the CTAs busy goes out as half tiles)
+        if (a.col_limit) {
+            const int lim = min(a.tiles_per_image, (int)(__ldcg(a.col_limit) / (unsigned)(2 * K::G)) + 1);
+            const int total = lim * a.batch, rounds = total / step, rem = total - rounds * step;
+            tiles_per_image = lim; full_tiles = total; half_tiles = 0;
+            if (K::HALF_OK && a.batch == 1 && rem > 0 && 2 * rem <= step && (a.w % (2 * K::G)) == 0) { full_tiles = rounds * step; half_tiles = 2 * rem; }
+        }
+    }
+    const int nt_full = first < full_tiles ? (full_tiles - first + step - 1) / step : 0;
+    const int half_idx = first - (step - half_tiles);         // the LAST half_tiles CTAs take one (the histogram tiles live on the first)
+    const bool has_half = K::HALF_OK && half_tiles > 0 && half_idx >= 0;
     const int nt = nt_full + (has_half ? 1 : 0);
     if (tid == 0) trace_info(a.trace, nt);
     // j-th element of the sequence -> image, first column, half tile?
     auto tile_at = [&](int j, int& img, int& c0) __attribute__((always_inline)) -> bool {
         if (j < nt_full) {
             int t = first + j * step - a.tile_rot;
-            if (t < 0) t += a.full_tiles;
-            img = t / a.tiles_per_image;
-            c0 = (t - img * a.tiles_per_image) * 2 * K::G;
+            if (t < 0) t += full_tiles;
+            img = t / tiles_per_image;
+            c0 = (t - img * tiles_per_image) * 2 * K::G;
             return false;
         }
-        const int t = a.full_tiles + (half_idx >> 1);
-        img = t / a.tiles_per_image;
-        c0 = (t - img * a.tiles_per_image) * 2 * K::G + (half_idx & 1) * K::G;
+        const int t = full_tiles + (half_idx >> 1);
+        img = t / tiles_per_image;
+        c0 = (t - img * tiles_per_image) * 2 * K::G + (half_idx & 1) * K::G;
         return true;
     };
 
@@ -595,6 +624,10 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
                 const int b = j & 1;
                 const unsigned src = sbase + b * K::BUF_BYTES;
                 const unsigned rowb = half ? K::ROWB / 2 : K::ROWB;
+                if constexpr (K::INVERSE) {
+                    // partial inverse of a batch: the schedule follows the widest image; every image keeps exactly its own columns
+                    if (a.col_limit_img && (unsigned)(c0 & ~(2 * K::G - 1)) > __ldcg(a.col_limit_img + img)) { tma_commit(); return; }
+                }
                 if constexpr (!K::INVERSE) {
                     const TmaMap* m = half ? &map_c2 : &map_c;
                     for (int bx = 0; bx < K::NBOX_FULL; ++bx)
@@ -823,6 +856,13 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
     cplx* fft = (cplx*)(pipe_smem + K::OFF_FFT);
     for (int j = 0; j < nt; ++j) {
         float* gout = K::INVERSE ? nullptr : a.plane + px_of(j);
+        int kcut = K::N + 1;
+        if constexpr (K::INVERSE) {
+            if (a.col_cut_img) {
+                const int img = (first + j * step) / a.tiles_per_image;
+                kcut = (int)(((__ldcg(a.col_cut_img + img) >> a.col_tile_shift) + 1u) << a.col_tile_shift);
+            }
+        }
         mbar_wait(bar_fullA, j & 1);                           // tile j has landed in A
         if (tid == 0) trace_tile(a.trace, j, 1);
         static_for<K::NPH>([&](auto ph) __attribute__((always_inline)) {
@@ -831,7 +871,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MINB) row_pipe_kernel(const __g
                 if (a.pdl_late && j + 1 == nt) pdl_trigger();
                 if constexpr (K::INVERSE) { mbar_wait(bar_fullB, j & 1); if (tid == 0) trace_tile(a.trace, j, 6); }   // the originals of tile j have landed in B
             }
-            K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, gout, tid, th);
+            K::template phase<p>(a, pipe_smem + K::OFF_A, fft, pipe_smem + K::OFF_B, gout, tid, th, kcut);
             if constexpr (p == 0 && !K::INPLACE) { mbar_arrive(bar_freeA); if (tid == 0) trace_tile(a.trace, j, 5); }   // (this thread's) reads of A are done
             if constexpr (p + 1 < K::NPH) named_sync(1 + team, K::T);
         });

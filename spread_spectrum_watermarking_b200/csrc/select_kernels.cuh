@@ -53,6 +53,9 @@ struct TopkScratch {
     unsigned* cand_count;  // [batch], zero between calls
     unsigned long long* cand;  // [batch][kTopkCap]
     unsigned* overflow;    // [1] sticky counter of images whose candidate list overflowed
+    unsigned* maxcol;      // [1] largest column index of a coefficient modified by the embedding of this launch (TopkApply mode 1 with
+                           //     width set): cleared by topk_collect, read by the partial inverse column pass (dct_pipe.cuh, PipeArgs::col_limit)
+    unsigned* maxcol_img;  // [batch] the same per image: what an image gets back from the partial inverse depends on the image alone
     unsigned* maxrow;      // [batch] largest coefficient row among the first k ordered indices (low-rank embed inverse);
                            // zeroed by topk_collect, 0xFFFFFFFF = the ordering of this frame failed
 };
@@ -274,6 +277,7 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
     const float* plane = planes + (long long)img * plane_stride;
     const unsigned bin_sel = ts.sel_bin[img];
     if (ts.maxrow && blockIdx.x == 0 && threadIdx.x == 0) ts.maxrow[img] = 0u;
+    if (ts.maxcol && blockIdx.x == 0 && threadIdx.x == 0) { ts.maxcol_img[img] = 0u; if (blockIdx.y == 0) *ts.maxcol = 0u; }
     unsigned* count = ts.cand_count + img;
     unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
     const unsigned n4 = n >> 2;
@@ -378,7 +382,7 @@ constexpr int kRankSpec = 8;   // keys per thread loaded before the count is kno
 struct TopkApply {
     int mode;                  // 0: indices only; 1: embed (scatter); 2: extract (gather [+ similarity]);
                                // 3: embed as deltas: out[r] = f(c, w_r) - c, plane untouched, ts.maxrow = max coefficient row (lowrank.cuh)
-    unsigned width;            // mode 3: frame width (row of a flat index)
+    unsigned width;            // mode 3: frame width (row of a flat index); mode 1: non-zero = record the largest modified column in ts.maxcol
     int method; float alpha;   // insertion / extraction option 1..3
     float* planes;             // mode 1: coefficient planes, modified in place; mode 2: base planes (read)
     const float* derived;      // mode 2
@@ -443,7 +447,10 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
             if (tid < (unsigned)kRankSlots && i < cnt && rank[tid] < k) {
                 const unsigned r = rank[tid], p = 0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull);
                 out[r] = p;
-                if (ap.mode == 1) plane[p] = insert_fn(ap.method, ap.alpha, plane[p], __ldg(mk + r));
+                if (ap.mode == 1) {
+                    plane[p] = insert_fn(ap.method, ap.alpha, plane[p], __ldg(mk + r));
+                    if (ap.width) { atomicMax(ts.maxcol, p % ap.width); atomicMax(ts.maxcol_img + img, p % ap.width); }
+                }
                 else if (ap.mode == 2) ext[r] = extract_fn(ap.method, ap.alpha, plane[p], dplane[p]);
                 else if (ap.mode == 3) {
                     const float c0 = plane[p];

@@ -89,6 +89,8 @@ struct ssw_ctx {
     bool force_line1 = false;              // SSW_FORCE_LINE1=1: single-line kernels wherever they have a plan
     int row_pipe = 1;                      // SSW_ROW_PIPE: 0 RowFwd / RowInv (one CTA per tile); 1 persistent bulk-copy pipelines (dct_pipe.cuh)
     int collect_occ = 0;                   // resident CTAs per SM of topk_collect (queried once)
+    struct { const unsigned* img = nullptr; int shift = 0; float gain = 1.f; bool used = false; } row_cut;   // see launch_row_pipe
+    int partial_inv = 1;                   // SSW_PARTIAL_INV=0: the fused embed sends every column back through the inverse column pass
     int row_inplace = 0;                   // SSW_ROW_INPLACE=1: inverse row pipeline with the in-place pre pass (RowPipeCfg::InvP: a third CTA per SM for 3840 / 1920-point rows)
     int col_pipe = 1;                      // SSW_COL_PIPE: 0 ColPass (one CTA per tile); 1..3 persistent TMA pipelines (dct_pipe.cuh):
                                            // 1 = 8 columns, 4 teams; 2 = 8 columns, 2 teams x 2 rounds; 3 = 4 columns, 2 teams (2 CTAs / SM)
@@ -251,6 +253,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_COL_PIPE")) c->col_pipe = atoi(s);
     if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
     if (const char* s = getenv("SSW_ROW_INPLACE")) c->row_inplace = atoi(s);
+    if (const char* s = getenv("SSW_PARTIAL_INV")) c->partial_inv = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_SPLIT")) c->col_split = atoi(s) != 0;
@@ -266,7 +269,7 @@ extern "C" int ssw_ctx_create(int device, ssw_ctx** out) { return ssw_ctx_create
 static void topk_scratch_free(ssw_ctx* c) {
     if (!c->ts_batch) return;
     cudaFree(c->ts.hist); cudaFree(c->ts.ticket); cudaFree(c->ts.sel_bin);
-    cudaFree(c->ts.cand_count); cudaFree(c->ts.cand); cudaFree(c->ts.overflow); cudaFree(c->ts.maxrow);
+    cudaFree(c->ts.cand_count); cudaFree(c->ts.cand); cudaFree(c->ts.overflow); cudaFree(c->ts.maxrow); cudaFree(c->ts.maxcol);
     c->ts = TopkScratch{};
     c->ts_batch = 0;
 }
@@ -625,6 +628,10 @@ static int launch_row_pipe(ssw_ctx* c, const char* name, const void* pix, float*
     a.pdl_late = c->pdl_mode != 0;
     a.neg_zero = -0.0f;
     a.trace = c->trace ? c->trace + (size_t)(c->trace_launch++ % 16u) * 1024 * 64 : nullptr;
+    if (K::INVERSE && c->row_cut.img) {   // rows after a partial inverse column pass (ssw_embed_batch_rgb8_dev)
+        a.col_cut_img = c->row_cut.img; a.col_tile_shift = c->row_cut.shift; a.col_gain = c->row_cut.gain;
+        c->row_cut.used = true;
+    }
     auto kernel = fast::row_pipe_kernel<K>;
     const void* key = (const void*)kernel;
     auto it = c->smem_attr.find(key);
@@ -664,6 +671,18 @@ static int pipe_row(ssw_ctx* c, bool inverse, const void* d_pix, float* d_plane,
         }
     });
     return rc;
+}
+
+// would pipe_row(inverse) run for these frames?  (the partial inverse needs it: only the row pipeline applies RowPipeArgs::col_cut_img)
+static bool pipe_row_available(const ssw_ctx* c, const void* d_pix, const void* d_out, int w, int h) {
+    if (c->row_pipe <= 0 || c->seg.active || !c->use_fast) return false;
+    if (!aligned(d_pix, 16) || !aligned(d_out, 16) || (((size_t)w * h * 3) & 15)) return false;
+    bool ok = false;
+    fast::with_plan(w, [&](auto p) {
+        using Cfg = fast::RowPipeCfg<decltype(p)>;
+        if constexpr (Cfg::OK) ok = Cfg::Fwd::supports(w, h);
+    });
+    return ok;
 }
 
 // returns SSW_OK and sets *done when a fast kernel ran; *done = false -> caller uses the generic kernel
@@ -794,13 +813,14 @@ static int tma_maps_for(ssw_ctx* c, const float* plane, int w, int h, int batch,
         if (r != CUDA_SUCCESS) return fail(SSW_ERR_CUDA, "cuTensorMapEncodeTiled (3-D coefficient view) failed: " + std::to_string((int)r));
         std::memcpy(&maps.second, &m, sizeof(m));
     }
-    if (c->tma_maps.size() > 4096) c->tma_maps.clear();   // planes come and go (cudaMallocAsync): bounded cache
     *out = &c->tma_maps.emplace(key, maps).first->second;
     return SSW_OK;
 }
 
+// d_plane: the plane the pass reads; d_out: the plane it writes (nullptr = in place); col_limit: PipeArgs::col_limit (inverse)
 template <class K>
-static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch, float* d_plane, float scale0, float scalen) {
+static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch, float* d_plane, float scale0, float scalen,
+                           float* d_out = nullptr, const unsigned* col_limit = nullptr) {
     using P = typename K::P;
     fast::PipeArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -821,10 +841,26 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
         a.oc = make_order(c->col_hist.ordering, w, h);
         c->col_hist.done = true;
     }
+    if (c->tma_maps.size() > 4096) c->tma_maps.clear();   // planes come and go (cudaMallocAsync): bounded cache (cleared before any lookup of this launch)
     const std::pair<fast::TmaMap, fast::TmaMap>* maps;
     CKS(tma_maps_for(c, d_plane, w, h, batch, K::G, K::RB_HALF, K::RB_FULL, K::SWZ, &maps));
     const std::pair<fast::TmaMap, fast::TmaMap>* maps2 = maps;   // boxes of G columns for half tiles
     if (K::HALF_OK) CKS(tma_maps_for(c, d_plane, w, h, batch, K::G / 2, K::RB_HALF, K::RB_FULL, false, &maps2));
+    // out of place: the side the pass stores through (forward: coefficient view, inverse: sample view) belongs to d_out
+    const std::pair<fast::TmaMap, fast::TmaMap>* omaps = maps;
+    const std::pair<fast::TmaMap, fast::TmaMap>* omaps2 = maps2;
+    if (d_out && d_out != d_plane) {
+        if (!aligned(d_out, 16)) return fail(SSW_ERR_INVALID, "column pipeline: destination plane must be 16-byte aligned");
+        CKS(tma_maps_for(c, d_out, w, h, batch, K::G, K::RB_HALF, K::RB_FULL, K::SWZ, &omaps));
+        omaps2 = omaps;
+        if (K::HALF_OK) CKS(tma_maps_for(c, d_out, w, h, batch, K::G / 2, K::RB_HALF, K::RB_FULL, false, &omaps2));
+    }
+    a.col_limit = K::INVERSE ? col_limit : nullptr;
+    a.col_limit_img = a.col_limit ? col_limit + 1 : nullptr;   // (TopkScratch::maxcol layout: [0] the launch, [1 + i] image i)
+    const fast::TmaMap& m_s = K::INVERSE ? omaps->first : maps->first;      // sample side: loaded by the forward pass, stored by the inverse
+    const fast::TmaMap& m_c = K::INVERSE ? maps->second : omaps->second;    // coefficient side
+    const fast::TmaMap& m_s2 = K::INVERSE ? omaps2->first : maps2->first;
+    const fast::TmaMap& m_c2 = K::INVERSE ? maps2->second : omaps2->second;
     auto kernel = fast::col_pipe_kernel<K>;
     const void* key = (const void*)kernel;
     auto it = c->smem_attr.find(key);
@@ -854,28 +890,31 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
     a.tab_bulk = aligned(a.tw, 16) && aligned(a.t4, 16);
     {
         KScope ks(c, name);
-        launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a, maps->first, maps->second, maps2->first, maps2->second);
+        launch_pdl(c, kernel, grid, K::THREADS, K::SMEM, c->stream, a, m_s, m_c, m_s2, m_c2);
     }
     CK(cudaGetLastError());
     return SSW_OK;
 }
 
 // *done = true when a pipeline ran
-static int pipe_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen, bool* done) {
+static bool pipe_col_available(const ssw_ctx* c, int w, int h) { return c->col_pipe > 0 && (w % 4) == 0 && (h == 2160 || h == 1080); }
+
+static int pipe_col(ssw_ctx* c, bool inverse, int w, int h, int batch, float* d_plane, float scale0, float scalen, bool* done,
+                    float* d_out = nullptr, const unsigned* col_limit = nullptr) {
     *done = false;
     if (c->col_pipe <= 0 || !aligned(d_plane, 16) || (w % 4) || (h & 1)) return SSW_OK;
-    const char* name = inverse ? "inv_cols" : "fwd_cols";
+    const char* name = inverse ? (col_limit ? "inv_cols_part" : "inv_cols") : "fwd_cols";
     int rc = SSW_OK;
-    auto run = [&](auto k) { using K = decltype(k); rc = launch_col_pipe<K>(c, name, w, h, batch, d_plane, scale0, scalen); *done = true; };
+    auto run = [&](auto k) { using K = decltype(k); rc = launch_col_pipe<K>(c, name, w, h, batch, d_plane, scale0, scalen, d_out, col_limit); *done = true; };
     if (h == 2160) {
         using P = fast::Plan2160;
-        // SSW_COL_PIPE=1 (default): 4 teams, one round per tile (800 threads at the 72-register cap of 25 warps per SM);
-        // =2: 2 teams x 2 rounds per tile (416 threads, registers to spare) with the split schedule (half tiles) and 32-byte
-        // swizzled tile buffers.  Measured on one 4K frame (profiles/r2_col_pipeline_variants.md): the kernels are equal
-        // alone (fwd 29.2 / 29.5 us, inv 31.2 / 31.2 us), the step is 0.214 / 0.217 ms.
-        if (c->col_pipe == 2) { if (inverse) run(fast::ColPipe<P, 4, 2, true>{}); else run(fast::ColPipe<P, 4, 2, false>{}); }
+        // SSW_COL_PIPE=1 (default) / 2: 2 teams x 2 rounds per tile (416 threads, registers to spare) with the split schedule
+        // (half tiles) and 32-byte swizzled tile buffers; =4: 4 teams, one round per tile (800 threads at the 72-register cap
+        // of 25 warps per SM); =3: 4-column tiles, two CTAs per SM.  Measured on one 4K frame with the spill-free build
+        // (profiles/r2b_*): step 0.193 ms (2 teams) / 0.198 ms (4 teams).
+        if (c->col_pipe == 4) { if (inverse) run(fast::ColPipe<P, 4, 4, true>{}); else run(fast::ColPipe<P, 4, 4, false>{}); }
         else if (c->col_pipe == 3) { if (inverse) run(fast::ColPipe<P, 2, 2, true, 2>{}); else run(fast::ColPipe<P, 2, 2, false, 2>{}); }
-        else { if (inverse) run(fast::ColPipe<P, 4, 4, true>{}); else run(fast::ColPipe<P, 4, 4, false>{}); }   // SSW_COL_PIPE=1
+        else { if (inverse) run(fast::ColPipe<P, 4, 2, true>{}); else run(fast::ColPipe<P, 4, 2, false>{}); }   // SSW_COL_PIPE=1 (default), 2
     } else if (h == 1080) {
         using P = fast::Plan1080;
         if (c->col_pipe == 2) { if (inverse) run(fast::ColPipe<P, 4, 4, true, 1>{}); else run(fast::ColPipe<P, 4, 4, false, 1>{}); }
@@ -1095,6 +1134,9 @@ static int ensure_topk_scratch(ssw_ctx* c, unsigned batch) {
     CK(cudaMalloc(&c->ts.overflow, sizeof(unsigned)));
     CK(cudaMalloc(&c->ts.maxrow, b * sizeof(unsigned)));
     CK(cudaMemset(c->ts.maxrow, 0, b * sizeof(unsigned)));
+    CK(cudaMalloc(&c->ts.maxcol, (1 + (size_t)b) * sizeof(unsigned)));   // [0]: the launch, [1 + i]: image i
+    CK(cudaMemset(c->ts.maxcol, 0, (1 + (size_t)b) * sizeof(unsigned)));
+    c->ts.maxcol_img = c->ts.maxcol + 1;
     CK(cudaMemset(c->ts.sel_bin, 0, b * sizeof(unsigned)));   // bit 31 = "bin published" (collecting column pipeline)
     CK(cudaMemset(c->ts.hist, 0, (size_t)b * kHistBins * sizeof(unsigned)));
     CK(cudaMemset(c->ts.ticket, 0, b * sizeof(unsigned)));
@@ -1142,7 +1184,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
-        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.maxrow += b0;
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.maxrow += b0; ts.maxcol_img += b0;
         ts.cand += (size_t)b0 * kTopkCap;
         if (full_hist) {
             KScope ks(c, "topk_hist");
@@ -1166,7 +1208,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
-        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap; ts.maxrow += b0;
+        ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap; ts.maxrow += b0; ts.maxcol_img += b0;
         TopkApply a;
         std::memset(&a, 0, sizeof(a));
         if (ap) {
@@ -1804,12 +1846,19 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
     const size_t np = (size_t)w * h;
     const size_t k = std::min(n, np - 1);
     if (k > (size_t)kTopkCap / 2) return fail(SSW_ERR_UNSUPPORTED, "fused pipeline supports mark lengths up to 4096; use the Writer API");
-    const unsigned cb = chunk_images(c, np, batch, 1);
+    // Partial inverse (SSW_PARTIAL_INV, default on; needs the column pipelines): the forward column pass runs out of place and
+    // keeps the row-transformed plane R; only the columns that hold a modified coefficient go back through the inverse
+    // column pass (C -> R), every other column of R already is the inverse column transform of its unchanged coefficients
+    // (up to the round-off of the two passes, ~1e-7 relative: RGB8 within +-1 LSB of the full inverse).
+    const bool partial = c->partial_inv && !c->lowrank && k > 0 && c->use_fast && pipe_col_available(c, (int)w, (int)h) && !c->force_line1 &&
+                         pipe_row_available(c, rgb, out_rgb, (int)w, (int)h);
+    const unsigned cb = chunk_images(c, np, batch, partial ? 2 : 1);
     CKS(ensure_topk_scratch(c, cb));
     float* d_planes = nullptr;
     unsigned* d_idx = nullptr;
     float* d_delta = nullptr;
-    CK(cudaMallocFromPoolAsync(&d_planes, (size_t)cb * np * sizeof(float), c->pool, c->stream));
+    CK(cudaMallocFromPoolAsync(&d_planes, (size_t)cb * np * sizeof(float) * (partial ? 2 : 1), c->pool, c->stream));
+    float* d_rows = partial ? d_planes + (size_t)cb * np : nullptr;   // R: row-transformed frames (partial inverse)
     CK(cudaMallocFromPoolAsync(&d_idx, (size_t)cb * std::max<size_t>(k, 1) * sizeof(unsigned), c->pool, c->stream));
     CK(cudaMallocFromPoolAsync(&d_delta, (size_t)cb * std::max<size_t>(k, 1) * sizeof(float), c->pool, c->stream));
     int rc = SSW_OK;
@@ -1821,7 +1870,14 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
         // was measured slower than the separate topk_block_bin kernel, whose cost is shared by the whole batch)
         c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = c->col_hist.collected = false;
         c->col_hist.k = (unsigned)k; c->col_hist.ordering = cfg->ordering;
-        rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
+        if (partial) {
+            rc = run_rows_forward(c, PIX_RGB8, src, w, h, nb, d_rows, 1.f, 1.f);
+            bool done = false;
+            if (rc == SSW_OK) rc = pipe_col(c, false, w, h, nb, d_rows, 1.f, 1.f, &done, d_planes);
+            if (rc == SSW_OK && !done) rc = fail(SSW_ERR_STATE, "partial inverse: no column pipeline for this frame");
+        } else {
+            rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
+        }
         const int hist_ready = c->col_hist.done ? (c->col_hist.collected ? 2 : 1) : 0;
         c->col_hist.want = false;
         const bool lowrank = c->lowrank && k > 0 && (w % 4u) == 0 && w <= 65535u && h <= 65535u && aligned(src, 4) && aligned(out_rgb, 4) &&
@@ -1831,7 +1887,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
             // the low-rank inverse, stores the change D_r = f(c, w_r) - c of that coefficient (lowrank.cuh)
             TopkApply ap;
             std::memset(&ap, 0, sizeof(ap));
-            ap.mode = lowrank ? 3 : 1; ap.method = cfg->method; ap.alpha = cfg->alpha; ap.width = w;
+            ap.mode = lowrank ? 3 : 1; ap.method = cfg->method; ap.alpha = cfg->alpha; ap.width = (lowrank || partial) ? w : 0u;
             ap.planes = d_planes; ap.plane_stride = (long long)np;
             ap.marks = marks + (size_t)b0 * n; ap.mark_stride = (long long)n;
             ap.out = d_delta; ap.out_stride = (long long)k;
@@ -1865,6 +1921,21 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
                                (unsigned char*)(out_rgb + ((size_t)b0 + i0) * np * 3), (const unsigned*)(c->ts.maxrow + i0), cy_tab, -0.0f);
                 }
                 CK(cudaGetLastError());
+            }
+        } else if (rc == SSW_OK && partial) {
+            bool done = false;
+            rc = pipe_col(c, true, w, h, nb, d_planes, 1.f, 1.f, &done, d_rows, c->ts.maxcol);
+            if (rc == SSW_OK && !done) rc = fail(SSW_ERR_STATE, "partial inverse: no column pipeline for this frame");
+            if (rc == SSW_OK) {
+                // the columns that skipped the column passes lack their gain h/2; the row pipeline applies it as it reads them
+                c->row_cut.img = c->ts.maxcol + 1;
+                c->row_cut.shift = (c->col_pipe == 3 && h == 2160) ? 2 : 3;   // log2(columns per tile of the column pipeline that ran)
+                c->row_cut.gain = 0.5f * (float)h;
+                c->row_cut.used = false;
+                rc = run_rows_inverse(c, d_rows, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3, 4.0f / (float)np);
+                const bool used = c->row_cut.used;
+                c->row_cut.img = nullptr;
+                if (rc == SSW_OK && !used) rc = fail(SSW_ERR_STATE, "partial inverse: the row pass did not take the pipeline");
             }
         } else if (rc == SSW_OK) {
             rc = run_inverse(c, d_planes, PIX_RGB8, src, w, h, nb, PIX_RGB8, out_rgb + (size_t)b0 * np * 3);

@@ -139,7 +139,7 @@ void emulate_col_pipe(PipeArgs a, float* plane, const cplx* tw, const cplx* t4, 
 // persistent bulk-copy row pipelines (dct_pipe.cuh): memcpy stands in for the linear bulk copies of a tile (2*TEAMS
 // adjacent rows); the phases run for all compute threads one after the other
 template <class K>
-void emulate_row_pipe(RowPipeArgs a) {
+void emulate_row_pipe(RowPipeArgs a, int kcut_arg = -1) {
     std::vector<unsigned char> A(K::A_BYTES + 16), B(K::B_BYTES + 16);
     std::vector<cplx> fft((size_t)K::TEAMS * K::P::PITCH + 8);
     std::vector<typename K::Thread> th(K::NC);
@@ -162,7 +162,8 @@ void emulate_row_pipe(RowPipeArgs a) {
         }
         static_for<K::NPH>([&](auto ph) {
             constexpr int p = decltype(ph)::value;
-            for (int c = 0; c < K::NC; ++c) K::template phase<p>(a, A.data(), fft.data(), B.data(), K::INVERSE ? nullptr : a.plane + px0, c, th[c]);
+            for (int c = 0; c < K::NC; ++c)
+                K::template phase<p>(a, A.data(), fft.data(), B.data(), K::INVERSE ? nullptr : a.plane + px0, c, th[c], kcut_arg >= 0 ? kcut_arg : K::N + 1);
         });
         if (K::INVERSE) std::memcpy(a.out + 3 * px0, B.data(), K::B_BYTES);
     }
@@ -173,7 +174,14 @@ void emulate_row_pipe(RowPipeArgs a) {
 extern "C" {
 
 // row pipelines: forward (pix -> plane) or inverse (plane + original pix -> out); -2 when the length has no pipeline
+int emul_row_pipe_cut(int inverse, const unsigned char* pix, int w, int h, int batch, float* plane, unsigned char* out, float scale0, float scalen,
+                      int kcut, float gain);
 int emul_row_pipe(int inverse, const unsigned char* pix, int w, int h, int batch, float* plane, unsigned char* out, float scale0, float scalen) {
+    return emul_row_pipe_cut(inverse, pix, w, h, batch, plane, out, scale0, scalen, -1, 1.f);
+}
+// kcut >= 0 (inverse): coefficients of columns >= kcut are multiplied by `gain` as they are read (RowPipeArgs::col_cut_img)
+int emul_row_pipe_cut(int inverse, const unsigned char* pix, int w, int h, int batch, float* plane, unsigned char* out, float scale0, float scalen,
+                      int kcut, float gain) {
     bool ran = false;
     with_plan(w, [&](auto p) {
         using P = decltype(p);
@@ -185,9 +193,10 @@ int emul_row_pipe(int inverse, const unsigned char* pix, int w, int h, int batch
             std::memset(&a, 0, sizeof(a));
             a.w = w; a.h = h; a.batch = batch; a.pix = pix; a.plane = plane; a.out = out; a.scale0 = scale0; a.scalen = scalen;
             a.tw = (const cplx*)tb.tw.data(); a.t4 = (const cplx*)tb.t4.data();
+            a.col_gain = gain;
             // inverse == 2: the in-place shape (RowPipeCfg::InvP); lengths without one report -2
-            if (inverse == 2) { if constexpr (Cfg::INPLACE_OK) emulate_row_pipe<typename Cfg::InvP>(a); else return; }
-            else if (inverse) emulate_row_pipe<typename Cfg::Inv>(a);
+            if (inverse == 2) { if constexpr (Cfg::INPLACE_OK) emulate_row_pipe<typename Cfg::InvP>(a, kcut); else return; }
+            else if (inverse) emulate_row_pipe<typename Cfg::Inv>(a, kcut);
             else emulate_row_pipe<typename Cfg::Fwd>(a);
             ran = true;
         }

@@ -267,3 +267,15 @@ def test_row_pipe_matches_row_kernels(emul, so, n, h):
         assert rc == 0   # the shapes the in-place pipeline is built for
     if rc == 0:
         assert np.array_equal(o1, o3)
+    # rows after a partial inverse column pass (RowPipeArgs::col_cut_img): the coefficients of the columns >= kcut come
+    # without the gain of the skipped passes and get it as they are read.  With a power-of-two gain the scaling is exact:
+    # plane / gain beyond kcut + the cut == the whole plane, byte for byte, in both shapes of the inverse pipeline
+    kcut, gain = 24, 512.0
+    scaled = coef.copy()
+    scaled[:, kcut:] *= np.float32(1.0 / gain)
+    for variant in (1, 2):
+        o4, c4 = np.zeros_like(rgb), scaled.copy()
+        rc = emul.emul_row_pipe_cut(variant, ptr(rgb), n, h, 2, ptr(c4), ptr(o4), f32(2.0 / n), f32(2.0 / n), kcut, f32(gain))
+        assert rc in (0, -2) and (variant == 2 or rc == 0)
+        if rc == 0:
+            assert np.array_equal(o1, o4)

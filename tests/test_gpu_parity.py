@@ -475,8 +475,9 @@ def test_second_embed_with_a_longer_mark_is_refused(wm, ctx, so):
 
 
 @pytest.mark.parametrize('env', [
-    {'SSW_COL_PIPE': '1'},                                               # 4 teams (default)
-    {'SSW_COL_PIPE': '2'},                                               # 2 teams, half tiles, 32-byte swizzled tile buffers
+    {'SSW_COL_PIPE': '1'},                                               # default: 2 teams, half tiles, 32-byte swizzled tile buffers
+    {'SSW_COL_PIPE': '4'},                                               # 4 teams, one round per tile
+    {'SSW_COL_PIPE': '2'},                                               # (== 1 for 2160-point columns)
     {'SSW_COL_PIPE': '2', 'SSW_COL_SPLIT': '0'},
     {'SSW_COL_PIPE': '2', 'SSW_COL_COLLECT': '1'},                        # candidates appended by the column pipeline
     {'SSW_COL_PIPE': '3'},                                               # 4-column tiles, two CTAs per SM
@@ -495,10 +496,11 @@ def test_pipeline_variants_are_bit_identical(wm, so, env, monkeypatch):
     monkeypatch.setenv('SSW_COL_PIPE', '0'); monkeypatch.setenv('SSW_ROW_PIPE', '0')
     c_ref = wm.Context(0)
     monkeypatch.delenv('SSW_ROW_PIPE'); monkeypatch.delenv('SSW_COL_PIPE')
+    monkeypatch.setenv('SSW_PARTIAL_INV', '0')   # (the partial inverse column pass is pinned by its own test: +-1 LSB, not bit-identity)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     c_var = wm.Context(0)
-    for k in list(env) + ['SSW_COL_PIPE']:
+    for k in list(env) + ['SSW_COL_PIPE', 'SSW_PARTIAL_INV']:
         monkeypatch.delenv(k, raising=False)
     try:
         for B in (1, 3):   # one frame: split schedule / histogram in the pipeline; three: tiles of several images per CTA
@@ -523,6 +525,59 @@ def test_pipeline_variants_are_bit_identical(wm, so, env, monkeypatch):
             assert (res[1][2] > 20).all()
     finally:
         c_ref.close(); c_var.close()
+
+
+@pytest.mark.parametrize('w,h,B,wide', [(3840, 2160, 1, False), (3840, 2160, 2, True), (1920, 1080, 3, False), (1920, 1080, 1, True)])
+def test_partial_inverse_matches_full_inverse(wm, so, w, h, B, wide, monkeypatch):
+    """fused embed with the partial inverse column pass (default: only the columns holding a modified coefficient go back
+    through the inverse column transform, the others keep the row-transformed plane of the forward pass -- csrc/ssw_api.cu
+    ssw_embed_batch_rgb8_dev, PipeArgs::col_limit) against the inverse transform of the whole modified plane
+    (SSW_PARTIAL_INV=0, the reference's structure, src/algorithm.rs:361-379): the same RGB8 up to isolated +-1 LSB ties
+    (north_star: pixels within +-1 LSB), the same extracted marks.  `wide`: a strong horizontal carrier puts one of the
+    ordered coefficients near the right edge of the spectrum, so almost every column is processed."""
+    import torch
+    n = 1000
+    monkeypatch.setenv('SSW_PARTIAL_INV', '0')
+    c_full = wm.Context(0)
+    monkeypatch.setenv('SSW_PARTIAL_INV', '1')
+    c_part = wm.Context(0)
+    monkeypatch.delenv('SSW_PARTIAL_INV')
+    try:
+        frames = _synth_dev(wm, c_part, w, h, 31, 0, B)
+        if wide:
+            x = torch.arange(w, device='cuda', dtype=torch.float32)
+            carrier = 24.0 * torch.cos(np.pi * (2 * x + 1) * (w - 200) / (2 * w))
+            frames = (frames.float() * 0.8 + 25.0 + carrier[None, None, :, None]).clamp(0, 255).round().to(torch.uint8).contiguous()
+        mk = torch.from_numpy(np.random.default_rng(w + B).standard_normal((B, n)).astype(np.float32)).cuda()
+        cfg = wm._lib.ssw_config(2, 0.1, 0)
+        res = []
+        for cx in (c_full, c_part):
+            out = torch.empty_like(frames)
+            ext = torch.empty((B, n), dtype=torch.float32, device='cuda')
+            sim = torch.empty((B,), dtype=torch.float32, device='cuda')
+            idx = None
+            torch.cuda.synchronize()
+            wm._lib.check(wm.lib.ssw_embed_batch_rgb8_dev(cx.handle, frames.data_ptr(), w, h, B, ctypes.byref(cfg), mk.data_ptr(), n, out.data_ptr()))
+            wm._lib.check(wm.lib.ssw_extract_batch_rgb8_dev(cx.handle, frames.data_ptr(), out.data_ptr(), w, h, B, ctypes.byref(cfg), n,
+                                                            ext.data_ptr(), mk.data_ptr(), sim.data_ptr()))
+            cx.synchronize()
+            assert cx.last_topk_fallbacks() == 0
+            res.append((out.cpu().numpy(), ext.cpu().numpy(), sim.cpu().numpy()))
+        full, part = res
+        assert (full[0] != frames.cpu().numpy()).mean() > 0.05                 # the frames were marked
+        d = np.abs(full[0].astype(int) - part[0].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+        assert (part[2] > 20).all() and np.allclose(part[2], full[2], rtol=2e-2)
+        if wide:
+            # the carrier's coefficient is one of the ordered ones: the column limit really is wide
+            wr = wm.Writer.new(frames[0].cpu().numpy(), ctx=c_full)
+            cols = np.asarray(wr.indices(n)) % w
+            assert cols.max() > w - 300
+            del wr
+    finally:
+        import gc
+        gc.collect()
+        c_full.close(); c_part.close()
 
 
 @pytest.mark.parametrize('w,h,B,method', [(3840, 2160, 1, 2), (1920, 1080, 3, 2), (640, 444, 2, 1), (1280, 720, 2, 3), (1000, 333, 1, 2)])

@@ -85,16 +85,16 @@ def main():
             srd = np.where(st_rd > 0, us(st_rd - st_iss), np.nan)
             print('   %4d  %5d  %12.2f  %13.2f  %7.2f  %18.2f  %10.2f' % (j, m.sum(), np.median(load_lat), np.median(wait_tile), np.median(comp),
                   np.nanmedian(d2s) if np.isfinite(d2s).any() else float('nan'), np.nanmedian(srd) if np.isfinite(srd).any() else float('nan')))
-        # one CTA with the most tiles, in full
-        k = int(np.argmax(nt))
-        r = b[k]
-        print('   example CTA %d (SM %d, %d tiles), us since its start:' % (used[k], r[6], r[5]))
-        print('      after dependency wait %.2f' % us(r[2] - r[1]))
-        for j in range(int(min(r[5], 7))):
-            base = 8 + 8 * j
-            ev = ['load issued', 'landed', 'compute done', 'store issued', 'store read', 'A released', 'B landed']
-            print('      tile %d: ' % j + ', '.join('%s %.2f' % (ev[q], us(r[base + q] - r[1])) for q in range(7) if r[base + q] > 0))
-        print('      compute warps finished %.2f' % us(r[3] - r[1]))
+        # one CTA with the most tiles and the CTA that lived longest, in full
+        for what, k in (('example', int(np.argmax(nt))), ('longest-lived', int(np.argmax(life)))):
+            r = b[k]
+            print('   %s CTA %d (SM %d, %d tiles), us since its start:' % (what, used[k], r[6], r[5]))
+            print('      after dependency wait %.2f' % us(r[2] - r[1]))
+            for j in range(int(min(r[5], 7))):
+                base = 8 + 8 * j
+                ev = ['load issued', 'landed', 'compute done', 'store issued', 'store read', 'A released', 'B landed', 'histogram done']
+                print('      tile %d: ' % j + ', '.join('%s %.2f' % (ev[q], us(r[base + q] - r[1])) for q in range(8) if r[base + q] > 0))
+            print('      compute warps finished %.2f' % us(r[3] - r[1]))
     ctx.close()
 
 
