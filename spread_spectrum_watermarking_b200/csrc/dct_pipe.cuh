@@ -58,6 +58,9 @@ struct PipeArgs {
     // for each of the first half_tiles CTAs, processed in a single round.  One 4K frame is 480 tiles on 148 CTAs: 3 rounds
     // of whole tiles + 72 half tiles instead of a fourth round that keeps 36 SMs busy and 112 idle.
     int full_tiles, half_tiles;
+    // forward pass of one frame with the histogram: the first hist_relief CTAs own the histogram tiles (~5-9 us of extra work
+    // each, the last of them also the search) -- each gives its last whole tile away as two half tiles (see the kernel)
+    int hist_relief;
     // inverse pass only: *col_limit = the largest column index whose coefficients were modified after the forward transform
     // (written by topk_rank); tiles beyond it are not processed.  The pass then runs OUT OF PLACE (tensor maps of two planes):
     // it reads the coefficient plane and overwrites, in the plane that still holds the row-transformed frame of the forward
@@ -576,9 +579,22 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
             if (K::HALF_OK && a.batch == 1 && rem > 0 && 2 * rem <= step && (a.w % (2 * K::G)) == 0) { full_tiles = rounds * step; half_tiles = 2 * rem; }
         }
     }
-    const int nt_full = first < full_tiles ? (full_tiles - first + step - 1) / step : 0;
+    int nt_full = first < full_tiles ? (full_tiles - first + step - 1) / step : 0;
     const int half_idx = first - (step - half_tiles);         // the LAST half_tiles CTAs take one (the histogram tiles live on the first)
-    const bool has_half = K::HALF_OK && half_tiles > 0 && half_idx >= 0;
+    bool has_half = K::HALF_OK && half_tiles > 0 && half_idx >= 0;
+    int half_tile = full_tiles + (half_idx >> 1), half_sub = half_idx & 1;
+    if constexpr (!K::INVERSE && K::HALF_OK) {
+        // relief for the CTAs that build the histogram (PipeArgs::hist_relief): CTA c < relief hands its last whole tile, as two
+        // half tiles, to the CTAs relief + 2c and relief + 2c + 1, which have neither a histogram nor a half tile of their own
+        const int relief = a.hist_relief;
+        if (first < relief) nt_full -= 1;
+        else if (first < 3 * relief) {
+            const int h = first - relief, owner = h >> 1;
+            has_half = true;
+            half_tile = owner + ((full_tiles - owner + step - 1) / step - 1) * step;
+            half_sub = h & 1;
+        }
+    }
     const int nt = nt_full + (has_half ? 1 : 0);
     if (tid == 0) trace_info(a.trace, nt);
     // j-th element of the sequence -> image, first column, half tile?
@@ -590,9 +606,9 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
             c0 = (t - img * tiles_per_image) * 2 * K::G;
             return false;
         }
-        const int t = full_tiles + (half_idx >> 1);
+        const int t = half_tile;
         img = t / tiles_per_image;
-        c0 = (t - img * tiles_per_image) * 2 * K::G + (half_idx & 1) * K::G;
+        c0 = (t - img * tiles_per_image) * 2 * K::G + half_sub * K::G;
         return true;
     };
 

@@ -90,6 +90,7 @@ struct ssw_ctx {
     int row_pipe = 1;                      // SSW_ROW_PIPE: 0 RowFwd / RowInv (one CTA per tile); 1 persistent bulk-copy pipelines (dct_pipe.cuh)
     int collect_occ = 0;                   // resident CTAs per SM of topk_collect (queried once)
     struct { const unsigned* img = nullptr; int shift = 0; float gain = 1.f; bool used = false; } row_cut;   // see launch_row_pipe
+    int hist_relief = 1;                   // SSW_HIST_RELIEF=0: the CTAs of the forward column pipeline that build the histogram keep all their tiles
     int partial_inv = 1;                   // SSW_PARTIAL_INV=0: the fused embed sends every column back through the inverse column pass
     int row_inplace = 0;                   // SSW_ROW_INPLACE=1: inverse row pipeline with the in-place pre pass (RowPipeCfg::InvP: a third CTA per SM for 3840 / 1920-point rows)
     int col_pipe = 1;                      // SSW_COL_PIPE: 0 ColPass (one CTA per tile); 1..3 persistent TMA pipelines (dct_pipe.cuh):
@@ -254,6 +255,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_ROW_PIPE")) c->row_pipe = atoi(s);
     if (const char* s = getenv("SSW_ROW_INPLACE")) c->row_inplace = atoi(s);
     if (const char* s = getenv("SSW_PARTIAL_INV")) c->partial_inv = atoi(s);
+    if (const char* s = getenv("SSW_HIST_RELIEF")) c->hist_relief = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_SPLIT")) c->col_split = atoi(s) != 0;
@@ -879,6 +881,10 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
     if (K::HALF_OK && c->col_split && batch == 1 && rounds >= 1 && rem > 0 && 2 * rem <= (long long)grid && (w % (2 * K::G)) == 0) {
         a.full_tiles = (int)(rounds * grid);
         a.half_tiles = (int)(2 * rem);
+    }
+    if (K::HALF_OK && !K::INVERSE && a.ts.hist && batch == 1 && a.half_tiles > 0 && c->hist_relief) {
+        const long long nh = (a.hist_cols + 2 * K::G - 1) / (2 * K::G);
+        if (rounds >= 2 && 3 * nh <= (long long)grid - a.half_tiles) a.hist_relief = (int)nh;
     }
     if (!K::INVERSE && a.ts.hist && batch == 1 && a.half_tiles == 0) {
         // one frame: `rot` CTAs get one tile more than the others and finish last -- keep the histogram tiles off them
