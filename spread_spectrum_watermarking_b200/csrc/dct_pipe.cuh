@@ -57,6 +57,11 @@ struct PipeArgs {
     // total_tiles - full_tiles tiles are cut into half_tiles = 2 * (total_tiles - full_tiles) half tiles (G columns), one
     // for each of the first half_tiles CTAs, processed in a single round.  One 4K frame is 480 tiles on 148 CTAs: 3 rounds
     // of whole tiles + 72 half tiles instead of a fourth round that keeps 36 SMs busy and 112 idle.
+    // forward pass: tile_max[image * tiles_per_image + tile] = bits of the largest |coefficient| of the tile (atomicMax of
+    // non-negative floats; zero between calls: the consumer, topk_collect_tiles, clears what it reads).  The candidate scan of
+    // the ordering then reads only the tiles that can hold a candidate -- for natural frames the 16 tiles of the low-frequency
+    // block instead of the whole plane.  nullptr: not wanted.
+    unsigned* tile_max;
     int full_tiles, half_tiles;
     // forward pass of one frame with the histogram: the first hist_relief CTAs own the histogram tiles (~5-9 us of extra work
     // each, the last of them also the search) -- each gives its last whole tile away as two half tiles (see the kernel)
@@ -98,6 +103,7 @@ struct ColPipe {
     static constexpr int TW_BYTES = ((P_::TW_TOTAL * 8 + 15) / 16) * 16;
     static constexpr int T4_BYTES = (((N / 2 + 1) * 8 + 15) / 16) * 16;
     static constexpr int BAR_BYTES = 64;
+    static constexpr int SMAX_OFF = 48;   // word behind the five mbarriers: running maximum of the tile (TRACK)
     static constexpr int BASE_BYTES = 2 * BUF_BYTES + FFT_BYTES + BAR_BYTES;
     static constexpr int MINB = MINB_;
     static constexpr int LIMIT = (228 * 1024) / MINB_ - 1024;   // 1 KB per resident CTA is reserved by the system
@@ -119,6 +125,10 @@ struct ColPipe {
     // and spill as soon as the kernel grows (measured: 1080-point fwd_cols 242 -> 317 us per 64-frame launch).
     static constexpr bool HALF_OK = (G_ == 4 && (TEAMS_ == 2 || TEAMS_ == 4) && MINB_ == 1) && ((RB_HALF * ROWB / 2) % 128 == 0) && ((RB_FULL * ROWB / 2) % 128 == 0);
     static constexpr bool COLLECT_OK = (TEAMS_ == 2 && MINB_ == 1);
+    // per-tile coefficient maxima for the tile-wise candidate scan (PipeArgs::tile_max): the shape of the batched launches only
+    // (4 teams, two CTAs per SM) -- there the scan of the whole plane is 10 % of the step; on single frames the ~3 % the
+    // bookkeeping costs the post pass outweigh the shorter scan (measured)
+    static constexpr bool TRACK = (G_ == 4 && TEAMS_ == 4 && MINB_ == 2 && !INVERSE_);
     // 2 teams read and write HALF rows of the tile buffer per round (line pairs {0,1} or {2,3} of the four in a 32-byte row):
     // rows r and r+4 would meet on the same banks (2-way conflicts, measured 21 % of the wavefronts).  The tensor maps of
     // whole tiles therefore use the 32-byte swizzle (16-byte half of a row ^= bit 2 of the row index): lanes that walk
@@ -175,7 +185,9 @@ struct ColPipe {
 
     // forward last phase: post pass -> coefficient rows (natural order) in the slots of this round's pairs
     template <int GG>
-    static SSW_HD void fwd_post(cplx* buf, const cplx* fft, const cplx* t4, int rd, int c, float scale0, float scalen) {
+    // TRACK: the largest |coefficient| written by this call is folded into the shared-memory word *smax (bits of a non-negative float)
+    static SSW_HD void fwd_post(cplx* buf, const cplx* fft, const cplx* t4, int rd, int c, float scale0, float scalen, unsigned* smax) {
+        float mx = 0.f;
         constexpr int TT = GG < TEAMS ? GG : TEAMS;   // line pairs in flight per round
 #pragma unroll 2
         for (int e = c; e < (N / 2 + 1) * TT; e += NC) {
@@ -186,9 +198,24 @@ struct ColPipe {
             dct2_post(s[P::idx(k)], s[P::idx(kr)], t4[k], xa, xb, ya, yb);
             const float sk = k ? scalen : scale0;
             const int q = rd * TT + qq;
-            buf[k * GG + sw<GG>(k, q)] = cmul_lanes(mk(xa, xb), sk, sk);
-            if (k && kr != k) buf[kr * GG + sw<GG>(kr, q)] = cmul_lanes(mk(ya, yb), scalen, scalen);
+            const cplx ck = cmul_lanes(mk(xa, xb), sk, sk);
+            buf[k * GG + sw<GG>(k, q)] = ck;
+            if constexpr (TRACK) mx = fmaxf(mx, fmaxf(fabsf(ck.x), fabsf(ck.y)));
+            if (k && kr != k) {
+                const cplx cr = cmul_lanes(mk(ya, yb), scalen, scalen);
+                buf[kr * GG + sw<GG>(kr, q)] = cr;
+                if constexpr (TRACK) mx = fmaxf(mx, fmaxf(fabsf(cr.x), fabsf(cr.y)));
+            }
         }
+        if constexpr (TRACK) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));   // (whole warps run the post pass)
+            if ((c & 31) == 0) atomicMax(smax, __float_as_uint(mx));
+#else
+            unsigned b; std::memcpy(&b, &mx, 4); if (b > *smax) *smax = b;
+#endif
+        } else { (void)mx; (void)smax; }
     }
 
     // inverse phase 0: pre pass, coefficient rows of this round's pairs -> FFT buffers
@@ -232,7 +259,8 @@ struct ColPipe {
         cplx* s = fft + g * PITCH;
         if constexpr (!INVERSE) {
             if constexpr (PH == 0) fwd_stage0<GG>(buf, fft, rd, c);
-            else if constexpr (PH == NPH_FWD - 1) fwd_post<GG>(buf, fft, t4, rd, c, a.scale0, a.scalen);
+            else if constexpr (PH == NPH_FWD - 1)
+                fwd_post<GG>(buf, fft, t4, rd, c, a.scale0, a.scalen, TRACK ? (unsigned*)((unsigned char*)fft + (OFF_BAR - OFF_FFT) + SMAX_OFF) : nullptr);
             else { if (GG >= TEAMS || g < GG) fft_phase<P, PH + 2, TW_SMEM>(s, tw, t, th.v); }   // PH 1 -> fft_phase 3 (load of stage 1), ...
         } else {
             if constexpr (PH == 0) inv_pre<GG>(buf, fft, t4, rd, c);
@@ -542,6 +570,7 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
         mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1);
         mbar_init(bar_ready0, 1); mbar_init(bar_ready0 + 8, 1);
         mbar_init(bar_tab, 1);
+        if constexpr (K::TRACK) *(unsigned*)(pipe_smem + K::OFF_BAR + K::SMAX_OFF) = 0u;
         fence_mbar_init();
     }
     if (tid == 0) trace_begin(a.trace);
@@ -790,6 +819,13 @@ col_pipe_kernel(const __grid_constant__ PipeArgs a, const __grid_constant__ TmaM
         fence_proxy_async();                                   // generic-proxy writes of BUF[b] -> visible to the TMA store
         named_sync(1, NC);                                     // (also: FFT buffers free for the next tile, candidates read)
         if (tid == 0) { trace_tile(a.trace, j, 2); mbar_arrive(bar_ready0 + 8 * b); }
+        if constexpr (K::TRACK) {
+            if (tid == 0) {                                    // every post pass of the tile has folded its maximum into the word
+                unsigned* smax = (unsigned*)(pipe_smem + K::OFF_BAR + K::SMAX_OFF);
+                if (a.tile_max) atomicMax(a.tile_max + (size_t)img * a.tiles_per_image + c0 / (2 * K::G), *smax);
+                *smax = 0u;                                    // (the next tile's post pass is several barriers away)
+            }
+        }
     }
     if (tid == 0) trace_end(a.trace);
 }

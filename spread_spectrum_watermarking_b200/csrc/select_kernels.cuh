@@ -56,6 +56,8 @@ struct TopkScratch {
     unsigned* maxcol;      // [1] largest column index of a coefficient modified by the embedding of this launch (TopkApply mode 1 with
                            //     width set): cleared by topk_collect, read by the partial inverse column pass (dct_pipe.cuh, PipeArgs::col_limit)
     unsigned* maxcol_img;  // [batch] the same per image: what an image gets back from the partial inverse depends on the image alone
+    unsigned* tile_max;    // [batch][tile_count] per-tile coefficient maxima consumed by topk_collect_tiles; topk_rank clears them
+    unsigned tile_count;
     unsigned* maxrow;      // [batch] largest coefficient row among the first k ordered indices (low-rank embed inverse);
                            // zeroed by topk_collect, 0xFFFFFFFF = the ordering of this frame failed
 };
@@ -333,6 +335,69 @@ topk_collect_kernel(const float* __restrict__ planes, long long plane_stride, un
     }
 }
 
+// ---- 2''. collect candidates, tile by tile -----------------------------------------------------------
+// The forward column pipeline leaves the largest |coefficient| of every column tile (dct_pipe.cuh, PipeArgs::tile_max;
+// tile = tile_cols adjacent columns x all rows).  fl(c*c) is monotone in |c|, so a tile whose maximum fails the test
+// "c*c >= thr" of topk_collect holds no candidate and is not read: for natural frames the scan shrinks from the whole plane to
+// the tiles of the low-frequency block.  One CTA per tile; Energy ordering of an unsharded plane only (the caller checks).
+// The CTA clears the word it consumed, which keeps the array zero between calls.
+constexpr int kTileSplit = 8;     // CTAs per image (row ranges)
+constexpr int kTileMaxTiles = 2048;   // column tiles per image the kernel can list (shared memory); wider frames take topk_collect
+__global__ void __launch_bounds__(256)
+topk_collect_tiles_kernel(const float* __restrict__ planes, long long plane_stride, unsigned w, unsigned h, unsigned tile_cols, unsigned tiles,
+                          TopkScratch ts, const unsigned* __restrict__ tile_max) {
+    pdl_enter();
+    __shared__ unsigned short live[kTileMaxTiles];
+    __shared__ unsigned n_live;
+    const unsigned img = blockIdx.y, tid = threadIdx.x;
+    const float* plane = planes + (long long)img * plane_stride;
+    const unsigned bin_sel = ts.sel_bin[img];
+    if (blockIdx.x == 0 && tid == 0) {
+        if (ts.maxrow) ts.maxrow[img] = 0u;
+        if (ts.maxcol) { ts.maxcol_img[img] = 0u; if (blockIdx.y == 0) *ts.maxcol = 0u; }
+    }
+    if (tid == 0) n_live = 0u;
+    __syncthreads();
+    const float thr = bin_sel > (1u << (kHistBits - 1)) ? __uint_as_float((bin_sel - (1u << (kHistBits - 1))) << (32 - kHistBits)) : 0.f;
+    // the tiles that can hold a candidate (a NaN threshold or maximum fails the comparison: the tile is read); any order will do
+    for (unsigned t = tid; t < tiles; t += blockDim.x) {
+        const float m = __uint_as_float(__ldcg(tile_max + (size_t)img * tiles + t));
+        if (!(__fmul_rn(m, m) < thr)) live[atomicAdd(&n_live, 1u)] = (unsigned short)t;
+    }
+    __syncthreads();
+    const unsigned nl = n_live;
+    unsigned* count = ts.cand_count + img;
+    unsigned long long* cand = ts.cand + (size_t)img * kTopkCap;
+    const unsigned q4 = tile_cols >> 2;   // 16-byte groups per row of a tile (w % 4 == 0, plane 16-byte aligned)
+    const unsigned rows = (h + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * rows, r1 = min(h, r0 + rows);
+    const unsigned per_tile = (r1 > r0 ? r1 - r0 : 0u) * q4, total = per_tile * nl;
+    constexpr int U = 4;   // independent loads in flight per thread
+    for (unsigned i0 = tid; i0 < total; i0 += U * blockDim.x) {
+        float4 v[U];
+        unsigned p[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned i = i0 + u * blockDim.x;
+            bool ok = i < total;
+            unsigned pos = 0xFFFFFFFFu;
+            if (ok) {
+                const unsigned li = i / per_tile, e = i - li * per_tile;
+                const unsigned r = r0 + e / q4, c = (unsigned)live[li] * tile_cols + 4u * (e % q4);
+                ok = c < w;
+                if (ok) pos = r * w + c;
+            }
+            p[u] = pos;
+            v[u] = ok ? __ldg((const float4*)(plane + pos)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool lo = (__fmul_rn(v[u].x, v[u].x) < thr) & (__fmul_rn(v[u].y, v[u].y) < thr) & (__fmul_rn(v[u].z, v[u].z) < thr) &
+                            (__fmul_rn(v[u].w, v[u].w) < thr);
+            if (!lo && p[u] != 0xFFFFFFFFu) topk_push4_energy(v[u], p[u], bin_sel, count, cand);
+        }
+    }
+}
+
 // ---- 2'. distributed merge: concatenate the candidate lists gathered from all ranks --------------
 __global__ void __launch_bounds__(256)
 topk_concat_kernel(const unsigned long long* __restrict__ lists, const unsigned* __restrict__ counts, unsigned n_lists,
@@ -419,6 +484,8 @@ topk_rank_kernel(TopkScratch ts, unsigned k, unsigned* __restrict__ idx_out, lon
     const float* dplane = ap.derived ? ap.derived + (long long)img * ap.plane_stride : nullptr;
     const float* mk = ap.marks ? ap.marks + (long long)img * ap.mark_stride : nullptr;
     float* ext = ap.out ? ap.out + (long long)img * ap.out_stride : nullptr;
+    if (ts.tile_max && blockIdx.x == gridDim.x - 1)   // (a CTA that rarely has candidates to rank)
+        for (unsigned i = tid; i < ts.tile_count; i += kRankThreads) ts.tile_max[(size_t)img * ts.tile_count + i] = 0u;
     if (bad) {
         for (unsigned r = blockIdx.x * kRankThreads + tid; r < k; r += gridDim.x * kRankThreads) {
             out[r] = kBadIndex;

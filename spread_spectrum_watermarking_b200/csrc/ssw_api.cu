@@ -90,6 +90,9 @@ struct ssw_ctx {
     int row_pipe = 1;                      // SSW_ROW_PIPE: 0 RowFwd / RowInv (one CTA per tile); 1 persistent bulk-copy pipelines (dct_pipe.cuh)
     int collect_occ = 0;                   // resident CTAs per SM of topk_collect (queried once)
     struct { const unsigned* img = nullptr; int shift = 0; float gain = 1.f; bool used = false; } row_cut;   // see launch_row_pipe
+    // per-tile coefficient maxima of the forward column pipeline (PipeArgs::tile_max) for the tile-wise candidate scan:
+    // want = the next forward column pass should produce them; tiles / cols = what the last one produced (0 = nothing)
+    struct { int on = 1; bool want = false; unsigned* buf = nullptr; size_t cap = 0; unsigned tiles = 0, cols = 0; const float* plane = nullptr; } tile_max;   // SSW_TILE_MAX=0 disables
     int hist_relief = 1;                   // SSW_HIST_RELIEF=0: the CTAs of the forward column pipeline that build the histogram keep all their tiles
     int partial_inv = 1;                   // SSW_PARTIAL_INV=0: the fused embed sends every column back through the inverse column pass
     int row_inplace = 0;                   // SSW_ROW_INPLACE=1: inverse row pipeline with the in-place pre pass (RowPipeCfg::InvP: a third CTA per SM for 3840 / 1920-point rows)
@@ -256,6 +259,7 @@ extern "C" int ssw_ctx_create_on_stream(int device, void* stream, ssw_ctx** out)
     if (const char* s = getenv("SSW_ROW_INPLACE")) c->row_inplace = atoi(s);
     if (const char* s = getenv("SSW_PARTIAL_INV")) c->partial_inv = atoi(s);
     if (const char* s = getenv("SSW_HIST_RELIEF")) c->hist_relief = atoi(s);
+    if (const char* s = getenv("SSW_TILE_MAX")) c->tile_max.on = atoi(s);
     if (const char* s = getenv("SSW_SIM_EXACT")) c->sim_exact = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_HIST")) c->col_hist_on = atoi(s) != 0;
     if (const char* s = getenv("SSW_COL_SPLIT")) c->col_split = atoi(s) != 0;
@@ -271,6 +275,7 @@ extern "C" int ssw_ctx_create(int device, ssw_ctx** out) { return ssw_ctx_create
 static void topk_scratch_free(ssw_ctx* c) {
     if (!c->ts_batch) return;
     cudaFree(c->ts.hist); cudaFree(c->ts.ticket); cudaFree(c->ts.sel_bin);
+    cudaFree(c->tile_max.buf); c->tile_max.buf = nullptr; c->tile_max.cap = 0;
     cudaFree(c->ts.cand_count); cudaFree(c->ts.cand); cudaFree(c->ts.overflow); cudaFree(c->ts.maxrow); cudaFree(c->ts.maxcol);
     c->ts = TopkScratch{};
     c->ts_batch = 0;
@@ -857,6 +862,19 @@ static int launch_col_pipe(ssw_ctx* c, const char* name, int w, int h, int batch
         omaps2 = omaps;
         if (K::HALF_OK) CKS(tma_maps_for(c, d_out, w, h, batch, K::G / 2, K::RB_HALF, K::RB_FULL, false, &omaps2));
     }
+    if (!K::INVERSE && K::TRACK && c->tile_max.want && c->tile_max.on) {
+        const size_t need = (size_t)tiles;
+        if (need > c->tile_max.cap) {
+            CK(cudaStreamSynchronize(c->stream));
+            cudaFree(c->tile_max.buf); c->tile_max.buf = nullptr; c->tile_max.cap = 0;
+            CK(cudaMalloc(&c->tile_max.buf, need * sizeof(unsigned)));
+            CK(cudaMemset(c->tile_max.buf, 0, need * sizeof(unsigned)));
+            c->tile_max.cap = need;
+        }
+        a.tile_max = c->tile_max.buf;
+        c->tile_max.tiles = (unsigned)a.tiles_per_image; c->tile_max.cols = 2 * K::G;
+        c->tile_max.plane = (d_out && d_out != d_plane) ? d_out : d_plane;   // the coefficient planes the maxima describe
+    }
     a.col_limit = K::INVERSE ? col_limit : nullptr;
     a.col_limit_img = a.col_limit ? col_limit + 1 : nullptr;   // (TopkScratch::maxcol layout: [0] the launch, [1 + i] image i)
     const fast::TmaMap& m_s = K::INVERSE ? omaps->first : maps->first;      // sample side: loaded by the forward pass, stored by the inverse
@@ -1187,6 +1205,8 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
     const unsigned cblocks = std::max(1u, (unsigned)std::min<size_t>(((size_t)n / 4 + 511) / 512, (size_t)std::max(1u, wave / std::min(batch, wave))));
     // hist_ready: the forward column pipeline has already left the selection bin of the low-frequency block in ts.sel_bin
     if (full_hist && hist_ready) return fail(SSW_ERR_STATE, "selection bin requested from both the block and the full plane");
+    unsigned* rank_tile_max = nullptr;   // tile maxima consumed by the tile-wise scan: the ranking kernel clears them
+    unsigned rank_tile_count = 0;
     for (unsigned b0 = 0; b0 < batch; b0 += 65535) {
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
@@ -1199,11 +1219,20 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
             KScope ks(c, "topk_block_bin");
             launch_pdl(c, topk_block_bin_kernel, dim3(nb), kBinThreads, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h, k, oc, ts);
         }
-        if (hist_ready < 2) {   // 2: the forward column pipeline has appended the candidates as well (PipeArgs::collect)
+        const bool by_tiles = !full_hist && c->tile_max.tiles && c->tile_max.tiles <= (unsigned)kTileMaxTiles && c->tile_max.buf && c->tile_max.plane == d_planes && ordering == 0 && batch <= 65535u && (w % 4) == 0 &&
+                              aligned(d_planes, 16) && (size_t)c->tile_max.tiles * batch <= c->tile_max.cap;
+        if (hist_ready < 2 && by_tiles) {
+            // the forward column pipeline left the largest |coefficient| of every column tile: only tiles that can hold a candidate are read
+            KScope ks(c, "topk_collect_tiles");
+            launch_pdl(c, topk_collect_tiles_kernel, dim3(kTileSplit, nb), 256, 0, c->stream, d_planes + (size_t)b0 * n, stride, (unsigned)w, (unsigned)h,
+                       c->tile_max.cols, c->tile_max.tiles, ts, (const unsigned*)(c->tile_max.buf + (size_t)b0 * c->tile_max.tiles));
+            rank_tile_max = c->tile_max.buf + (size_t)b0 * c->tile_max.tiles; rank_tile_count = c->tile_max.tiles;
+        } else if (hist_ready < 2) {   // 2: the forward column pipeline has appended the candidates as well (PipeArgs::collect)
             KScope ks(c, "topk_collect"); launch_pdl(c, topk_collect_kernel, dim3(cblocks, nb), 512, 0, c->stream, d_planes + (size_t)b0 * n, stride, n, oc, ts);
         }
         CK(cudaGetLastError());
     }
+    c->tile_max.tiles = 0;   // (consumed, or not applicable: the next forward pass has to produce them again)
     if (join_before_apply) CK(cudaStreamWaitEvent(c->stream, join_before_apply, 0));   // extract: the derived planes
     const void* key = (const void*)topk_rank_kernel;
     const int smem = kTopkCap * (int)sizeof(unsigned long long);
@@ -1215,6 +1244,7 @@ static int run_topk_fast(ssw_ctx* c, const float* d_planes, int w, int h, unsign
         const unsigned nb = std::min(65535u, batch - b0);
         TopkScratch ts = c->ts;
         ts.hist += (size_t)b0 * kHistBins; ts.ticket += b0; ts.sel_bin += b0; ts.cand_count += b0; ts.cand += (size_t)b0 * kTopkCap; ts.maxrow += b0; ts.maxcol_img += b0;
+        ts.tile_max = rank_tile_max; ts.tile_count = rank_tile_count;   // (set only by the single-launch tile-wise scan above)
         TopkApply a;
         std::memset(&a, 0, sizeof(a));
         if (ap) {
@@ -1876,6 +1906,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
         // was measured slower than the separate topk_block_bin kernel, whose cost is shared by the whole batch)
         c->col_hist.want = k > 0 && !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = c->col_hist.collected = false;
         c->col_hist.k = (unsigned)k; c->col_hist.ordering = cfg->ordering;
+        c->tile_max.want = k > 0 && cfg->ordering == 0 && !c->topk_full_hist; c->tile_max.tiles = 0;
         if (partial) {
             rc = run_rows_forward(c, PIX_RGB8, src, w, h, nb, d_rows, 1.f, 1.f);
             bool done = false;
@@ -1885,7 +1916,7 @@ extern "C" int ssw_embed_batch_rgb8_dev(ssw_ctx* c, const uint8_t* rgb, uint32_t
             rc = run_forward(c, PIX_RGB8, src, w, h, nb, d_planes, SSW_DCT2);
         }
         const int hist_ready = c->col_hist.done ? (c->col_hist.collected ? 2 : 1) : 0;
-        c->col_hist.want = false;
+        c->col_hist.want = false; c->tile_max.want = false;
         const bool lowrank = c->lowrank && k > 0 && (w % 4u) == 0 && w <= 65535u && h <= 65535u && aligned(src, 4) && aligned(out_rgb, 4) &&
                              ((np * 3) % 4) == 0;
         if (rc == SSW_OK && k) {
@@ -1988,8 +2019,9 @@ extern "C" int ssw_extract_batch_rgb8_dev(ssw_ctx* c, const uint8_t* base_rgb, c
         auto base_forward = [&]() -> int {
             c->col_hist.want = !c->topk_full_hist && c->col_hist_on && nb <= 4; c->col_hist.done = c->col_hist.collected = false;
             c->col_hist.k = (unsigned)n; c->col_hist.ordering = cfg->ordering;
+            c->tile_max.want = cfg->ordering == 0 && !c->topk_full_hist; c->tile_max.tiles = 0;
             const int r = run_forward(c, PIX_RGB8, base_rgb + (size_t)b0 * np * 3, w, h, nb, pb, SSW_DCT2);
-            c->col_hist.want = false;
+            c->col_hist.want = false; c->tile_max.want = false;
             return r;
         };
         int hist_ready = 0;
